@@ -1,0 +1,496 @@
+// rtb_api.cu — the C ABI of include/rtb200.h: context, device buffers, uploads, pass dispatch, read-back.
+// This layer is what replaces ignis (GPUBuffer / Texture / Descriptors / Pipeline / CommandList) under the
+// reference's render tasks.  No CPU fallback exists: without a usable CUDA device every call fails.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rtb200.h"
+#include "rtb_bvh.h"
+#include "rtb_kernels.cuh"
+
+using namespace rtb;
+
+namespace {
+std::string g_createError;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t count = 0;
+    cudaError_t alloc(size_t n) {
+        if (n <= count && p) return cudaSuccess;
+        release();
+        const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), (n ? n : 1) * sizeof(T));
+        if (e == cudaSuccess) count = n ? n : 1; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; count = 0; }
+    size_t bytes() const { return count * sizeof(T); }
+};
+}  // namespace
+
+struct rtb_ctx {
+    int device = 0;
+    rtb_limits limits{};
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    std::string error;
+
+    // host mirrors of the small uniform buffers
+    CameraRec camera{}; bool cameraSet = false;
+    SceneInfoRec info{};
+    uint32_t shadowSamplesProp = 1;
+
+    // scene buffers (device)
+    DevBuf<TriangleRec> triangles; DevBuf<float4> spheres; DevBuf<float> cubes; DevBuf<float4> planes;
+    DevBuf<LightRec> lights; DevBuf<MaterialRec> materials; DevBuf<uint32_t> materialIndices;
+    DevBuf<uint2> skybox; uint32_t skyW = 0, skyH = 0;
+    DevBuf<SeedRec> seed;
+    std::vector<uint8_t> triangleMirror;   // host copy of the triangle buffer: the BVH is built on the host
+
+    // acceleration structure
+    DevBuf<BvhNode> nodes; DevBuf<TravTri> travTris;
+    uint32_t nodeCount = 0; rtb_accel_mode accelMode = RTB_ACCEL_BRUTE; bool accelValid = false;
+    BvhStats stats;
+
+    // frame resources
+    uint32_t width = 0, height = 0, samples = 0;
+    FrameMap fm{};
+    uint32_t tileRank = 0, tileCount = 1;
+    DevBuf<float4> dirT, uvN, accum; DevBuf<uint2> lighting; DevBuf<uint32_t> bits, rgba8, rgba8Tiled;
+    DevBuf<RayRec> rays; DevBuf<TriHit> hits;
+    DevBuf<uint32_t> workCounter;
+    DevBuf<TraceCounters> counters;   // [0] primary, [1] shadow
+    bool countersOn = false;
+
+    // rays-in scratch
+    DevBuf<RayRec> rinRays; DevBuf<TriHit> rinHits; DevBuf<uint32_t> rinObj; DevBuf<float> rinT; DevBuf<float2> rinUv; DevBuf<uint8_t> rinOcc, rinOcc2;
+
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool frameTimed = false;
+};
+
+namespace {
+
+int fail(rtb_ctx* c, rtb_status st, const std::string& msg) { if (c) c->error = msg; else g_createError = msg; return st; }
+int cudaFail(rtb_ctx* c, cudaError_t e, const char* what) { return fail(c, RTB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
+
+#define RTB_CUDA(c, call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return cudaFail((c), e_, #call); } while (0)
+#define RTB_BIND(c) do { const cudaError_t e_ = cudaSetDevice((c)->device); if (e_ != cudaSuccess) return cudaFail((c), e_, "cudaSetDevice"); } while (0)
+
+SceneView sceneView(const rtb_ctx* c) {
+    SceneView v{};
+    v.triangles = c->triangles.p; v.spheres = c->spheres.p; v.cubes = c->cubes.p; v.planes = c->planes.p;
+    v.lights = c->lights.p; v.materials = c->materials.p; v.materialIndices = c->materialIndices.p;
+    v.skybox = c->skyW ? c->skybox.p : nullptr; v.skyW = c->skyW; v.skyH = c->skyH;
+    v.info = c->info;
+    v.nodes = c->nodes.p; v.travTris = c->travTris.p; v.nodeCount = c->nodeCount;
+    v.useBvh = (c->accelMode == RTB_ACCEL_BVH && c->accelValid) ? 1u : 0u;
+    return v;
+}
+
+void makeFrameMap(rtb_ctx* c) {
+    FrameMap& fm = c->fm;
+    fm.w = c->width; fm.h = c->height;
+    fm.blocksX = (c->width + 31) / 32; fm.blocksY = (c->height + 31) / 32;
+    fm.rank = c->tileRank; fm.nranks = c->tileCount;
+    const uint32_t total = fm.blocksX * fm.blocksY;
+    fm.localBlocks = total > fm.rank ? (total - fm.rank + fm.nranks - 1) / fm.nranks : 0;
+    fm.localSlots = fm.localBlocks * 1024u;
+}
+
+uint32_t shadowWords(uint32_t w, uint32_t h, uint32_t samples) { return ((w + 15) / 16) * ((h + 1) / 2) * samples; }
+
+int allocFrame(rtb_ctx* c) {
+    makeFrameMap(c);
+    const size_t px = (size_t)c->width * c->height;
+    RTB_CUDA(c, c->dirT.alloc(px)); RTB_CUDA(c, c->uvN.alloc(px)); RTB_CUDA(c, c->accum.alloc(px));
+    RTB_CUDA(c, c->lighting.alloc(px)); RTB_CUDA(c, c->rgba8.alloc(px));
+    RTB_CUDA(c, c->bits.alloc(shadowWords(c->width, c->height, c->samples)));
+    RTB_CUDA(c, c->rgba8Tiled.alloc(c->fm.localSlots));
+    RTB_CUDA(c, c->rays.alloc((size_t)c->fm.localSlots * (c->samples ? c->samples : 1)));
+    RTB_CUDA(c, c->hits.alloc(c->fm.localSlots));
+    // pixels owned by other ranks are never written: keep them defined
+    RTB_CUDA(c, cudaMemsetAsync(c->dirT.p, 0, c->dirT.bytes(), c->stream));
+    RTB_CUDA(c, cudaMemsetAsync(c->uvN.p, 0, c->uvN.bytes(), c->stream));
+    RTB_CUDA(c, cudaMemsetAsync(c->accum.p, 0, c->accum.bytes(), c->stream));
+    RTB_CUDA(c, cudaMemsetAsync(c->lighting.p, 0, c->lighting.bytes(), c->stream));
+    RTB_CUDA(c, cudaMemsetAsync(c->rgba8.p, 0, c->rgba8.bytes(), c->stream));
+    RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, c->bits.bytes(), c->stream));
+    return RTB_OK;
+}
+
+int checkReady(rtb_ctx* c) {
+    if (!c->width || !c->height) return fail(c, RTB_ERR_STATE, "rtb_dispatch before rtb_resize");
+    if (!c->cameraSet) return fail(c, RTB_ERR_STATE, "rtb_dispatch before the camera was uploaded");
+    if (c->camera.width != c->width || c->camera.height != c->height)
+        return fail(c, RTB_ERR_STATE, "camera.width/height differ from the size given to rtb_resize");
+    if (c->accelMode == RTB_ACCEL_BVH && !c->accelValid && c->info.triangleCount)
+        return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
+    if (c->info.triangleCount > c->limits.max_triangles || c->info.sphereCount > c->limits.max_spheres || c->info.cubeCount > c->limits.max_cubes ||
+        c->info.planeCount > c->limits.max_planes || c->info.lightCount > c->limits.max_lights || c->info.materialCount > c->limits.max_materials)
+        return fail(c, RTB_ERR_CAPACITY, "scene info counts exceed the capacities given to rtb_create");
+    return RTB_OK;
+}
+
+int passRaygen(rtb_ctx* c) {
+    const SceneView sv = sceneView(c);
+    launch_raygen(c->fm, &c->camera, c->seed.p, c->rays.p, c->stream);
+    launch_trace_closest(sv, c->rays.p, c->fm.localSlots, c->hits.p, c->workCounter.p, c->countersOn ? c->counters.p : nullptr, c->stream);
+    launch_finish_primary(c->fm, sv, c->rays.p, c->hits.p, c->dirT.p, c->uvN.p, c->stream);
+    return RTB_OK;
+}
+int passShadow(rtb_ctx* c) {
+    const SceneView sv = sceneView(c);
+    RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, c->samples) * 4, c->stream));
+    launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, c->stream);
+    launch_trace_any_bits(c->fm, sv, c->rays.p, c->fm.localSlots * c->samples, c->bits.p, c->workCounter.p, c->countersOn ? c->counters.p + 1 : nullptr, c->stream);
+    return RTB_OK;
+}
+int passShade(rtb_ctx* c, int what) {
+    const SceneView sv = sceneView(c);
+    launch_shade(what, c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->uvN.p, c->bits.p, c->lighting.p, c->accum.p,
+                 c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, c->stream);
+    return RTB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtb_create(rtb_ctx** out, int cudaDevice, const rtb_limits* limits) {
+    if (!out || !limits) return fail(nullptr, RTB_ERR_ARG, "rtb_create: null argument");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(nullptr, RTB_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (cudaDevice < 0 || cudaDevice >= n) return fail(nullptr, RTB_ERR_ARG, "rtb_create: device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cudaDevice)) != cudaSuccess) return cudaFail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10) return fail(nullptr, RTB_ERR_CUDA, "librtb200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    if ((e = cudaSetDevice(cudaDevice)) != cudaSuccess) return cudaFail(nullptr, e, "cudaSetDevice");
+    rtb_ctx* c = new rtb_ctx();
+    c->device = cudaDevice; c->limits = *limits;
+    auto bail = [&](cudaError_t err, const char* what) { const int rc = cudaFail(nullptr, err, what); rtb_destroy(c); return rc; };
+    if ((e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    c->stream = c->ownStream;
+    for (auto& ev : c->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = c->triangles.alloc(limits->max_triangles)) != cudaSuccess) return bail(e, "alloc triangles");
+    if ((e = c->spheres.alloc(limits->max_spheres)) != cudaSuccess) return bail(e, "alloc spheres");
+    if ((e = c->cubes.alloc((size_t)limits->max_cubes * 6)) != cudaSuccess) return bail(e, "alloc cubes");
+    if ((e = c->planes.alloc(limits->max_planes)) != cudaSuccess) return bail(e, "alloc planes");
+    if ((e = c->lights.alloc(limits->max_lights)) != cudaSuccess) return bail(e, "alloc lights");
+    if ((e = c->materials.alloc(limits->max_materials)) != cudaSuccess) return bail(e, "alloc materials");
+    const size_t objects = (size_t)limits->max_triangles + limits->max_spheres + limits->max_cubes + limits->max_planes;
+    if ((e = c->materialIndices.alloc(objects)) != cudaSuccess) return bail(e, "alloc materialIndices");
+    if ((e = c->seed.alloc(1)) != cudaSuccess) return bail(e, "alloc seed");
+    if ((e = c->workCounter.alloc(1)) != cudaSuccess) return bail(e, "alloc workCounter");
+    if ((e = c->counters.alloc(2)) != cudaSuccess) return bail(e, "alloc counters");
+    cudaMemset(c->lights.p, 0, c->lights.bytes());
+    cudaMemset(c->materials.p, 0, c->materials.bytes());
+    cudaMemset(c->materialIndices.p, 0, c->materialIndices.bytes());
+    cudaMemset(c->seed.p, 0, sizeof(SeedRec));
+    cudaMemset(c->counters.p, 0, 2 * sizeof(TraceCounters));
+    c->triangleMirror.resize((size_t)limits->max_triangles * sizeof(TriangleRec));
+    *out = c;
+    return RTB_OK;
+}
+
+void rtb_destroy(rtb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->triangles.release(); c->spheres.release(); c->cubes.release(); c->planes.release(); c->lights.release(); c->materials.release();
+    c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->travTris.release();
+    c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
+    c->rays.release(); c->hits.release(); c->workCounter.release(); c->counters.release();
+    c->rinRays.release(); c->rinHits.release(); c->rinObj.release(); c->rinT.release(); c->rinUv.release(); c->rinOcc.release(); c->rinOcc2.release();
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->ownStream) cudaStreamDestroy(c->ownStream);
+    delete c;
+}
+
+const char* rtb_last_error(const rtb_ctx* c) { return c ? c->error.c_str() : g_createError.c_str(); }
+
+int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
+    if (!c) return RTB_ERR_ARG;
+    switch (opt) {
+        case RTB_OPT_COUNTERS: c->countersOn = value != 0; return RTB_OK;
+        case RTB_OPT_TILE_RANK:
+            c->tileRank = value;
+            if (c->width) { RTB_BIND(c); return allocFrame(c); }
+            return RTB_OK;
+        case RTB_OPT_TILE_COUNT:
+            if (!value) return fail(c, RTB_ERR_ARG, "tile count must be >= 1");
+            c->tileCount = value;
+            if (c->width) { RTB_BIND(c); return allocFrame(c); }
+            return RTB_OK;
+        case RTB_OPT_SKIP_PARITY_STORES:
+            return value ? fail(c, RTB_ERR_ARG, "RTB_OPT_SKIP_PARITY_STORES is reserved") : RTB_OK;
+    }
+    return fail(c, RTB_ERR_ARG, "unknown option");
+}
+
+int rtb_set_stream(rtb_ctx* c, void* s) {
+    if (!c) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? static_cast<cudaStream_t>(s) : c->ownStream;
+    return RTB_OK;
+}
+
+int rtb_resize(rtb_ctx* c, uint32_t w, uint32_t h, uint32_t shadowSamples) {
+    if (!c) return RTB_ERR_ARG;
+    if (!w || !h || !shadowSamples || w > 32768 || h > 32768 || shadowSamples > 512) return fail(c, RTB_ERR_ARG, "rtb_resize: size or sample count out of range");
+    RTB_BIND(c);
+    if (w == c->width && h == c->height && shadowSamples == c->samples) return RTB_OK;
+    if ((uint64_t)((w + 31) / 32) * ((h + 31) / 32) * 1024ull * shadowSamples > 0xFFFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_resize: too many shadow rays per frame");
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->width = w; c->height = h; c->samples = shadowSamples; c->shadowSamplesProp = shadowSamples;
+    return allocFrame(c);
+}
+
+int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* src) {
+    if (!c || (!src && bytes)) return c ? fail(c, RTB_ERR_ARG, "rtb_upload: null source") : RTB_ERR_ARG;
+    RTB_BIND(c);
+    void* dst = nullptr; size_t cap = 0;
+    switch (id) {
+        case RTB_BUF_CAMERA:
+            if (off + bytes > sizeof(CameraRec)) return fail(c, RTB_ERR_CAPACITY, "camera upload past 144 bytes");
+            std::memcpy(reinterpret_cast<uint8_t*>(&c->camera) + off, src, bytes); c->cameraSet = true;
+            return RTB_OK;
+        case RTB_BUF_SCENE_INFO: {
+            if (off + bytes > sizeof(SceneInfoRec)) return fail(c, RTB_ERR_CAPACITY, "scene info upload past 36 bytes");
+            const uint32_t before = c->info.triangleCount;
+            std::memcpy(reinterpret_cast<uint8_t*>(&c->info) + off, src, bytes);
+            if (c->info.triangleCount != before) c->accelValid = false;
+            return RTB_OK;
+        }
+        case RTB_BUF_SHADOW_PROPS:
+            if (off + bytes > 4) return fail(c, RTB_ERR_CAPACITY, "shadow properties upload past 4 bytes");
+            std::memcpy(reinterpret_cast<uint8_t*>(&c->shadowSamplesProp) + off, src, bytes);
+            if (c->width && c->shadowSamplesProp != c->samples) return rtb_resize(c, c->width, c->height, c->shadowSamplesProp);
+            return RTB_OK;
+        case RTB_BUF_SEED: dst = c->seed.p; cap = sizeof(SeedRec); break;
+        case RTB_BUF_TRIANGLES: dst = c->triangles.p; cap = (size_t)c->limits.max_triangles * sizeof(TriangleRec); break;
+        case RTB_BUF_SPHERES: dst = c->spheres.p; cap = (size_t)c->limits.max_spheres * 16; break;
+        case RTB_BUF_CUBES: dst = c->cubes.p; cap = (size_t)c->limits.max_cubes * 24; break;
+        case RTB_BUF_PLANES: dst = c->planes.p; cap = (size_t)c->limits.max_planes * 16; break;
+        case RTB_BUF_LIGHTS: dst = c->lights.p; cap = (size_t)c->limits.max_lights * 32; break;
+        case RTB_BUF_MATERIALS: dst = c->materials.p; cap = (size_t)c->limits.max_materials * 32; break;
+        case RTB_BUF_MATERIAL_INDICES:
+            dst = c->materialIndices.p;
+            cap = ((size_t)c->limits.max_triangles + c->limits.max_spheres + c->limits.max_cubes + c->limits.max_planes) * 4;
+            break;
+        default: return fail(c, RTB_ERR_ARG, "rtb_upload: unknown buffer id");
+    }
+    if (off + bytes > cap) return fail(c, RTB_ERR_CAPACITY, "rtb_upload: range exceeds the capacity given to rtb_create");
+    if (!bytes) return RTB_OK;
+    if (id == RTB_BUF_TRIANGLES) { std::memcpy(c->triangleMirror.data() + off, src, bytes); c->accelValid = false; }
+    // pageable source: cudaMemcpyAsync stages it before returning, so the caller may reuse src at once (like GPUBuffer::flush)
+    RTB_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return RTB_OK;
+}
+
+int rtb_upload_skybox(rtb_ctx* c, uint32_t w, uint32_t h, const uint16_t* px) {
+    if (!c) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (!w || !h || !px) { c->skyW = c->skyH = 0; return RTB_OK; }
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RTB_CUDA(c, c->skybox.alloc((size_t)w * h));
+    RTB_CUDA(c, cudaMemcpyAsync(c->skybox.p, px, (size_t)w * h * 8, cudaMemcpyHostToDevice, c->stream));
+    c->skyW = w; c->skyH = h;
+    return RTB_OK;
+}
+
+int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
+    if (!c) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (mode != RTB_ACCEL_BRUTE && mode != RTB_ACCEL_BVH) return fail(c, RTB_ERR_ARG, "rtb_build_accel: unknown mode");
+    c->accelMode = mode;
+    c->stats = BvhStats();
+    c->nodeCount = 0;
+    if (mode == RTB_ACCEL_BRUTE) { c->accelValid = true; return RTB_OK; }
+    if (c->info.triangleCount > c->limits.max_triangles) return fail(c, RTB_ERR_CAPACITY, "triangleCount exceeds max_triangles");
+    std::vector<BvhNode> nodes; std::vector<TravTri> tt;
+    buildBvh(reinterpret_cast<const TriangleRec*>(c->triangleMirror.data()), c->info.triangleCount, 256, 0, nodes, tt, c->stats);
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RTB_CUDA(c, c->nodes.alloc(nodes.size()));
+    RTB_CUDA(c, c->travTris.alloc(tt.size()));
+    if (!nodes.empty()) RTB_CUDA(c, cudaMemcpy(c->nodes.p, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+    if (!tt.empty()) RTB_CUDA(c, cudaMemcpy(c->travTris.p, tt.data(), tt.size() * sizeof(TravTri), cudaMemcpyHostToDevice));
+    c->nodeCount = (uint32_t)nodes.size();
+    c->accelValid = true;
+    return RTB_OK;
+}
+
+int rtb_accel_info_get(const rtb_ctx* c, rtb_accel_info* out) {
+    if (!c || !out) return RTB_ERR_ARG;
+    out->mode = c->accelMode; out->node_count = c->nodeCount; out->node_bytes = sizeof(BvhNode); out->leaf_count = c->stats.leafCount;
+    out->max_depth = c->stats.maxDepth; out->tri_record_bytes = sizeof(TravTri); out->sah_cost = c->stats.sahCost; out->build_ms = c->stats.buildMs;
+    return RTB_OK;
+}
+
+int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
+    if (!c) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (pass != RTB_PASS_INIT) { const int rc = checkReady(c); if (rc) return rc; }
+    int rc = RTB_OK;
+    switch (pass) {
+        case RTB_PASS_INIT: launch_init(c->seed.p, c->stream); break;
+        case RTB_PASS_RAYGEN: rc = passRaygen(c); break;
+        case RTB_PASS_SHADOW: rc = passShadow(c); break;
+        case RTB_PASS_LIGHTING: rc = passShade(c, SHADE_LIGHTING); break;
+        case RTB_PASS_COMPOSITE: rc = passShade(c, SHADE_COMPOSITE); break;
+        case RTB_PASS_FRAME:
+            if (c->countersOn) RTB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(TraceCounters), c->stream));
+            RTB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+            launch_init(c->seed.p, c->stream);
+            RTB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+            if ((rc = passRaygen(c))) return rc;
+            RTB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+            if ((rc = passShadow(c))) return rc;
+            RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+            if ((rc = passShade(c, SHADE_BOTH))) return rc;
+            RTB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+            c->frameTimed = true;
+            break;
+        default: return fail(c, RTB_ERR_ARG, "rtb_dispatch: unknown pass");
+    }
+    if (rc) return rc;
+    RTB_CUDA(c, cudaGetLastError());
+    return RTB_OK;
+}
+
+int rtb_device_ptr(rtb_ctx* c, rtb_target t, void** out, size_t* bytes) {
+    if (!c || !out) return RTB_ERR_ARG;
+    const size_t px = (size_t)c->width * c->height;
+    void* p = nullptr; size_t n = 0;
+    switch (t) {
+        case RTB_TGT_DIR_T: p = c->dirT.p; n = px * 16; break;
+        case RTB_TGT_UV_NORMAL: p = c->uvN.p; n = px * 16; break;
+        case RTB_TGT_SHADOW_BITS: p = c->bits.p; n = (size_t)shadowWords(c->width, c->height, c->samples) * 4; break;
+        case RTB_TGT_LIGHTING: p = c->lighting.p; n = px * 8; break;
+        case RTB_TGT_ACCUM: p = c->accum.p; n = px * 16; break;
+        case RTB_TGT_RGBA8: p = c->rgba8.p; n = px * 4; break;
+        case RTB_TGT_SEED: p = c->seed.p; n = sizeof(SeedRec); break;
+        case RTB_TGT_RGBA8_TILED: p = c->rgba8Tiled.p; n = (size_t)c->fm.localSlots * 4; break;
+        default: return fail(c, RTB_ERR_ARG, "unknown target");
+    }
+    if (t != RTB_TGT_SEED && !px) return fail(c, RTB_ERR_STATE, "no frame resources before rtb_resize");
+    *out = p; if (bytes) *bytes = n;
+    return RTB_OK;
+}
+
+int rtb_readback(rtb_ctx* c, rtb_target t, void* dst, size_t bytes) {
+    if (!c || !dst) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    void* p; size_t n;
+    const int rc = rtb_device_ptr(c, t, &p, &n);
+    if (rc) return rc;
+    if (bytes > n) return fail(c, RTB_ERR_ARG, "rtb_readback: more bytes requested than the target holds");
+    RTB_CUDA(c, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_untile(rtb_ctx* c, const void* tiledAll, uint32_t nranks, uint32_t slotsPerRank, void* out) {
+    if (!c || !tiledAll || !nranks) return c ? fail(c, RTB_ERR_ARG, "rtb_untile: bad argument") : RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (!c->width) return fail(c, RTB_ERR_STATE, "rtb_untile before rtb_resize");
+    FrameMap fm = c->fm;
+    fm.nranks = nranks; fm.rank = 0;
+    const uint32_t total = fm.blocksX * fm.blocksY;
+    if ((uint64_t)((total + nranks - 1) / nranks) * 1024ull > slotsPerRank) return fail(c, RTB_ERR_ARG, "rtb_untile: slots_per_rank too small for this frame");
+    launch_untile(fm, static_cast<const uint32_t*>(tiledAll), slotsPerRank, out ? static_cast<uint32_t*>(out) : c->rgba8.p, c->stream);
+    RTB_CUDA(c, cudaGetLastError());
+    return RTB_OK;
+}
+
+int rtb_sync(rtb_ctx* c) {
+    if (!c) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_counters_get(rtb_ctx* c, rtb_counters* out) {
+    if (!c || !out) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    TraceCounters h[2];
+    RTB_CUDA(c, cudaMemcpyAsync(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->primary_rays = h[0].rays; out->primary_nodes = h[0].nodes; out->primary_tris = h[0].tris; out->primary_hits = h[0].hits;
+    out->shadow_rays = h[1].rays; out->shadow_nodes = h[1].nodes; out->shadow_tris = h[1].tris; out->shadow_occluded = h[1].hits;
+    return RTB_OK;
+}
+
+int rtb_last_frame_ms(rtb_ctx* c, float ms[5]) {
+    if (!c || !ms) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (!c->frameTimed) return fail(c, RTB_ERR_STATE, "no RTB_PASS_FRAME has been dispatched yet");
+    RTB_CUDA(c, cudaEventSynchronize(c->ev[4]));
+    for (int i = 0; i < 4; ++i) RTB_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    RTB_CUDA(c, cudaEventElapsedTime(&ms[4], c->ev[0], c->ev[4]));
+    return RTB_OK;
+}
+
+// ---- rays-in mode ---------------------------------------------------------------------------------------------
+static int stageRays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* prev, const float* maxDist) {
+    std::vector<RayRec> h((size_t)n);
+    for (size_t i = 0; i < (size_t)n; ++i) {
+        RayRec& r = h[i];
+        r.ox = rays[6 * i]; r.oy = rays[6 * i + 1]; r.oz = rays[6 * i + 2]; r.prev = prev ? prev[i] : NO_RAY_HIT;
+        r.dx = rays[6 * i + 3]; r.dy = rays[6 * i + 4]; r.dz = rays[6 * i + 5]; r.tmax = maxDist ? maxDist[i] : NO_HIT;
+    }
+    RTB_CUDA(c, c->rinRays.alloc((size_t)n));
+    RTB_CUDA(c, cudaMemcpyAsync(c->rinRays.p, h.data(), (size_t)n * sizeof(RayRec), cudaMemcpyHostToDevice, c->stream));
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_trace_rays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* prev, uint32_t* object, float* t, float* uv) {
+    if (!c || (!rays && n)) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (n > 0x7FFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_trace_rays: too many rays");
+    if (c->accelMode == RTB_ACCEL_BVH && !c->accelValid && c->info.triangleCount) return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
+    if (!n) return RTB_OK;
+    int rc = stageRays(c, rays, n, prev, nullptr);
+    if (rc) return rc;
+    RTB_CUDA(c, c->rinHits.alloc((size_t)n)); RTB_CUDA(c, c->rinObj.alloc((size_t)n)); RTB_CUDA(c, c->rinT.alloc((size_t)n)); RTB_CUDA(c, c->rinUv.alloc((size_t)n));
+    const SceneView sv = sceneView(c);
+    launch_trace_closest(sv, c->rinRays.p, (uint32_t)n, c->rinHits.p, c->workCounter.p, nullptr, c->stream);
+    launch_finish_rays(sv, c->rinRays.p, c->rinHits.p, (uint32_t)n, c->rinObj.p, c->rinT.p, c->rinUv.p, c->stream);
+    RTB_CUDA(c, cudaGetLastError());
+    if (object) RTB_CUDA(c, cudaMemcpyAsync(object, c->rinObj.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (t) RTB_CUDA(c, cudaMemcpyAsync(t, c->rinT.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (uv) RTB_CUDA(c, cudaMemcpyAsync(uv, c->rinUv.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_occlusion_rays(rtb_ctx* c, const float* rays, uint64_t n, const float* maxDist, const uint32_t* prev, uint8_t* occluded) {
+    if (!c || (!rays && n) || (!occluded && n)) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (n > 0x7FFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_occlusion_rays: too many rays");
+    if (c->accelMode == RTB_ACCEL_BVH && !c->accelValid && c->info.triangleCount) return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
+    if (!n) return RTB_OK;
+    int rc = stageRays(c, rays, n, prev, maxDist);
+    if (rc) return rc;
+    RTB_CUDA(c, c->rinOcc.alloc((size_t)n)); RTB_CUDA(c, c->rinOcc2.alloc((size_t)n));
+    const SceneView sv = sceneView(c);
+    launch_occlusion_others(sv, c->rinRays.p, (uint32_t)n, c->rinOcc.p, c->stream);
+    launch_trace_any_bytes(sv, c->rinRays.p, (uint32_t)n, c->rinOcc2.p, c->workCounter.p, c->stream);
+    RTB_CUDA(c, cudaGetLastError());
+    std::vector<uint8_t> a((size_t)n), b((size_t)n);
+    RTB_CUDA(c, cudaMemcpyAsync(a.data(), c->rinOcc.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(c, cudaMemcpyAsync(b.data(), c->rinOcc2.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < (size_t)n; ++i) occluded[i] = (a[i] | b[i]) ? 1 : 0;
+    return RTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+// rtb_bvh.cpp — multi-threaded binned-SAH BVH builder (host).  See rtb_bvh.h.
+#include "rtb_bvh.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <thread>
+
+namespace rtb {
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -std::numeric_limits<float>::infinity(); } }
+    void grow(const Box& b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    void grow(const float* p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    float area() const {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (!(dx >= 0.0f && dy >= 0.0f && dz >= 0.0f)) return 0.0f;
+        return 2.0f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct Prim { Box b; float c[3]; };
+
+// temporary node: links >= 0 index the owning vector, < 0 are leaf codes ~((first << 3) | (count - 1))
+struct TNode { Box b0, b1; int32_t c0, c1; };
+
+constexpr int BINS = 16;
+constexpr float C_TRAV = 1.0f;
+
+inline int32_t leafLink(uint32_t first, uint32_t count) { return (int32_t)~((first << 3) | (count - 1u)); }
+
+struct Split { int axis; int bin; float cost; Box left, right; uint32_t nLeft; float cbLo, scale; };
+
+struct Builder {
+    const Prim* prims;
+    uint32_t* idx;
+
+    Box boundsOf(uint32_t b, uint32_t e) const { Box r; r.reset(); for (uint32_t i = b; i < e; ++i) r.grow(prims[idx[i]].b); return r; }
+
+    // best binned split of [b, e); returns false when every centroid coincides
+    bool findSplit(uint32_t b, uint32_t e, Split& best) const {
+        Box cb; cb.reset();
+        for (uint32_t i = b; i < e; ++i) cb.grow(prims[idx[i]].c);
+        Box binBox[3][BINS]; uint32_t binCnt[3][BINS];
+        float scale[3];
+        bool any = false;
+        for (int a = 0; a < 3; ++a) {
+            const float ext = cb.hi[a] - cb.lo[a];
+            scale[a] = ext > 0.0f ? (float)BINS * (1.0f - 1e-6f) / ext : 0.0f;
+            any |= ext > 0.0f;
+            for (int k = 0; k < BINS; ++k) { binBox[a][k].reset(); binCnt[a][k] = 0; }
+        }
+        if (!any) return false;
+        for (uint32_t i = b; i < e; ++i) {
+            const Prim& p = prims[idx[i]];
+            for (int a = 0; a < 3; ++a) {
+                if (scale[a] == 0.0f) continue;
+                int k = (int)((p.c[a] - cb.lo[a]) * scale[a]);
+                k = k < 0 ? 0 : (k >= BINS ? BINS - 1 : k);
+                binBox[a][k].grow(p.b); binCnt[a][k]++;
+            }
+        }
+        best.cost = std::numeric_limits<float>::infinity();
+        for (int a = 0; a < 3; ++a) {
+            if (scale[a] == 0.0f) continue;
+            float rightArea[BINS]; uint32_t rightCnt[BINS]; Box rightBox[BINS];
+            Box acc; acc.reset(); uint32_t cnt = 0;
+            for (int k = BINS - 1; k > 0; --k) { acc.grow(binBox[a][k]); cnt += binCnt[a][k]; rightArea[k] = acc.area(); rightCnt[k] = cnt; rightBox[k] = acc; }
+            acc.reset(); cnt = 0;
+            for (int k = 1; k < BINS; ++k) {
+                acc.grow(binBox[a][k - 1]); cnt += binCnt[a][k - 1];
+                if (cnt == 0 || rightCnt[k] == 0) continue;
+                const float cost = acc.area() * (float)cnt + rightArea[k] * (float)rightCnt[k];
+                if (cost < best.cost) { best.cost = cost; best.axis = a; best.bin = k; best.left = acc; best.right = rightBox[k]; best.nLeft = cnt; best.cbLo = cb.lo[a]; best.scale = scale[a]; }
+            }
+        }
+        return best.cost < std::numeric_limits<float>::infinity();
+    }
+
+    // partitions [b, e) and returns the middle; boxes of the halves in lb, rb
+    uint32_t partition(uint32_t b, uint32_t e, uint32_t depth, const Box& box, Box& lb, Box& rb, bool& makeLeaf) const {
+        const uint32_t n = e - b;
+        makeLeaf = false;
+        Split s;
+        const bool forceMedian = depth >= 32;
+        if (!forceMedian && findSplit(b, e, s)) {
+            if (n <= BVH_MAX_LEAF) {
+                const float leafCost = (float)n * box.area();
+                if (leafCost <= C_TRAV * box.area() + s.cost) { makeLeaf = true; return b; }
+            }
+            const int axis = s.axis, bin = s.bin; const float lo = s.cbLo, sc = s.scale;
+            uint32_t* mid = std::partition(idx + b, idx + e, [&](uint32_t id) {
+                int k = (int)((prims[id].c[axis] - lo) * sc);
+                k = k < 0 ? 0 : (k >= BINS ? BINS - 1 : k);
+                return k < bin;
+            });
+            const uint32_t m = (uint32_t)(mid - idx);
+            if (m > b && m < e) { lb = s.left; rb = s.right; return m; }
+        }
+        if (n <= BVH_MAX_LEAF && !forceMedian) { makeLeaf = true; return b; }
+        if (n <= BVH_MAX_LEAF && forceMedian) { makeLeaf = true; return b; }
+        // object median along the widest axis of the box
+        int axis = 0;
+        for (int a = 1; a < 3; ++a) if (box.hi[a] - box.lo[a] > box.hi[axis] - box.lo[axis]) axis = a;
+        const uint32_t m = b + n / 2;
+        std::nth_element(idx + b, idx + m, idx + e, [&](uint32_t x, uint32_t y) { return prims[x].c[axis] < prims[y].c[axis]; });
+        lb = boundsOf(b, m); rb = boundsOf(m, e);
+        return m;
+    }
+
+    // recursive build of [b, e) into `out`; returns the link (leaf code or index into out)
+    int32_t build(uint32_t b, uint32_t e, uint32_t depth, const Box& box, std::vector<TNode>& out) const {
+        const uint32_t n = e - b;
+        if (n == 1) return leafLink(b, 1);
+        Box lb, rb; bool makeLeaf;
+        const uint32_t m = partition(b, e, depth, box, lb, rb, makeLeaf);
+        if (makeLeaf) return leafLink(b, n);
+        const int32_t self = (int32_t)out.size();
+        out.emplace_back();
+        const int32_t l = build(b, m, depth + 1, lb, out);
+        const int32_t r = build(m, e, depth + 1, rb, out);
+        TNode& t = out[(size_t)self];
+        t.b0 = lb; t.b1 = rb; t.c0 = l; t.c1 = r;
+        return self;
+    }
+};
+
+template <class F>
+void parallelFor(int threads, uint32_t n, uint32_t chunk, F&& body) {
+    if (threads <= 1 || n <= chunk) { body(0u, n); return; }
+    std::atomic<uint32_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t b = next.fetch_add(chunk);
+            if (b >= n) break;
+            body(b, std::min(n, b + chunk));
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+}
+
+}  // namespace
+
+void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int threads, std::vector<BvhNode>& nodes,
+              std::vector<TravTri>& travTris, BvhStats& stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    nodes.clear(); travTris.clear();
+    stats = BvhStats();
+    if (count == 0) return;
+    if (threads <= 0) { threads = (int)std::thread::hardware_concurrency(); if (threads <= 0) threads = 1; }
+
+    // ---- primitive boxes, padded -------------------------------------------------------------------------
+    float maxAbs = 0.0f;
+    for (uint32_t i = 0; i < count; ++i) {
+        const TriangleRec& t = tris[i];
+        for (int a = 0; a < 3; ++a) maxAbs = std::max(maxAbs, std::max(std::fabs(t.p0[a]), std::max(std::fabs(t.p1[a]), std::fabs(t.p2[a]))));
+    }
+    if (!(maxAbs < std::numeric_limits<float>::infinity())) maxAbs = 1.0f;
+    const float pad = std::max(maxAbs * 3.814697265625e-6f /* 2^-18 */, 1e-30f);
+    std::vector<Prim> prims(count);
+    std::vector<uint32_t> idx(count);
+    parallelFor(threads, count, 1u << 16, [&](uint32_t b, uint32_t e) {
+        for (uint32_t i = b; i < e; ++i) {
+            const TriangleRec& t = tris[i];
+            Prim& p = prims[i];
+            p.b.reset(); p.b.grow(t.p0); p.b.grow(t.p1); p.b.grow(t.p2);
+            for (int a = 0; a < 3; ++a) {
+                p.c[a] = 0.5f * (p.b.lo[a] + p.b.hi[a]);
+                p.b.lo[a] -= pad; p.b.hi[a] += pad;
+                if (!(p.b.lo[a] <= p.b.hi[a])) { p.b.lo[a] = -maxAbs - pad; p.b.hi[a] = maxAbs + pad; p.c[a] = 0.0f; }   // NaN vertex: keep it reachable
+            }
+            idx[i] = i;
+        }
+    });
+    Builder bl{prims.data(), idx.data()};
+
+    // ---- top of the tree, sequential: split the largest open range until there is enough parallel work -----
+    struct Open { uint32_t b, e, depth; Box box; int32_t parent; int side; };
+    std::vector<TNode> top;
+    std::vector<Open> open;
+    int32_t rootLink;
+    {
+        Box rootBox = bl.boundsOf(0, count);
+        open.push_back({0, count, 0, rootBox, -1, 0});
+    }
+    const size_t wantRanges = threads > 1 ? (size_t)threads * 8 : 1;
+    std::vector<Open> done;   // ranges that became leaves during the top phase
+    while (open.size() < wantRanges) {
+        size_t big = 0;
+        for (size_t i = 1; i < open.size(); ++i) if (open[i].e - open[i].b > open[big].e - open[big].b) big = i;
+        Open o = open[big];
+        if (o.e - o.b <= 4096) break;
+        Box lb, rb; bool makeLeaf;
+        const uint32_t m = bl.partition(o.b, o.e, o.depth, o.box, lb, rb, makeLeaf);
+        if (makeLeaf) break;   // cannot happen for > BVH_MAX_LEAF primitives
+        const int32_t self = (int32_t)top.size();
+        top.emplace_back();
+        top[(size_t)self].b0 = lb; top[(size_t)self].b1 = rb; top[(size_t)self].c0 = 0; top[(size_t)self].c1 = 0;
+        if (o.parent >= 0) (o.side ? top[(size_t)o.parent].c1 : top[(size_t)o.parent].c0) = self;
+        open[big] = {o.b, m, o.depth + 1, lb, self, 0};
+        open.push_back({m, o.e, o.depth + 1, rb, self, 1});
+    }
+
+    // ---- subtrees in parallel ---------------------------------------------------------------------------
+    std::vector<std::vector<TNode>> sub(open.size());
+    std::vector<int32_t> subRoot(open.size());
+    {
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= open.size()) break;
+                sub[i].reserve((open[i].e - open[i].b) / 2 + 4);
+                subRoot[i] = bl.build(open[i].b, open[i].e, open[i].depth, open[i].box, sub[i]);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads && (size_t)t < open.size(); ++t) pool.emplace_back(worker);
+        worker();
+        for (auto& t : pool) t.join();
+    }
+
+    // ---- merge into one temporary array -------------------------------------------------------------------
+    std::vector<TNode> all;
+    {
+        size_t total = top.size();
+        for (auto& s : sub) total += s.size();
+        all.reserve(total + 1);
+        all = top;
+        for (size_t i = 0; i < open.size(); ++i) {
+            const int32_t off = (int32_t)all.size();
+            for (TNode t : sub[i]) { if (t.c0 >= 0) t.c0 += off; if (t.c1 >= 0) t.c1 += off; all.push_back(t); }
+            const int32_t link = subRoot[i] >= 0 ? subRoot[i] + off : subRoot[i];
+            if (open[i].parent >= 0) (open[i].side ? all[(size_t)open[i].parent].c1 : all[(size_t)open[i].parent].c0) = link;
+            else rootLink = link;
+            std::vector<TNode>().swap(sub[i]);
+        }
+        if (open.size() > 1 || top.size() > 0) rootLink = 0;
+    }
+    // a scene that is a single leaf still gets an inner root: child 1 is an empty box no ray can enter
+    if (rootLink < 0) {
+        TNode r;
+        r.b0 = bl.boundsOf(0, count);
+        r.b1.reset();
+        r.c0 = rootLink; r.c1 = leafLink(0, 1);
+        all.clear(); all.push_back(r);
+        rootLink = 0;
+    }
+
+    // ---- final order: breadth-first prefix of `topNodes`, then depth-first --------------------------------
+    const size_t nNodes = all.size();
+    std::vector<int32_t> order; order.reserve(nNodes);          // temp index by final position
+    std::vector<int32_t> finalOf(nNodes, -1);
+    {
+        std::deque<int32_t> q; q.push_back(rootLink);
+        while (!q.empty() && order.size() < topNodes) {
+            const int32_t t = q.front(); q.pop_front();
+            finalOf[(size_t)t] = (int32_t)order.size(); order.push_back(t);
+            if (all[(size_t)t].c0 >= 0) q.push_back(all[(size_t)t].c0);
+            if (all[(size_t)t].c1 >= 0) q.push_back(all[(size_t)t].c1);
+        }
+        std::vector<int32_t> stack;
+        while (!q.empty()) {
+            stack.push_back(q.front()); q.pop_front();
+            while (!stack.empty()) {
+                const int32_t t = stack.back(); stack.pop_back();
+                finalOf[(size_t)t] = (int32_t)order.size(); order.push_back(t);
+                if (all[(size_t)t].c1 >= 0) stack.push_back(all[(size_t)t].c1);
+                if (all[(size_t)t].c0 >= 0) stack.push_back(all[(size_t)t].c0);
+            }
+        }
+    }
+    nodes.resize(order.size());
+    parallelFor(threads, (uint32_t)order.size(), 1u << 15, [&](uint32_t b, uint32_t e) {
+        for (uint32_t f = b; f < e; ++f) {
+            const TNode& t = all[(size_t)order[f]];
+            BvhNode& n = nodes[f];
+            n.c0lox = t.b0.lo[0]; n.c0hix = t.b0.hi[0]; n.c0loy = t.b0.lo[1]; n.c0hiy = t.b0.hi[1];
+            n.c1lox = t.b1.lo[0]; n.c1hix = t.b1.hi[0]; n.c1loy = t.b1.lo[1]; n.c1hiy = t.b1.hi[1];
+            n.c0loz = t.b0.lo[2]; n.c0hiz = t.b0.hi[2]; n.c1loz = t.b1.lo[2]; n.c1hiz = t.b1.hi[2];
+            n.child0 = t.c0 >= 0 ? finalOf[(size_t)t.c0] : t.c0;
+            n.child1 = t.c1 >= 0 ? finalOf[(size_t)t.c1] : t.c1;
+            n.pad0 = 0; n.pad1 = 0;
+        }
+    });
+
+    // ---- traversal triangles in leaf order ----------------------------------------------------------------
+    travTris.resize(count);
+    parallelFor(threads, count, 1u << 16, [&](uint32_t b, uint32_t e) {
+        for (uint32_t k = b; k < e; ++k) {
+            const uint32_t id = idx[k];
+            const TriangleRec& t = tris[id];
+            TravTri& o = travTris[k];
+            for (int a = 0; a < 3; ++a) { o.p0[a] = t.p0[a]; o.e1[a] = t.p1[a] - t.p0[a]; o.e2[a] = t.p2[a] - t.p0[a]; }
+            o.id = id; o.pad1 = 0; o.pad2 = 0;
+        }
+    });
+
+    // ---- statistics ---------------------------------------------------------------------------------------
+    {
+        Box root; root = all[(size_t)rootLink].b0; root.grow(all[(size_t)rootLink].b1);
+        const float rootArea = std::max(root.area(), 1e-30f);
+        double cost = C_TRAV;   // the root itself
+        uint32_t leaves = 0, maxDepth = 0;
+        std::vector<std::pair<int32_t, uint32_t>> st; st.push_back({rootLink, 1});
+        while (!st.empty()) {
+            auto [t, d] = st.back(); st.pop_back();
+            maxDepth = std::max(maxDepth, d);
+            const TNode& n = all[(size_t)t];
+            const Box* bx[2] = {&n.b0, &n.b1}; const int32_t ch[2] = {n.c0, n.c1};
+            for (int s = 0; s < 2; ++s) {
+                const float rel = bx[s]->area() / rootArea;
+                if (ch[s] >= 0) { cost += C_TRAV * rel; st.push_back({ch[s], d + 1}); }
+                else { cost += rel * (float)((~(uint32_t)ch[s] & 7u) + 1u); leaves++; }
+            }
+        }
+        stats.nodeCount = (uint32_t)nodes.size(); stats.leafCount = leaves; stats.maxDepth = maxDepth; stats.sahCost = (float)cost;
+    }
+    stats.buildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace rtb

@@ -1,0 +1,642 @@
+// rtb_kernels.cu — the sm_100a kernels of the hot path.
+//
+//   k_init            init.comp                     (SH/init.comp:12-18)
+//   k_raygen          primary-ray generation        (SH/raygen.comp:16-37, SH/camera.glsl)
+//   k_trace_bvh       persistent, warp-refilled, stack-based BVH traversal with Möller–Trumbore fused
+//                     into the leaf loop (replaces the triangle loop of SH/trace.glsl:25-29 / :78-81)
+//   k_trace_brute     the reference's linear triangle loop, shared-memory tiled (GPU-side cross-check)
+//   k_finish_primary  sphere/cube/plane loops, normal interpolation, G-buffer stores (SH/trace.glsl:31-63,
+//                     SH/raygen.comp:39-51)
+//   k_shadowgen       shadow-ray set-up + non-triangle occluders (SH/nv_all.shadow.comp:50-143)
+//   k_shade           lighting.comp + composite.comp fused, coalesced rgba8 store
+//
+// "SH/" = res/shaders/ of the reference.  Compiled with -fmad=false (see rtb_math.cuh).
+#include "rtb_kernels.cuh"
+#include "rtb_math.cuh"
+
+namespace rtb {
+
+// --------------------------------------------------------------------------------------------------------
+// slot <-> pixel
+// --------------------------------------------------------------------------------------------------------
+RTB_DI bool slotToPixel(const FrameMap& fm, uint32_t i, uint32_t& x, uint32_t& y) {
+    const uint32_t k = i >> 10, s = (i >> 5) & 31u, lane = i & 31u;
+    const uint32_t g = k * fm.nranks + fm.rank;
+    if (g >= fm.blocksX * fm.blocksY) return false;
+    const uint32_t bx = g % fm.blocksX, by = g / fm.blocksX;
+    x = bx * 32u + (s & 3u) * 8u + (lane & 7u);
+    y = by * 32u + (s >> 2) * 4u + (lane >> 3);
+    return x < fm.w && y < fm.h;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K0
+// --------------------------------------------------------------------------------------------------------
+__global__ void k_init(SeedRec* seed) {
+    SeedRec s = *seed;
+    vec2 off = rand2(mk2(s.cpuOffsetX, s.cpuOffsetY) + (float)s.sampleCount);
+    s.randomX = off.x; s.randomY = off.y;
+    ++s.sampleCount; ++s.sampleOffset;
+    *seed = s;
+}
+void launch_init(SeedRec* seed, cudaStream_t st) { k_init<<<1, 1, 0, st>>>(seed); }
+
+// --------------------------------------------------------------------------------------------------------
+// K1a: primary rays
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raygen(const FrameMap fm, const CameraRec cam, const SeedRec* __restrict__ seed,
+                                                RayRec* __restrict__ rays) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fm.localSlots) return;
+    uint32_t x, y;
+    float4 o, d;
+    if (slotToPixel(fm, i, x, y)) {
+        const vec2 rnd = mk2(__ldg(&seed->randomX), __ldg(&seed->randomY));
+        const Ray r = calculatePrimary(cam, x, y, rnd);
+        o = make_float4(r.pos.x, r.pos.y, r.pos.z, ubits(NO_RAY_HIT));
+        d = make_float4(r.dir.x, r.dir.y, r.dir.z, NO_HIT);
+    } else {
+        o = make_float4(0.f, 0.f, 0.f, ubits(NO_RAY_HIT));
+        d = make_float4(0.f, 0.f, 1.f, -1.0f);
+    }
+    float4* out = reinterpret_cast<float4*>(rays + i);
+    out[0] = o; out[1] = d;
+}
+void launch_raygen(const FrameMap& fm, const CameraRec* cam, const SeedRec* seed, RayRec* rays, cudaStream_t st) {
+    if (!fm.localSlots) return;
+    k_raygen<<<(fm.localSlots + 255) / 256, 256, 0, st>>>(fm, *cam, seed, rays);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// BVH traversal
+// --------------------------------------------------------------------------------------------------------
+constexpr int TRACE_THREADS = 256;
+constexpr int TOP_NODES = 256;              // top of the tree (breadth-first prefix) staged in shared memory: 16 KB
+constexpr int STACK_SIZE = 64;              // the builder bounds the depth to STACK_SIZE - 2
+constexpr int REFILL_THRESHOLD = 20;        // refill when fewer lanes than this still traverse
+constexpr int SENTINEL = 0x7FFFFFFF;
+
+enum { MODE_CLOSEST = 0, MODE_ANY_BITS = 1, MODE_ANY_BYTES = 2 };
+
+struct TraceArgs {
+    const RayRec* rays; uint32_t n;
+    const float4* nodes; const float4* tris; uint32_t nodeCount;
+    TriHit* hits;               // MODE_CLOSEST
+    uint32_t* bits; FrameMap fm;// MODE_ANY_BITS
+    uint8_t* bytes;             // MODE_ANY_BYTES
+    uint32_t* workCounter;
+    TraceCounters* counters;
+};
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) {
+    __shared__ float4 sTop[TOP_NODES * 4];
+    const int topN = min((int)a.nodeCount, TOP_NODES);
+    for (int i = threadIdx.x; i < topN * 4; i += TRACE_THREADS) sTop[i] = __ldg(a.nodes + i);
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lanesBelow = (1u << lane) - 1u;
+    int stack[STACK_SIZE];
+
+    bool active = false, exhausted = false;
+    uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0, oodx = 0, oody = 0, oodz = 0;
+    float best = 0, bu = 0, bv = 0;
+    int node = SENTINEL, sp = 0;
+    unsigned long long cRays = 0, cNodes = 0, cTris = 0, cHits = 0;
+
+    for (;;) {
+        // ---- refill: idle lanes take the next rays of the wavefront (one atomic per warp) -------------
+        const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+        if (need && !exhausted) {
+            uint32_t base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(a.workCounter, (uint32_t)__popc(need));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            exhausted = base + (uint32_t)__popc(need) >= a.n;
+            if (!active) {
+                slot = base + (uint32_t)__popc(need & lanesBelow);
+                if (slot < a.n) {
+                    const float4 o = __ldg(reinterpret_cast<const float4*>(a.rays + slot));
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(a.rays + slot) + 1);
+                    if (d.w >= 0.0f) {
+                        ox = o.x; oy = o.y; oz = o.z; prev = fbits(o.w);
+                        dx = d.x; dy = d.y; dz = d.z; best = d.w;
+                        const float tiny = 8.271806e-25f;   // 2^-80: keeps 1/d finite for axis-parallel rays
+                        idx = 1.0f / (fabsf(dx) > tiny ? dx : copysignf(tiny, dx));
+                        idy = 1.0f / (fabsf(dy) > tiny ? dy : copysignf(tiny, dy));
+                        idz = 1.0f / (fabsf(dz) > tiny ? dz : copysignf(tiny, dz));
+                        oodx = ox * idx; oody = oy * idy; oodz = oz * idz;
+                        bestId = NO_RAY_HIT; bu = 0.0f; bv = 0.0f;
+                        stack[0] = SENTINEL; sp = 0; node = 0;
+                        active = true;
+                        if (COUNT) cRays++;
+                    } else if (MODE == MODE_CLOSEST) {
+                        TriHit h; h.t = NO_HIT; h.id = NO_RAY_HIT; h.u = 0.0f; h.v = 0.0f;
+                        *reinterpret_cast<float4*>(a.hits + slot) = *reinterpret_cast<float4*>(&h);
+                    } else if (MODE == MODE_ANY_BYTES) {
+                        a.bytes[slot] = 0;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- traverse in lock-step until too few lanes are left -----------------------------------------
+        for (;;) {
+            if (active) {
+                // inner nodes: both children's slabs come with the node
+                while ((unsigned)node < (unsigned)SENTINEL) {
+                    float4 n0, n1, n2, n3;
+                    if (node < topN) {
+                        const float4* p = sTop + node * 4;
+                        n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+                    } else {
+                        const float4* p = a.nodes + (size_t)node * 4;
+                        n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
+                    }
+                    if (COUNT) cNodes++;
+                    const float c0lox = fmaf(n0.x, idx, -oodx), c0hix = fmaf(n0.y, idx, -oodx);
+                    const float c0loy = fmaf(n0.z, idy, -oody), c0hiy = fmaf(n0.w, idy, -oody);
+                    const float c1lox = fmaf(n1.x, idx, -oodx), c1hix = fmaf(n1.y, idx, -oodx);
+                    const float c1loy = fmaf(n1.z, idy, -oody), c1hiy = fmaf(n1.w, idy, -oody);
+                    const float c0loz = fmaf(n2.x, idz, -oodz), c0hiz = fmaf(n2.y, idz, -oodz);
+                    const float c1loz = fmaf(n2.z, idz, -oodz), c1hiz = fmaf(n2.w, idz, -oodz);
+                    const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+                    const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best));
+                    const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+                    const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best));
+                    const bool h0 = c0max >= c0min, h1 = c1max >= c1min;
+                    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                    if (!h0 && !h1) {
+                        node = stack[sp]; sp--;
+                    } else {
+                        node = h0 ? c0 : c1;
+                        if (h0 && h1) {
+                            int far = c1;
+                            if (c1min < c0min) { far = c0; node = c1; }
+                            stack[++sp] = far;
+                        }
+                    }
+                }
+                // one leaf
+                if (node < 0) {
+                    const uint32_t link = ~(uint32_t)node;
+                    const uint32_t first = link >> 3, count = (link & 7u) + 1u;
+                    const vec3 ro = mk3(ox, oy, oz), rd = mk3(dx, dy, dz);
+                    for (uint32_t k = 0; k < count; ++k) {
+                        const float4* tp = a.tris + (size_t)(first + k) * 3;
+                        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                        if (COUNT) cTris++;
+                        float u, v, t, aa;
+                        if (!triCandidate(ro, rd, mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), u, v, t, aa)) continue;
+                        const uint32_t id = fbits(t0.w);
+                        if (!(t > 0.0f) || id == prev) continue;
+                        if (MODE == MODE_CLOSEST) {
+                            // reference: strict t < hitT in index order => on equal t the lower index wins
+                            if (t < best || (t == best && id < bestId)) { best = t; bestId = id; bu = u; bv = v; }
+                        } else {
+                            if (t < best) { bestId = id; break; }
+                        }
+                    }
+                    if (MODE != MODE_CLOSEST && bestId != NO_RAY_HIT) node = SENTINEL;
+                    else { node = stack[sp]; sp--; }
+                }
+                if (node == SENTINEL) {
+                    active = false;
+                    if (MODE == MODE_CLOSEST) {
+                        TriHit h; h.t = bestId == NO_RAY_HIT ? NO_HIT : best; h.id = bestId; h.u = bu; h.v = bv;
+                        *reinterpret_cast<float4*>(a.hits + slot) = *reinterpret_cast<float4*>(&h);
+                        if (COUNT && bestId != NO_RAY_HIT) cHits++;
+                    } else if (MODE == MODE_ANY_BITS) {
+                        if (bestId != NO_RAY_HIT) {
+                            const uint32_t sample = slot / a.fm.localSlots, i = slot - sample * a.fm.localSlots;
+                            uint32_t x, y;
+                            slotToPixel(a.fm, i, x, y);
+                            atomicOr(a.bits + indexToLight(x, y, a.fm.w, a.fm.h, sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
+                            if (COUNT) cHits++;
+                        }
+                    } else {
+                        a.bytes[slot] = bestId != NO_RAY_HIT ? 1 : 0;
+                    }
+                }
+            }
+            if (__popc(__ballot_sync(0xFFFFFFFFu, active)) < REFILL_THRESHOLD) break;
+        }
+    }
+
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            cRays += __shfl_xor_sync(0xFFFFFFFFu, cRays, o); cNodes += __shfl_xor_sync(0xFFFFFFFFu, cNodes, o);
+            cTris += __shfl_xor_sync(0xFFFFFFFFu, cTris, o); cHits += __shfl_xor_sync(0xFFFFFFFFu, cHits, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.counters->rays, cRays); atomicAdd(&a.counters->nodes, cNodes);
+            atomicAdd(&a.counters->tris, cTris); atomicAdd(&a.counters->hits, cHits);
+        }
+    }
+}
+
+static int g_traceBlocks = 0;
+template <int MODE, bool COUNT>
+static void launchTraceBvh(const TraceArgs& a, cudaStream_t st) {
+    static int blocks = 0;
+    if (!blocks) {
+        int dev = 0, sms = 0, perSm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace_bvh<MODE, COUNT>, TRACE_THREADS, 0);
+        blocks = sms * (perSm > 0 ? perSm : 1);
+        if (!COUNT) g_traceBlocks = blocks;
+    }
+    cudaMemsetAsync(a.workCounter, 0, sizeof(uint32_t), st);
+    const uint32_t warpsNeeded = (a.n + 31u) / 32u, blocksNeeded = (warpsNeeded + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32);
+    k_trace_bvh<MODE, COUNT><<<min((uint32_t)blocks, blocksNeeded ? blocksNeeded : 1u), TRACE_THREADS, 0, st>>>(a);
+}
+int trace_grid_blocks() { return g_traceBlocks; }
+
+// --------------------------------------------------------------------------------------------------------
+// brute force: the reference's triangle loop (SH/trace.glsl:25-29, :78-81), triangles staged through shared memory
+// --------------------------------------------------------------------------------------------------------
+constexpr int BRUTE_THREADS = 256, BRUTE_CHUNK = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(BRUTE_THREADS) k_trace_brute(const RayRec* __restrict__ rays, uint32_t n,
+                                                               const TriangleRec* __restrict__ tris, uint32_t triCount,
+                                                               TriHit* __restrict__ hits, uint32_t* __restrict__ bits, const FrameMap fm,
+                                                               uint8_t* __restrict__ bytes) {
+    __shared__ float4 sTri[BRUTE_CHUNK * 3];
+    const uint32_t slot = blockIdx.x * BRUTE_THREADS + threadIdx.x;
+    const bool inRange = slot < n;
+    float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, -1.0f);
+    if (inRange) { o = __ldg(reinterpret_cast<const float4*>(rays + slot)); d = __ldg(reinterpret_cast<const float4*>(rays + slot) + 1); }
+    const bool live = inRange && d.w >= 0.0f;
+    const vec3 ro = mk3(o.x, o.y, o.z), rd = mk3(d.x, d.y, d.z);
+    const uint32_t prev = fbits(o.w);
+    float hitT = live ? d.w : 0.0f, bu = 0.0f, bv = 0.0f;
+    uint32_t object = NO_RAY_HIT;
+    for (uint32_t base = 0; base < triCount; base += BRUTE_CHUNK) {
+        const uint32_t cnt = min((uint32_t)BRUTE_CHUNK, triCount - base);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt * 3; i += BRUTE_THREADS) sTri[i] = __ldg(reinterpret_cast<const float4*>(tris + base) + i);
+        __syncthreads();
+        if (!live) continue;
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const float4 a0 = sTri[k * 3], a1 = sTri[k * 3 + 1], a2 = sTri[k * 3 + 2];
+            const vec3 p0 = mk3(a0.x, a0.y, a0.z);
+            float u, v, t, aa;
+            if (!triCandidate(ro, rd, p0, mk3(a1.x, a1.y, a1.z) - p0, mk3(a2.x, a2.y, a2.z) - p0, u, v, t, aa)) continue;
+            const uint32_t id = base + k;
+            if (t <= 0.0f || id == prev || t >= hitT) continue;   // SH/primitive.glsl:268 (a NaN t passes, as in the reference)
+            hitT = t; object = id; bu = u; bv = v;
+        }
+    }
+    if (!inRange) return;
+    if (MODE == MODE_CLOSEST) {
+        TriHit h; h.t = object == NO_RAY_HIT ? NO_HIT : hitT; h.id = object; h.u = bu; h.v = bv;
+        *reinterpret_cast<float4*>(hits + slot) = *reinterpret_cast<float4*>(&h);
+    } else if (MODE == MODE_ANY_BITS) {
+        if (live && object != NO_RAY_HIT) {
+            const uint32_t sample = slot / fm.localSlots, i = slot - sample * fm.localSlots;
+            uint32_t x, y;
+            slotToPixel(fm, i, x, y);
+            atomicOr(bits + indexToLight(x, y, fm.w, fm.h, sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
+        }
+    } else {
+        bytes[slot] = (live && object != NO_RAY_HIT) ? 1 : 0;
+    }
+}
+
+__global__ void k_fill_miss(TriHit* hits, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TriHit h; h.t = NO_HIT; h.id = NO_RAY_HIT; h.u = 0.0f; h.v = 0.0f;
+    *reinterpret_cast<float4*>(hits + i) = *reinterpret_cast<float4*>(&h);
+}
+
+static TraceArgs makeArgs(const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* workCounter, TraceCounters* counters) {
+    TraceArgs a{};
+    a.rays = rays; a.n = n;
+    a.nodes = reinterpret_cast<const float4*>(sv.nodes); a.tris = reinterpret_cast<const float4*>(sv.travTris); a.nodeCount = sv.nodeCount;
+    a.workCounter = workCounter; a.counters = counters;
+    return a;
+}
+
+void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
+                          TraceCounters* counters, cudaStream_t st) {
+    if (!n) return;
+    if (sv.info.triangleCount == 0) { k_fill_miss<<<(n + 255) / 256, 256, 0, st>>>(hits, n); return; }
+    if (sv.useBvh) {
+        TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
+        a.hits = hits;
+        if (counters) launchTraceBvh<MODE_CLOSEST, true>(a, st); else launchTraceBvh<MODE_CLOSEST, false>(a, st);
+    } else {
+        FrameMap fm{};
+        k_trace_brute<MODE_CLOSEST><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, hits, nullptr, fm, nullptr);
+    }
+}
+
+void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits,
+                           uint32_t* workCounter, TraceCounters* counters, cudaStream_t st) {
+    if (!n || sv.info.triangleCount == 0) return;
+    if (sv.useBvh) {
+        TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
+        a.bits = bits; a.fm = fm;
+        if (counters) launchTraceBvh<MODE_ANY_BITS, true>(a, st); else launchTraceBvh<MODE_ANY_BITS, false>(a, st);
+    } else {
+        k_trace_brute<MODE_ANY_BITS><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, bits, fm, nullptr);
+    }
+}
+
+void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n, uint8_t* occluded, uint32_t* workCounter, cudaStream_t st) {
+    if (!n) return;
+    if (sv.info.triangleCount == 0) { cudaMemsetAsync(occluded, 0, n, st); return; }
+    if (sv.useBvh) {
+        TraceArgs a = makeArgs(sv, rays, n, workCounter, nullptr);
+        a.bytes = occluded;
+        launchTraceBvh<MODE_ANY_BYTES, false>(a, st);
+    } else {
+        FrameMap fm{};
+        k_trace_brute<MODE_ANY_BYTES><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, nullptr, fm, occluded);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K1b: the rest of traceGeometry after the triangle loop, then the G-buffer stores
+// --------------------------------------------------------------------------------------------------------
+// SH/trace.glsl:31-63: spheres, cubes, planes in order with running ids; then the normal selection.
+RTB_DI void finishGeometry(const SceneView& sv, const Ray& ray, uint32_t prev, const TriHit& th, Hit& hit, vec3& objectNormal) {
+    hit.hitT = th.id == NO_RAY_HIT ? NO_HIT : th.t;
+    hit.uv = mk2(th.u, th.v);
+    hit.object = th.id == NO_RAY_HIT ? 0u : th.id;
+    hit.geometryNormal = mk3(0.0f, 0.0f, 0.0f);
+    uint32_t j = sv.info.triangleCount;
+    for (uint32_t i = 0; i < sv.info.sphereCount; ++i, ++j)
+        if (rayIntersectSphere(ray, __ldg(sv.spheres + i), hit, j, prev)) hit.object = j;
+    for (uint32_t i = 0; i < sv.info.cubeCount; ++i, ++j) {
+        float c[6];
+        const float2* cp = reinterpret_cast<const float2*>(sv.cubes + 6 * (size_t)i);
+        const float2 c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
+        c[0] = c0.x; c[1] = c0.y; c[2] = c1.x; c[3] = c1.y; c[4] = c2.x; c[5] = c2.y;
+        if (rayIntersectCube(ray, c, hit, j, prev)) hit.object = j;
+    }
+    for (uint32_t i = 0; i < sv.info.planeCount; ++i, ++j)
+        if (rayIntersectPlane(ray, __ldg(sv.planes + i), hit, j, prev)) hit.object = j;
+    if (hit.object < sv.info.triangleCount) {   // also taken on a miss when the scene has triangles (object == 0)
+        const TriangleRec* t = sv.triangles + hit.object;
+        const uint32_t e0 = __ldg(&t->n0), e1 = __ldg(&t->n1), e2 = __ldg(&t->n2);
+        objectNormal = interpolate(decodeSpheremap(e0), decodeSpheremap(e1), decodeSpheremap(e2), hit.uv);
+    } else
+        objectNormal = hit.geometryNormal;
+}
+
+__global__ void __launch_bounds__(256) k_finish_primary(const FrameMap fm, const SceneView sv, const RayRec* __restrict__ rays,
+                                                        const TriHit* __restrict__ hits, float4* __restrict__ dirT, float4* __restrict__ uvN) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fm.localSlots) return;
+    uint32_t x, y;
+    if (!slotToPixel(fm, i, x, y)) return;
+    const float4 o = __ldg(reinterpret_cast<const float4*>(rays + i)), d = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(hits + i));
+    TriHit th; th.t = hv.x; th.id = fbits(hv.y); th.u = hv.z; th.v = hv.w;
+    Ray ray; ray.pos = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
+    Hit hit; vec3 objectNormal;
+    finishGeometry(sv, ray, NO_RAY_HIT, th, hit, objectNormal);
+    // SH/raygen.comp:39-51
+    float4 out0;
+    if (hit.hitT == NO_HIT) out0 = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ubits(NO_RAY_HIT));
+    else { const vec3 v = ray.dir * hit.hitT; out0 = make_float4(v.x, v.y, v.z, ubits(hit.object)); }
+    uint32_t ex, ey;
+    encodeNormalGpu(objectNormal, ex, ey);
+    const size_t px = (size_t)y * fm.w + x;
+    dirT[px] = out0;
+    uvN[px] = make_float4(hit.uv.x, hit.uv.y, ubits(ex), ubits(ey));
+}
+void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits, float4* dirT, float4* uvN, cudaStream_t st) {
+    if (!fm.localSlots) return;
+    k_finish_primary<<<(fm.localSlots + 255) / 256, 256, 0, st>>>(fm, sv, rays, hits, dirT, uvN);
+}
+
+__global__ void __launch_bounds__(256) k_finish_rays(const SceneView sv, const RayRec* __restrict__ rays, const TriHit* __restrict__ hits,
+                                                     uint32_t n, uint32_t* __restrict__ object, float* __restrict__ t, float2* __restrict__ uv) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = __ldg(reinterpret_cast<const float4*>(rays + i)), d = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(hits + i));
+    TriHit th; th.t = hv.x; th.id = fbits(hv.y); th.u = hv.z; th.v = hv.w;
+    Ray ray; ray.pos = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
+    Hit hit; vec3 objectNormal;
+    finishGeometry(sv, ray, fbits(o.w), th, hit, objectNormal);
+    if (object) object[i] = hit.hitT == NO_HIT ? NO_RAY_HIT : hit.object;
+    if (t) t[i] = hit.hitT;
+    if (uv) uv[i] = make_float2(hit.uv.x, hit.uv.y);
+}
+void launch_finish_rays(const SceneView& sv, const RayRec* rays, const TriHit* hits, uint32_t n, uint32_t* object, float* t, float2* uv, cudaStream_t st) {
+    if (!n) return;
+    k_finish_rays<<<(n + 255) / 256, 256, 0, st>>>(sv, rays, hits, n, object, t, uv);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K2: shadow rays
+// --------------------------------------------------------------------------------------------------------
+// Occlusion by spheres, cubes and planes: the tail of traceOcclusion (SH/trace.glsl:83-96).  The loops only ever lower
+// hitT, so "hitT < maxDist after all loops" is the same as "some primitive's candidate distance is < maxDist", which
+// lets the triangles be searched separately (any-hit) without changing the result.
+RTB_DI bool occludedByOthers(const SceneView& sv, const Ray& ray, float maxDist, uint32_t prev) {
+    Hit hit;
+    hit.hitT = NO_HIT; hit.uv = mk2(0.0f, 0.0f); hit.object = 0; hit.geometryNormal = mk3(0.0f, 0.0f, 0.0f);
+    uint32_t j = sv.info.triangleCount;
+    for (uint32_t i = 0; i < sv.info.sphereCount; ++i, ++j) {
+        if (j == prev) continue;
+        const float t = sphereCandidateT(ray, __ldg(sv.spheres + i));
+        if (t < hit.hitT) hit.hitT = t;
+    }
+    for (uint32_t i = 0; i < sv.info.cubeCount; ++i, ++j) {
+        float c[6];
+        const float2* cp = reinterpret_cast<const float2*>(sv.cubes + 6 * (size_t)i);
+        const float2 c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
+        c[0] = c0.x; c[1] = c0.y; c[2] = c1.x; c[3] = c1.y; c[4] = c2.x; c[5] = c2.y;
+        rayIntersectCube(ray, c, hit, j, prev);
+    }
+    for (uint32_t i = 0; i < sv.info.planeCount; ++i, ++j) rayIntersectPlane(ray, __ldg(sv.planes + i), hit, j, prev);
+    return hit.hitT < maxDist;
+}
+
+__global__ void __launch_bounds__(256) k_shadowgen(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
+                                                   uint32_t samples, const float4* __restrict__ dirT, RayRec* __restrict__ rays,
+                                                   uint32_t* __restrict__ bits) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= fm.localSlots * samples) return;
+    const uint32_t sample = j / fm.localSlots, i = j - sample * fm.localSlots;
+    float4 ro = make_float4(0.f, 0.f, 0.f, ubits(NO_RAY_HIT)), rd = make_float4(0.f, 0.f, 1.f, -1.0f);
+    uint32_t x, y;
+    if (slotToPixel(fm, i, x, y)) {
+        const float4 dt = __ldg(dirT + (size_t)y * fm.w + x);
+        const uint32_t object = fbits(dt.w);
+        if (object != NO_RAY_HIT) {
+            // SH/nv_all.shadow.comp:84-126
+            const vec3 hitPos = mk3(cam.eye) + mk3(dt.x, dt.y, dt.z);
+            const vec2 loc = mk2((float)x, (float)y);
+            vec2 uv = (loc + rand2(loc + mk2(__ldg(&seed->randomX), __ldg(&seed->randomY)))) / 128.0f;
+            uv = uv + hammersley(sample, samples);
+            const vec2 random = rand2(uv);
+            const LightRec light = sv.lights[0];   // lightId = 0 (SH/nv_all.shadow.comp:97)
+            float brightness, dist;
+            const vec3 l = getDirToLight(light, hitPos, brightness, dist, random);
+            Ray ray; ray.pos = hitPos; ray.dir = -l;
+            float maxDist = -1.0f;
+            if (dist >= 0.0f) {
+                const vec2 radOrigin = unpackHalf2x16(light.radOrigin);
+                if (dist >= radOrigin.y && dist < radOrigin.x) maxDist = dist - radOrigin.y;
+            } else
+                maxDist = NO_HIT;
+            // maxDist <= 0 can never be undercut by a triangle (t > 0) but a cube entered from inside reports t < 0
+            if (maxDist != -1.0f) {
+                if (occludedByOthers(sv, ray, maxDist, object))
+                    atomicOr(bits + indexToLight(x, y, fm.w, fm.h, sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
+                else if (maxDist > 0.0f) {
+                    ro = make_float4(ray.pos.x, ray.pos.y, ray.pos.z, ubits(object));
+                    rd = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, maxDist);
+                }
+            }
+        }
+    }
+    float4* out = reinterpret_cast<float4*>(rays + j);
+    out[0] = ro; out[1] = rd;
+}
+void launch_shadowgen(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
+                      const float4* dirT, RayRec* rays, uint32_t* bits, cudaStream_t st) {
+    const uint32_t n = fm.localSlots * samples;
+    if (!n) return;
+    k_shadowgen<<<(n + 255) / 256, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, rays, bits);
+}
+
+__global__ void __launch_bounds__(256) k_occlusion_others(const SceneView sv, RayRec* __restrict__ rays, uint32_t n, uint8_t* __restrict__ occluded) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = *reinterpret_cast<const float4*>(rays + i), d = *(reinterpret_cast<const float4*>(rays + i) + 1);
+    Ray ray; ray.pos = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
+    const bool occ = occludedByOthers(sv, ray, d.w, fbits(o.w));
+    occluded[i] = occ ? 1 : 0;
+    if (occ || !(d.w > 0.0f)) rays[i].tmax = -1.0f;   // nothing left for the triangle search
+}
+void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t st) {
+    if (!n) return;
+    k_occlusion_others<<<(n + 255) / 256, 256, 0, st>>>(sv, rays, n, occluded);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K3 + K4: lighting and composite, one thread per pixel
+// --------------------------------------------------------------------------------------------------------
+// DO_LIGHT: evaluate lighting.comp; DO_COMP: evaluate composite.comp.  Both: the fused frame path (the rgba16f
+// rounding of the lighting texture is reproduced in registers); one only: the reference's separate dispatches.
+template <bool DO_LIGHT, bool DO_COMP>
+__global__ void __launch_bounds__(256) k_shade(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
+                                               uint32_t samples, const float4* __restrict__ dirT, const float4* __restrict__ uvN,
+                                               const uint32_t* __restrict__ bits, uint2* __restrict__ lighting, float4* __restrict__ accum,
+                                               uint32_t* __restrict__ rgba8, uint32_t* __restrict__ rgba8Tiled) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fm.localSlots) return;
+    uint32_t x, y;
+    if (!slotToPixel(fm, i, x, y)) { if (DO_COMP && rgba8Tiled) rgba8Tiled[i] = 0u; return; }
+    const size_t px = (size_t)y * fm.w + x;
+    const float4 dt = __ldg(dirT + px), un = __ldg(uvN + px);
+    const uint32_t object = fbits(dt.w);
+    const vec3 dxyz = mk3(dt.x, dt.y, dt.z);
+    const vec3 eye = mk3(cam.eye);
+    const vec3 n = decodeNormal(fbits(un.z), fbits(un.w));
+    const bool isHit = object != NO_RAY_HIT;
+
+    MatU m;
+    if (isHit) m = unpackMaterial(sv.materials + __ldg(sv.materialIndices + object));
+
+    uint32_t lx, ly, lz;
+    if (DO_LIGHT) {
+        // ---- lighting.comp (SH/nv_all.lighting.comp:33-103) --------------------------------------------
+        vec3 light = mk3(0.0f, 0.0f, 0.0f);
+        if (isHit) {
+            const vec3 hitPos = eye + dxyz;
+            const vec3 F0 = mix(mk3(0.04f, 0.04f, 0.04f), m.albedo, m.metallic);
+            const vec3 v = normalize(dxyz);
+            const float NdotV = fmaxf(dot(v, -n), 0.0f);
+            const vec2 loc = mk2((float)x, (float)y);
+            const vec2 uv = (loc + rand2(loc + mk2(0.0f, 0.0f))) / 128.0f;   // Seed is unbound in lighting.comp: reads as zero (decree D8)
+            const LightRec l0 = sv.lights[0];
+            const uint32_t bit = 1u << ((x & 15u) | ((y & 1u) << 4));
+            for (uint32_t s = 0; s < samples; ++s) {
+                const vec2 random = rand2(uv + hammersley(s, samples));
+                const uint32_t word = __ldg(bits + indexToLight(x, y, fm.w, fm.h, s));
+                if (!(word & bit)) light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, l0, hitPos, n, v, NdotV, random);
+            }
+            light = light / (float)samples * (float)sv.info.lightCount;
+        }
+        // imageStore to rgba16f (alpha 1 on a hit; the shipped DEBUG shader stores vec4(0) on a miss)
+        lx = f2h_rn(light.x); ly = f2h_rn(light.y); lz = f2h_rn(light.z);
+        if (lighting) lighting[px] = make_uint2(lx | (ly << 16), lz | ((isHit ? 0x3C00u : 0u) << 16));
+        if (!DO_COMP) return;
+    } else {
+        const uint2 lv = __ldg(lighting + px);
+        lx = lv.x & 0xFFFFu; ly = lv.x >> 16; lz = lv.y & 0xFFFFu;
+    }
+    const vec3 light = mk3(h2f(lx), h2f(ly), h2f(lz));
+
+    // ---- composite.comp (SH/composite.comp:52-285, SH/light.glsl:205-219) ---------------------------------
+    const SkyView sky = {sv.skybox, sv.skyW, sv.skyH};
+    const vec3 rayDir = normalize(dxyz);
+    vec3 color;
+    if (!isHit)
+        color = sampleSkybox(sky, cam, rayDir);
+    else {
+        const float NdotV = fmaxf(dot(rayDir, -n), 0.0f);
+        const vec3 reflected = sampleSkybox(sky, cam, reflect(rayDir, n));
+        color = shade(m, NdotV, light, reflected);
+    }
+    color = mix(color, mk3(0.0f, 0.0f, 0.0f), 0.0f);   // cloud term is vec4(0) (SH/composite.comp:93-97)
+    if (cam.flags & CAMERA_USE_SUPERSAMPLING) {          // SH/composite.comp:249-257
+        const uint32_t sampleCount = __ldg(&seed->sampleCount);
+        if (sampleCount > 1) { const float4 p = accum[px]; color = color + mk3(p.x, p.y, p.z); }
+        accum[px] = make_float4(color.x, color.y, color.z, 0.0f);
+        color = color / (float)sampleCount;
+    }
+    const vec3 e = -color * cam.exposure;
+    color = vmax(mk3(1.0f, 1.0f, 1.0f) - mk3(cr_exp(e.x), cr_exp(e.y), cr_exp(e.z)), mk3(0.0f, 0.0f, 0.0f));
+    const uint32_t out = unorm8(color.x) | (unorm8(color.y) << 8) | (unorm8(color.z) << 16) | (255u << 24);
+    if (rgba8) rgba8[px] = out;
+    if (rgba8Tiled) rgba8Tiled[i] = out;
+}
+void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
+                  const float4* dirT, const float4* uvN, const uint32_t* bits, uint2* lighting, float4* accum,
+                  uint32_t* rgba8, uint32_t* rgba8Tiled, cudaStream_t st) {
+    if (!fm.localSlots) return;
+    const uint32_t g = (fm.localSlots + 255) / 256;
+    if (what == SHADE_LIGHTING) k_shade<true, false><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled);
+    else if (what == SHADE_COMPOSITE) k_shade<false, true><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled);
+    else k_shade<true, true><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// rank 0 after the gather: [nranks][slotsPerRank] tiled pixels -> scan-line order
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_untile(const FrameMap fm, const uint32_t* __restrict__ tiledAll, uint32_t slotsPerRank,
+                                                uint32_t* __restrict__ rgba8) {
+    const uint32_t gslot = blockIdx.x * blockDim.x + threadIdx.x;   // over all global blocks * 1024
+    const uint32_t g = gslot >> 10;
+    if (g >= fm.blocksX * fm.blocksY) return;
+    const uint32_t s = (gslot >> 5) & 31u, lane = gslot & 31u;
+    const uint32_t bx = g % fm.blocksX, by = g / fm.blocksX;
+    const uint32_t x = bx * 32u + (s & 3u) * 8u + (lane & 7u), y = by * 32u + (s >> 2) * 4u + (lane >> 3);
+    if (x >= fm.w || y >= fm.h) return;
+    const uint32_t rank = g % fm.nranks, k = g / fm.nranks;
+    rgba8[(size_t)y * fm.w + x] = __ldg(tiledAll + (size_t)rank * slotsPerRank + (size_t)k * 1024u + (gslot & 1023u));
+}
+void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsPerRank, uint32_t* rgba8, cudaStream_t st) {
+    const uint32_t n = fm.blocksX * fm.blocksY * 1024u;
+    if (!n) return;
+    k_untile<<<(n + 255) / 256, 256, 0, st>>>(fm, tiledAll, slotsPerRank, rgba8);
+}
+
+}  // namespace rtb

@@ -1,0 +1,59 @@
+// rtb_kernels.cuh — launch interface between the C-ABI layer (rtb_api.cu) and the kernels (rtb_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "rtb_types.h"
+
+namespace rtb {
+
+// Which pixels this context renders and where each wavefront slot lives.
+// The screen is cut into 32x32-pixel blocks; block g belongs to rank g % nranks.  Local slot i:
+//   k = i >> 10 (local block, global block g = k * nranks + rank), s = (i >> 5) & 31 (8x4 sub-tile),
+//   lane = i & 31 -> pixel (bx*32 + (s&3)*8 + (lane&7), by*32 + (s>>2)*4 + (lane>>3)).
+// One warp of consecutive slots is therefore an 8x4 pixel patch: coherent primary rays and full 32-byte
+// sectors on every scan-line-order store.
+struct FrameMap {
+    uint32_t w, h, blocksX, blocksY, rank, nranks, localBlocks, localSlots;
+};
+
+struct SceneView {
+    const TriangleRec* triangles; const float4* spheres; const float* cubes; const float4* planes;
+    const LightRec* lights; const MaterialRec* materials; const uint32_t* materialIndices;
+    const uint2* skybox; uint32_t skyW, skyH;
+    SceneInfoRec info;            // host mirror of the reference's SceneData UBO, passed by value
+    const BvhNode* nodes; const TravTri* travTris; uint32_t nodeCount; uint32_t useBvh;
+};
+
+struct TraceCounters { unsigned long long rays, nodes, tris, hits; };
+
+void launch_init(SeedRec* seed, cudaStream_t s);
+void launch_raygen(const FrameMap& fm, const CameraRec* cam, const SeedRec* seed, RayRec* rays, cudaStream_t s);
+// nearest triangle for every ray slot (BVH or brute force according to sv.useBvh)
+void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
+                          TraceCounters* counters, cudaStream_t s);
+// spheres, cubes, planes after the triangles, normal interpolation, G-buffer stores (raygen.comp:39-51)
+void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits,
+                           float4* dirT, float4* uvN, cudaStream_t s);
+// shadow.comp ray set-up + occlusion by the non-triangle primitives; leaves triangle work in `rays`
+void launch_shadowgen(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
+                      const float4* dirT, RayRec* rays, uint32_t* bits, cudaStream_t s);
+// any-hit over the triangles; sets the (pixel, sample) bit of every occluded slot
+void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits,
+                           uint32_t* workCounter, TraceCounters* counters, cudaStream_t s);
+// any-hit, one byte per ray (rays-in mode)
+void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n, uint8_t* occluded, uint32_t* workCounter,
+                            cudaStream_t s);
+// lighting.comp + composite.comp
+enum { SHADE_LIGHTING = 1, SHADE_COMPOSITE = 2, SHADE_BOTH = 3 };
+void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
+                  const float4* dirT, const float4* uvN, const uint32_t* bits, uint2* lighting, float4* accum,
+                  uint32_t* rgba8, uint32_t* rgba8Tiled, cudaStream_t s);
+// rays-in helpers
+void launch_finish_rays(const SceneView& sv, const RayRec* rays, const TriHit* hits, uint32_t n, uint32_t* object, float* t,
+                        float2* uv, cudaStream_t s);
+void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t s);
+// rank 0: gathered [nranks][slotsPerRank] tiled pixels -> scan-line rgba8
+void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsPerRank, uint32_t* rgba8, cudaStream_t s);
+
+int trace_grid_blocks();   // persistent grid size used by the traversal kernels (for reporting)
+
+}  // namespace rtb

@@ -1,0 +1,83 @@
+// rtb_types.h — byte layouts shared by host and device code.
+//
+// The scene-side records keep the reference's GPU layouts byte for byte:
+//   Camera 144 B   ref: igx/include/types/scene_object_types.hpp:32-66, res/shaders/camera.glsl:14-42
+//   Seed 24 B      ref: include/rt/structs.hpp:8-14, res/shaders/rand_util.glsl:6-10
+//   SceneInfo 36 B ref: igx/include/helpers/scene_graph.hpp:61-74, res/shaders/scene.glsl:6-20
+//   Triangle 48 B  ref: scene_object_types.hpp:74-112, res/shaders/primitive.glsl:28-38
+//   Light 32 B     ref: scene_object_types.hpp:158-265, primitive.glsl:46-54
+//   Material 32 B  ref: scene_object_types.hpp:267-290, primitive.glsl:72-81
+// The BVH node and traversal-triangle records are new (the reference has no acceleration structure).
+#pragma once
+#include <stdint.h>
+
+namespace rtb {
+
+struct CameraRec {
+    float eye[3]; uint32_t width;
+    float p0[3]; uint32_t height;
+    float p1[3]; float ipd;
+    float p2[3]; uint32_t projectionType;
+    float skyboxColor[3]; float exposure;
+    float p3[3]; float focalDistance;
+    float p4[3]; float aperature;
+    float p5[3]; uint32_t flags;
+    float invRes[2]; uint32_t tiles[2];
+};
+static_assert(sizeof(CameraRec) == 144, "Camera is 144 bytes");
+
+struct SeedRec { float randomX, randomY, cpuOffsetX, cpuOffsetY; uint32_t sampleCount, sampleOffset; };
+static_assert(sizeof(SeedRec) == 24, "Seed is 24 bytes");
+
+struct SceneInfoRec {
+    uint32_t lightCount, materialCount, triangleCount, sphereCount, cubeCount, planeCount;
+    uint32_t directionalLightCount, spotLightCount, pointLightCount;
+};
+static_assert(sizeof(SceneInfoRec) == 36, "SceneInfo is 36 bytes");
+
+struct TriangleRec { float p0[3]; uint32_t n0; float p1[3]; uint32_t n1; float p2[3]; uint32_t n2; };
+static_assert(sizeof(TriangleRec) == 48, "Triangle is 48 bytes");
+
+struct LightRec { float pos[3]; uint32_t radOrigin; uint32_t dir[2]; uint32_t colorRG; uint32_t colorBType; };
+static_assert(sizeof(LightRec) == 32, "Light is 32 bytes");
+
+struct MaterialRec { uint32_t albedoMetallic[2]; uint32_t ambientRoughness[2]; uint32_t emissive[2]; float transparency; uint32_t materialInfo; };
+static_assert(sizeof(MaterialRec) == 32, "Material is 32 bytes");
+
+enum : uint32_t { CAMERA_USE_UI = 1u, CAMERA_USE_SUPERSAMPLING = 2u };
+enum : uint32_t { LIGHT_DIRECTIONAL = 0u, LIGHT_SPOT = 1u, LIGHT_POINT = 2u };
+
+// ---- acceleration structure (new) ------------------------------------------------------------------
+//
+// Binary BVH, one 64-byte record per inner node holding BOTH children's boxes, so one node fetch
+// (4 x 16-byte vector loads, 64-byte aligned = two 32-byte sectors of one 128-byte line... ) decides
+// both children.  Child links: >= 0 inner-node index; < 0 leaf: ~link = (firstTri << 3) | (count - 1).
+struct alignas(64) BvhNode {
+    float c0lox, c0hix, c0loy, c0hiy;   // child 0: x and y slabs
+    float c1lox, c1hix, c1loy, c1hiy;   // child 1: x and y slabs
+    float c0loz, c0hiz, c1loz, c1hiz;   // both children: z slabs
+    int32_t child0, child1; uint32_t pad0, pad1;
+};
+static_assert(sizeof(BvhNode) == 64, "BVH node is 64 bytes");
+
+// Traversal triangle, in leaf order: p0, e1 = p1 - p0, e2 = p2 - p0 (the same float subtractions the
+// reference shader performs per test, done once), and the triangle's index in the uploaded array.
+struct alignas(16) TravTri {
+    float p0[3]; uint32_t id;
+    float e1[3]; uint32_t pad1;
+    float e2[3]; uint32_t pad2;
+};
+static_assert(sizeof(TravTri) == 48, "traversal triangle is 48 bytes");
+
+constexpr float NO_HIT = 3.4028235e38f;          // ref: res/shaders/primitive.glsl:6
+constexpr uint32_t NO_RAY_HIT = 0xFFFFFFFFu;     // ref: res/shaders/primitive.glsl:7
+
+// One ray of the wavefront: 32 bytes, two 16-byte vector accesses.
+//   o.xyz origin, o.w = bits(prev object id to exclude); d.xyz direction, d.w = tmax (< 0: inactive slot)
+struct alignas(16) RayRec { float ox, oy, oz; uint32_t prev; float dx, dy, dz, tmax; };
+static_assert(sizeof(RayRec) == 32, "ray is 32 bytes");
+
+// Nearest-triangle result of the BVH search: 16 bytes.
+struct alignas(16) TriHit { float t; uint32_t id; float u, v; };
+
+}  // namespace rtb

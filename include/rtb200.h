@@ -1,0 +1,200 @@
+/*
+ * rtb200.h — C ABI of librtb200, the B200 (sm_100a) replacement for the compute-dispatch and
+ * buffer-upload layer under igx_raytracing's hot path.
+ *
+ * The reference drives its five compute shaders (init -> raygen -> shadow -> lighting -> composite)
+ * by recording ignis commands: FlushBuffer / FlushImage / BindDescriptors / BindPipeline / Dispatch,
+ * then Graphics::present / presentToCpu.  Every entry point below names the reference call site it
+ * replaces ("ref:" paths are relative to the reference root; "IGNIS/" = igx/igxi-tool/igxi/ignis/).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
+ * rtb_status on failure (the reference aborts through log()->fatal; we return a code and keep a
+ * message, see rtb_last_error).  A context is bound to one CUDA device and, like ignis::Graphics
+ * (ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:88), must be driven by one thread at a time.
+ * All work is stream-ordered on the context's stream; rtb_readback / rtb_sync synchronise.
+ *
+ * There is no CPU fallback: every call fails with RTB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rtb_ctx rtb_ctx;
+
+typedef enum rtb_status {
+    RTB_OK = 0,
+    RTB_ERR_ARG = 1,      /* bad argument / out of range (reference: oicAssert / silently skipped command) */
+    RTB_ERR_CUDA = 2,     /* CUDA runtime error, message holds cudaGetErrorString */
+    RTB_ERR_STATE = 3,    /* call order violated (e.g. dispatch before resize) */
+    RTB_ERR_CAPACITY = 4  /* upload past the capacity given at rtb_create (reference: add() returns 0) */
+} rtb_status;
+
+/* Object capacities.  The reference hard-codes 65536/32768/16384/256 in the SceneGraph constructor
+ * (ref: igx/include/helpers/scene_graph.hpp:132-146, initialiser igx/src/helpers/scene_graph.cpp:86-95);
+ * here they are explicit so 1M / 10M-triangle scenes fit. */
+typedef struct rtb_limits {
+    uint32_t max_triangles, max_spheres, max_cubes, max_planes, max_lights, max_materials;
+} rtb_limits;
+
+/* Buffers a host may upload: one per reference GPUBuffer on the path. */
+typedef enum rtb_buffer {
+    RTB_BUF_CAMERA = 0,        /* 144 B  ref: src/rt/raytracing_interface.cpp:21-26,327-328 */
+    RTB_BUF_SEED = 1,          /* 24 B   ref: src/rt/task/composite_task.cpp:31-36,239-243 */
+    RTB_BUF_SCENE_INFO = 2,    /* 36 B   ref: igx/src/helpers/scene_graph.cpp:144-154 */
+    RTB_BUF_SHADOW_PROPS = 3,  /* 4 B    ref: src/rt/task/shadow_task.cpp:32-35,189-192 */
+    RTB_BUF_TRIANGLES = 4,     /* 48 B each   ref: igx/src/helpers/scene_graph.cpp:116-128,297-303 */
+    RTB_BUF_SPHERES = 5,       /* 16 B each */
+    RTB_BUF_CUBES = 6,         /* 24 B each */
+    RTB_BUF_PLANES = 7,        /* 16 B each */
+    RTB_BUF_LIGHTS = 8,        /* 32 B each */
+    RTB_BUF_MATERIALS = 9,     /* 32 B each */
+    RTB_BUF_MATERIAL_INDICES = 10, /* u32 per global object id  ref: igx/src/helpers/scene_graph.cpp:130-138,478-489 */
+    RTB_BUF_COUNT = 11
+} rtb_buffer;
+
+/* Passes: one per reference Dispatch, plus the whole frame. */
+typedef enum rtb_pass {
+    RTB_PASS_INIT = 0,       /* init.comp        ref: src/rt/task/composite_task.cpp:260-264 */
+    RTB_PASS_RAYGEN = 1,     /* raygen.comp      ref: src/rt/task/raygen_task.cpp:88-94 */
+    RTB_PASS_SHADOW = 2,     /* shadow.comp      ref: src/rt/task/shadow_task.cpp:194-204 */
+    RTB_PASS_LIGHTING = 3,   /* lighting.comp    ref: src/rt/task/shadow_task.cpp:206-210 */
+    RTB_PASS_COMPOSITE = 4,  /* composite.comp   ref: src/rt/task/composite_task.cpp:266-276 */
+    RTB_PASS_FRAME = 5       /* the recorded command list replayed once: INIT..COMPOSITE
+                                ref: src/rt/raytracing_interface.cpp:144-179 */
+} rtb_pass;
+
+/* Render targets that can be read back: one per reference texture / buffer written by the path. */
+typedef enum rtb_target {
+    RTB_TGT_DIR_T = 0,        /* rgba32f  w*h*16 B   ref: src/rt/task/raygen_task.cpp:18-20 */
+    RTB_TGT_UV_NORMAL = 1,    /* rgba32f  w*h*16 B */
+    RTB_TGT_SHADOW_BITS = 2,  /* u32[ceil(w/16)*ceil(h/2)*samples]  ref: src/rt/task/shadow_task.cpp:146-165 */
+    RTB_TGT_LIGHTING = 3,     /* rgba16f  w*h*8 B    ref: src/rt/task/shadow_task.cpp:20-22 */
+    RTB_TGT_ACCUM = 4,        /* rgba32f  w*h*16 B   ref: src/rt/task/composite_task.cpp:20-22 */
+    RTB_TGT_RGBA8 = 5,        /* rgba8    w*h*4 B    (what presentToCpu copies out) */
+    RTB_TGT_SEED = 6,         /* 24 B: the Seed buffer after K0 */
+    RTB_TGT_RGBA8_TILED = 7,  /* multi-GPU only: this rank's pixels in wavefront-slot order, local_slots*4 B (see rtb_untile) */
+    RTB_TGT_COUNT = 8
+} rtb_target;
+
+/* How the nearest-hit search runs.  The reference has exactly one way: a linear loop over every
+ * primitive (ref: res/shaders/trace.glsl:25-45,78-94).  BVH is new and returns the same hits. */
+typedef enum rtb_accel_mode {
+    RTB_ACCEL_BRUTE = 0,   /* the reference algorithm, verbatim, on the GPU */
+    RTB_ACCEL_BVH = 1      /* triangles through the BVH; spheres, cubes, planes stay linear */
+} rtb_accel_mode;
+
+typedef struct rtb_accel_info {
+    uint32_t mode;            /* rtb_accel_mode in effect */
+    uint32_t node_count;      /* BVH nodes */
+    uint32_t node_bytes;      /* bytes per node record */
+    uint32_t leaf_count;
+    uint32_t max_depth;
+    uint32_t tri_record_bytes;/* bytes per traversal triangle record */
+    float    sah_cost;
+    float    build_ms;        /* host wall clock of the last build */
+} rtb_accel_info;
+
+/* Counters of the last instrumented dispatch (rtb_set_option(RTB_OPT_COUNTERS, 1)); the timed build
+ * never touches them.  Used for the roofline's algorithmic bytes per ray. */
+typedef struct rtb_counters {
+    uint64_t primary_rays, shadow_rays;          /* rays handed to the nearest-hit / occlusion search */
+    uint64_t primary_nodes, primary_tris;        /* node records fetched, triangle records tested */
+    uint64_t shadow_nodes, shadow_tris;
+    uint64_t primary_hits, shadow_occluded;
+} rtb_counters;
+
+typedef enum rtb_option {
+    RTB_OPT_COUNTERS = 0,     /* 0/1: run the instrumented traversal kernels */
+    RTB_OPT_TILE_RANK = 1,    /* multi-GPU screen partition: this context renders tiles t with t % count == rank */
+    RTB_OPT_TILE_COUNT = 2,
+    RTB_OPT_SKIP_PARITY_STORES = 3 /* 0/1: RELEASE-shader behaviour (no uvObjectNormal/lighting store on misses) is NOT
+                                      modelled; reserved, must be 0 */
+} rtb_option;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+/* replaces ignis::Graphics + FactoryContainer creation (ref: test/main.cpp:8-12) */
+int  rtb_create(rtb_ctx** out, int cuda_device, const rtb_limits* limits);
+void rtb_destroy(rtb_ctx* ctx);
+const char* rtb_last_error(const rtb_ctx* ctx);   /* ctx may be NULL: error of the last failed rtb_create */
+int  rtb_set_option(rtb_ctx* ctx, rtb_option opt, uint32_t value);
+/* run on a caller-owned cudaStream_t (passed as void*); NULL = the context's own stream */
+int  rtb_set_stream(rtb_ctx* ctx, void* cuda_stream);
+
+/* ---- resources ----------------------------------------------------------------------------------- */
+/* replaces TextureRenderTask::resize / ShadowTask::resize / CompositeTask::resize
+ * (ref: igx/include/helpers/render_task.hpp:67-97, src/rt/task/shadow_task.cpp:139-187,
+ *  src/rt/task/composite_task.cpp:205-233) */
+int  rtb_resize(rtb_ctx* ctx, uint32_t width, uint32_t height, uint32_t shadow_samples);
+/* replaces GPUBuffer::getBuffer()+flush() and cmd::FlushBuffer
+ * (ref: IGNIS/include/graphics/command/commands.hpp FlushBuffer; call sites listed per rtb_buffer) */
+int  rtb_upload(rtb_ctx* ctx, rtb_buffer id, size_t byte_offset, size_t bytes, const void* src);
+/* replaces cmd::FlushImage(skybox) (ref: igx/src/helpers/scene_graph.cpp:97-101,253-257).
+ * rgba16f, row 0 first, w*h*8 bytes; w == 0 or pixels == NULL removes the skybox (camera.skyboxColor is used). */
+int  rtb_upload_skybox(rtb_ctx* ctx, uint32_t width, uint32_t height, const uint16_t* rgba16f);
+/* NEW (no reference counterpart): (re)build the acceleration structure over the uploaded triangles.
+ * Must be called after triangle uploads and before a dispatch when mode == RTB_ACCEL_BVH. */
+int  rtb_build_accel(rtb_ctx* ctx, rtb_accel_mode mode);
+int  rtb_accel_info_get(const rtb_ctx* ctx, rtb_accel_info* out);
+
+/* ---- execution ----------------------------------------------------------------------------------- */
+/* replaces cmd::BindPipeline + cmd::BindDescriptors + cmd::Dispatch (ref: IGNIS/api/opengl/src/graphics/
+ * command/gl_command_list.cpp:311-335); asynchronous, stream-ordered */
+int  rtb_dispatch(rtb_ctx* ctx, rtb_pass pass);
+/* replaces Graphics::presentToCpu + wait (ref: src/rt/raytracing_interface.cpp:222-226,
+ * IGNIS/api/opengl/src/graphics/gl_graphics.cpp:221-242); blocks until the copy has landed */
+int  rtb_readback(rtb_ctx* ctx, rtb_target target, void* dst, size_t bytes);
+/* device address of a target (for zero-copy consumers such as an NCCL gather); valid until the next rtb_resize */
+int  rtb_device_ptr(rtb_ctx* ctx, rtb_target target, void** out_ptr, size_t* out_bytes);
+/* Multi-GPU presentation (no reference counterpart; the reference is single-GPU).  With RTB_OPT_TILE_COUNT = n > 1 each
+ * context renders the 32x32-pixel screen blocks b with b % n == rank and leaves them in RTB_TGT_RGBA8_TILED.  After the
+ * caller has gathered the n tiled buffers (NCCL) into one DEVICE array of n * slots_per_rank words on this context's
+ * GPU, rtb_untile writes the scan-line rgba8 frame to rgba8_out_device (NULL: into RTB_TGT_RGBA8).  Stream-ordered. */
+int  rtb_untile(rtb_ctx* ctx, const void* tiled_all_device, uint32_t nranks, uint32_t slots_per_rank, void* rgba8_out_device);
+/* replaces Graphics::wait (ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:546-595) */
+int  rtb_sync(rtb_ctx* ctx);
+int  rtb_counters_get(rtb_ctx* ctx, rtb_counters* out);
+/* milliseconds spent in each pass of the last RTB_PASS_FRAME (CUDA events): init, raygen(+nearest hit),
+ * shadow, lighting+composite, total.  Synchronises. */
+int  rtb_last_frame_ms(rtb_ctx* ctx, float out_ms[5]);
+
+/* ---- rays-in mode (parity harness: same traversal, explicit rays) --------------------------------- */
+/* rays: n * 6 floats (origin, dir) in HOST memory; prev: n object ids to exclude or NULL (= none).
+ * Outputs (host): object id (0xFFFFFFFF on a miss), t (3.4028235e38 on a miss), uv (2 floats) — any may be NULL. */
+int  rtb_trace_rays(rtb_ctx* ctx, const float* rays, uint64_t n, const uint32_t* prev,
+                    uint32_t* object, float* t, float* uv);
+/* occluded[i] = 1 when any primitive other than prev[i] is hit at a distance < max_dist[i] (NULL: 3.4028235e38) */
+int  rtb_occlusion_rays(rtb_ctx* ctx, const float* rays, uint64_t n, const float* max_dist,
+                        const uint32_t* prev, uint8_t* occluded);
+
+/* ---- host-side packing (the igx:: POD constructors; see include/igx_rt.hpp for the C++ faces) ------ */
+/* ref: igx/include/types/scene_object_types.hpp:98-106 (3-point ctor) and :87-96 (with normals) */
+void rtb_pack_triangle(const float p[9], const float* normals9_or_null, void* out48);
+/* ref: scene_object_types.hpp:166-171 / :173-179 */
+void rtb_pack_light_directional(const float dir[3], const float color[3], float angular_extent, void* out32);
+void rtb_pack_light_point(const float pos[3], const float color[3], float rad, float origin, float specularity, void* out32);
+/* ref: scene_object_types.hpp:267-288 */
+void rtb_pack_material(const float albedo[3], const float ambient[3], const float emission[3],
+                       float metallic, float roughness, float transparency, void* out32);
+/* CPUCamera::getView + RaytracingInterface::resize/update (ref: src/rt/structs.cpp:5-42,
+ * src/rt/raytracing_interface.cpp:96-107,279-328).  Angles in radians, fov in degrees. */
+void rtb_pack_camera(const float eye[3], float pitch, float yaw, float roll, float left_fov, float right_fov,
+                     float ipd, uint32_t projection, uint32_t width, uint32_t height, uint32_t flags,
+                     float exposure, const float skybox_color[3], void* out144);
+/* Radiance .hdr -> rgba16f the way igxi-convert does (ref: igx/igxi-tool/src/igxi/convert.cpp:59-78,148-153,209-231).
+ * out == NULL only queries the size. */
+int  rtb_load_hdr(const char* path, uint16_t* out, uint32_t* width, uint32_t* height);
+
+/* ---- synthetic scenes of BASELINE.json (no reference counterpart; deterministic) ------------------- */
+/* n flat-shaded triangles: centre uniform in [-10,10]^3, three offsets uniform in [-0.05,0.05]^3 */
+void rtb_gen_soup(uint64_t n, uint64_t seed, void* out_triangles48);
+/* (grid x grid) quads of a displaced height field over [-10,10]^2, smooth normals: 2*grid*grid triangles */
+void rtb_gen_heightfield(uint32_t grid, uint64_t seed, void* out_triangles48);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,305 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): nearest-hit ids exact except rays the oracle flags (edge / tie / parallel /
+NaN); t within 1e-5 relative; final RGB within 1/255.  The kernels evaluate the shader arithmetic in the
+oracle's operation order with -fmad=false, so in practice everything below is compared bit-for-bit and
+the tolerances are only a budget for the rare 1-ulp difference between CUDA's and glibc's binary64
+transcendentals (each test states its budget).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NO_RAY_HIT = 0xFFFFFFFF
+
+
+def to_oracle_scene(scene, sky=None):
+    from oracle.oracle import Scene
+    return Scene(scene.get("triangles"), scene.get("spheres"), scene.get("cubes"), scene.get("planes"), scene.get("lights"),
+                 scene.get("materials"), scene.get("material_indices"), scene.get("info"), sky)
+
+
+def make_ctx(rtb, scene, sky, w, h, samples, accel, **limits):
+    ctx = rtb.Context(**limits)
+    ctx.resize(w, h, samples)
+    ctx.upload_scene(scene, sky)
+    ctx.build_accel(accel)
+    return ctx
+
+
+def frame_both(rtb, oracle, scene, sky, cam_kwargs, w, h, samples, accel, cpu_offset=(0.0, 0.0), frames=1, limits=None):
+    ctx = make_ctx(rtb, scene, sky, w, h, samples, accel, **(limits or {}))
+    cam = rtb.pack_camera(w, h, **cam_kwargs)
+    ocam = oracle.camera(w, h, **cam_kwargs)
+    assert np.array_equal(cam, ocam), "camera packing differs from the oracle"
+    ctx.upload(rtb.BUF_CAMERA, cam)
+    ctx.upload(rtb.BUF_SEED, rtb.make_seed(cpu_offset))
+    oseed = oracle.seed(cpu_offset)
+    osc = to_oracle_scene(scene, sky)
+    accum = np.zeros((h, w, 4), np.float32)
+    for _ in range(frames):
+        ctx.dispatch(rtb.PASS_FRAME)
+        ref = oracle.frame(osc, ocam, oseed, samples, accum=accum)
+    got = dict(dirT=ctx.readback(rtb.TGT_DIR_T), uvN=ctx.readback(rtb.TGT_UV_NORMAL), bits=ctx.readback(rtb.TGT_SHADOW_BITS),
+               lighting=ctx.readback(rtb.TGT_LIGHTING), rgba8=ctx.readback(rtb.TGT_RGBA8), accum=ctx.readback(rtb.TGT_ACCUM),
+               seed=ctx.readback(rtb.TGT_SEED))
+    ref["accum"] = accum
+    ref["seed"] = oseed
+    ctx.close()
+    return got, ref
+
+
+def check_frame(got, ref, w, h, budget=2e-5, rgb_budget=2e-5):
+    n = w * h
+    assert np.array_equal(got["seed"], ref["seed"]), "Seed after init.comp differs"
+    gid, rid = got["dirT"][..., 3].view(np.uint32), ref["dirT"][..., 3].view(np.uint32)
+    bad_id = int((gid != rid).sum())
+    assert bad_id <= budget * n, f"{bad_id} of {n} hit ids differ"
+    same = gid == rid
+    gd, rd = got["dirT"][..., :3].view(np.uint32), ref["dirT"][..., :3].view(np.uint32)
+    bad_bits = int((gd[same] != rd[same]).any(axis=-1).sum())
+    assert bad_bits <= budget * n, f"{bad_bits} of {n} dirT vectors differ bitwise"
+    # stated bar: |t| within 1e-5 relative
+    gt, rt_ = np.linalg.norm(got["dirT"][..., :3][same].astype(np.float64), axis=-1), np.linalg.norm(ref["dirT"][..., :3][same].astype(np.float64), axis=-1)
+    rel = np.abs(gt - rt_) / np.maximum(np.abs(rt_), 1e-30)
+    assert int((rel > 1e-5).sum()) <= budget * n
+    bad_uvn = int((got["uvN"].view(np.uint32)[same] != ref["uvN"].view(np.uint32)[same]).any(axis=-1).sum())
+    assert bad_uvn <= budget * n, f"{bad_uvn} uvObjectNormal texels differ"
+    bad_words = int((got["bits"] != ref["bits"]).sum())
+    assert bad_words <= max(2, budget * n), f"{bad_words} shadow-mask words differ"
+    bad_l = int((got["lighting"] != ref["lighting"]).any(axis=-1).sum())
+    assert bad_l <= max(4, 4 * budget * n), f"{bad_l} lighting texels differ"
+    g8, r8 = got["rgba8"].view(np.uint8).reshape(h, w, 4).astype(np.int32), ref["rgba8"].view(np.uint8).reshape(h, w, 4).astype(np.int32)
+    diff = np.abs(g8 - r8).max(axis=-1)
+    assert int((diff > 1).sum()) <= max(4, 4 * rgb_budget * n), f"{int((diff > 1).sum())} pixels differ by more than 1/255"
+    assert int((diff > 0).sum()) <= max(8, 50 * rgb_budget * n), f"{int((diff > 0).sum())} pixels differ at all"
+
+
+POSES = {
+    "default": dict(eye=(4, 2, -2)),
+    "all_objects": dict(eye=(6, 5, 12)),
+    "inside_cube": dict(eye=(0.5, 0.5, 0.5)),
+    "grazing_plane": dict(eye=(4, 1e-3, -2)),
+    "rotated": dict(eye=(6, 5, 12), pitch=0.2, yaw=0.4, roll=0.1),
+}
+
+
+@pytest.mark.parametrize("accel", ["brute", "bvh"])
+@pytest.mark.parametrize("pose", list(POSES))
+def test_niels_frame(rtb, oracle, sky, pose, accel):
+    """BASELINE config 1: NielsScene t=0, 640x360, 1 primary + 1 shadow sample; full-frame compare of every target."""
+    w, h = 640, 360
+    scene = rtb.niels_scene(0.0)
+    osc = oracle.niels_scene(0.0)
+    for k in ("triangles", "spheres", "cubes", "planes", "lights", "materials"):
+        assert np.array_equal(scene[k], getattr(osc, k)), f"NielsScene {k} differ from the oracle's"
+    got, ref = frame_both(rtb, oracle, scene, sky, POSES[pose], w, h, 1, rtb.ACCEL_BVH if accel == "bvh" else rtb.ACCEL_BRUTE)
+    check_frame(got, ref, w, h)
+    if pose == "all_objects":
+        ids = set(np.unique(got["dirT"][..., 3].view(np.uint32)).tolist()) - {NO_RAY_HIT}
+        assert ids == set(range(13)), "pose must exercise all 13 objects"
+
+
+def test_niels_no_skybox_two_samples(rtb, oracle):
+    w, h = 320, 180
+    got, ref = frame_both(rtb, oracle, rtb.niels_scene(0.7), None, POSES["all_objects"], w, h, 2, rtb.ACCEL_BVH, cpu_offset=(12.5, -431.25))
+    check_frame(got, ref, w, h)
+
+
+def test_ragged_size(rtb, oracle, sky):
+    """Sizes that are not multiples of the 32x32 block, the 16x2 shadow strip or the 8x4 warp patch."""
+    w, h = 333, 127
+    got, ref = frame_both(rtb, oracle, rtb.niels_scene(0.0), sky, POSES["all_objects"], w, h, 3, rtb.ACCEL_BVH)
+    check_frame(got, ref, w, h)
+
+
+def test_progressive_accumulation(rtb, oracle, sky):
+    """USE_SUPERSAMPLING: replaying the frame accumulates in fp32 (composite.comp:249-257)."""
+    w, h = 320, 180
+    cam = dict(POSES["all_objects"], flags=2)
+    got, ref = frame_both(rtb, oracle, rtb.niels_scene(0.0), sky, cam, w, h, 1, rtb.ACCEL_BVH, cpu_offset=(3.0, 9.0), frames=4)
+    assert got["seed"][16:].view(np.uint32)[0] == 4
+    check_frame(got, ref, w, h, budget=1e-4, rgb_budget=1e-4)
+    bad = int((got["accum"].view(np.uint32) != ref["accum"].view(np.uint32)).any(axis=-1).sum())
+    assert bad <= 1e-3 * w * h, f"{bad} accumulation texels differ"
+
+
+@pytest.mark.parametrize("projection", [1, 2, 3, 4, 5])
+def test_projection_modes(rtb, oracle, sky, projection):
+    w, h = 256, 128
+    cam = dict(eye=(6, 5, 12), projection=projection, yaw=0.3)
+    got, ref = frame_both(rtb, oracle, rtb.niels_scene(0.0), sky, cam, w, h, 1, rtb.ACCEL_BVH)
+    check_frame(got, ref, w, h, budget=1e-4, rgb_budget=1e-4)
+
+
+def test_point_light_first(rtb, oracle, sky):
+    """lights[0] a point light: exercises the point branch of getDirToLight and the ranged occlusion test."""
+    w, h = 320, 180
+    scene = rtb.niels_scene(0.0)
+    lights = scene["lights"].reshape(3, 32)
+    scene["lights"] = np.concatenate([lights[2], lights[1], lights[0]])   # the host would never order them so; the shaders do not care
+    got, ref = frame_both(rtb, oracle, scene, sky, POSES["all_objects"], w, h, 2, rtb.ACCEL_BVH)
+    check_frame(got, ref, w, h, budget=1e-4, rgb_budget=1e-4)
+    assert got["bits"].any(), "some pixel must be shadowed from the point light"
+
+
+def soup_scene(rtb, n, seed=0xB200):
+    tris = rtb.gen_soup(n, seed)
+    mat = rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0)
+    sun = rtb.niels_scene()["lights"][:32]
+    return dict(triangles=tris, lights=sun, materials=mat, material_indices=np.zeros(n, np.uint32),
+                info=np.array([1, 1, n, 0, 0, 0, 1, 0, 0], np.uint32))
+
+
+def camera_rays(oracle, w, h, n, eye, rng):
+    """n primary rays of a w x h view (oracle camera maths), returned as (n, 6)."""
+    cam = oracle.camera(w, h, eye=eye)
+    from oracle.oracle import Scene
+    empty = Scene(info=[0] * 9)
+    seed = oracle.init_pass(oracle.seed((1.0, 2.0)))
+    _, _, rays, _ = oracle.raygen(empty, cam, seed, want_rays=True)
+    rays = rays.reshape(-1, 6)
+    return rays[rng.choice(rays.shape[0], n, replace=False)]
+
+
+@pytest.mark.parametrize("accel", ["brute", "bvh"])
+def test_soup_rays_in(rtb, oracle, accel):
+    """Random-soup triangles, explicit rays: ids exact on unflagged rays, t bit-exact where ids agree."""
+    n_tri, n_rays = 50_000, 8192
+    scene = soup_scene(rtb, n_tri)
+    rng = np.random.default_rng(1)
+    rays = camera_rays(oracle, 512, 288, n_rays, (0, 0, 30), rng)
+    osc = to_oracle_scene(scene)
+    oid, ot, ouv, _, flags = oracle.trace_rays(osc, rays, want_flags=True)
+    ctx = rtb.Context(max_triangles=n_tri)
+    ctx.upload_scene(scene)
+    ctx.build_accel(rtb.ACCEL_BVH if accel == "bvh" else rtb.ACCEL_BRUTE)
+    gid, gt, guv = ctx.trace_rays(rays)
+    ctx.close()
+    assert (oid != NO_RAY_HIT).mean() > 0.3, "the sample must hit something"
+    unflagged = flags == 0
+    assert unflagged.mean() > 0.97, f"flagged fraction {1 - unflagged.mean():.4f} is implausibly high"
+    assert np.array_equal(gid[unflagged], oid[unflagged]), f"{int((gid[unflagged] != oid[unflagged]).sum())} unflagged ids differ"
+    same = gid == oid
+    assert same.mean() > 0.999
+    assert np.array_equal(gt[same].view(np.uint32), ot[same].view(np.uint32)), "t must be bit-exact where ids agree"
+    assert np.array_equal(guv[same].view(np.uint32), ouv[same].view(np.uint32))
+
+
+def test_soup_occlusion_rays(rtb, oracle):
+    n_tri, n_rays = 50_000, 8192
+    scene = soup_scene(rtb, n_tri)
+    rng = np.random.default_rng(2)
+    o = rng.uniform(-9, 9, (n_rays, 3)).astype(np.float32)
+    d = rng.normal(size=(n_rays, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    rays = np.concatenate([o, d], axis=1).astype(np.float32)
+    max_dist = np.where(rng.random(n_rays) < 0.5, np.float32(3.4028235e38), rng.uniform(0.1, 6.0, n_rays)).astype(np.float32)
+    prev = rng.integers(0, n_tri, n_rays).astype(np.uint32)
+    want = oracle.occlusion_rays(to_oracle_scene(scene), rays, max_dist, prev)
+    ctx = rtb.Context(max_triangles=n_tri)
+    ctx.upload_scene(scene)
+    for mode in (rtb.ACCEL_BRUTE, rtb.ACCEL_BVH):
+        ctx.build_accel(mode)
+        got = ctx.occlusion_rays(rays, max_dist, prev)
+        assert int((got != want).sum()) <= 2, f"mode {mode}: {int((got != want).sum())} occlusion results differ"
+    ctx.close()
+    assert 0.05 < want.mean() < 0.95
+
+
+def test_niels_occlusion_rays_all_primitives(rtb, oracle):
+    """Occlusion through spheres, cubes (incl. origin inside: negative tmin) and the plane."""
+    scene = rtb.niels_scene(0.0)
+    rng = np.random.default_rng(3)
+    n = 20000
+    o = rng.uniform(-6, 8, (n, 3)).astype(np.float32)
+    o[: n // 10] = rng.uniform(0.05, 0.95, (n // 10, 3)).astype(np.float32)   # inside cube [0,1]^3
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    rays = np.concatenate([o, d], axis=1).astype(np.float32)
+    max_dist = np.where(rng.random(n) < 0.5, np.float32(3.4028235e38), rng.uniform(0.0, 10.0, n)).astype(np.float32)
+    prev = rng.integers(0, 14, n).astype(np.uint32)
+    want = oracle.occlusion_rays(to_oracle_scene(scene), rays, max_dist, prev)
+    ctx = rtb.Context()
+    ctx.upload_scene(scene)
+    for mode in (rtb.ACCEL_BRUTE, rtb.ACCEL_BVH):
+        ctx.build_accel(mode)
+        got = ctx.occlusion_rays(rays, max_dist, prev)
+        assert np.array_equal(got, want), f"mode {mode}: {int((got != want).sum())} differ"
+        gid, gt, guv = ctx.trace_rays(rays, prev)
+        oid, ot, ouv, _, fl = oracle.trace_rays(to_oracle_scene(scene), rays, prev, want_flags=True)
+        ok = fl == 0
+        assert np.array_equal(gid[ok], oid[ok])
+        same = gid == oid
+        assert np.array_equal(gt[same].view(np.uint32), ot[same].view(np.uint32))
+    ctx.close()
+
+
+def test_soup_full_size_bvh_equals_brute(rtb):
+    """BASELINE config 3 geometry (1M-triangle soup): the BVH search returns what the reference's linear loop
+    returns, on a reduced frame (the brute-force kernel is the at-scale stand-in for the oracle)."""
+    n_tri, w, h = 1_000_000, 480, 270
+    scene = soup_scene(rtb, n_tri)
+    out = {}
+    for mode in (rtb.ACCEL_BVH, rtb.ACCEL_BRUTE):
+        ctx = make_ctx(rtb, scene, None, w, h, 1, mode, max_triangles=n_tri)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 30)))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+        ctx.dispatch(rtb.PASS_FRAME)
+        out[mode] = (ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8))
+        if mode == rtb.ACCEL_BVH:
+            info = ctx.accel_info()
+            assert info.node_count > n_tri // 8 and info.max_depth <= 60
+        ctx.close()
+    a, b = out[rtb.ACCEL_BVH], out[rtb.ACCEL_BRUTE]
+    n = w * h
+    ids_a, ids_b = a[0][..., 3].view(np.uint32), b[0][..., 3].view(np.uint32)
+    assert (ids_a != NO_RAY_HIT).mean() > 0.5
+    assert int((ids_a != ids_b).sum()) <= 1e-4 * n, f"{int((ids_a != ids_b).sum())} ids differ between BVH and brute force"
+    same = ids_a == ids_b
+    assert np.array_equal(a[0].view(np.uint32)[same], b[0].view(np.uint32)[same])
+    assert int((a[1] != b[1]).sum()) <= 1e-4 * n
+    assert int((a[2] != b[2]).sum()) <= 2e-4 * n
+
+
+def test_tile_partition_matches_single(rtb, sky):
+    """Two contexts rendering interleaved screen blocks + rtb_untile == one context rendering everything."""
+    import ctypes as C
+    w, h = 333, 200
+    scene = rtb.niels_scene(0.0)
+    cam = rtb.pack_camera(w, h, eye=(6, 5, 12))
+
+    def render(rank, count):
+        ctx = rtb.Context()
+        ctx.set_option(rtb.OPT_TILE_COUNT, count)
+        ctx.set_option(rtb.OPT_TILE_RANK, rank)
+        ctx.resize(w, h, 2)
+        ctx.upload_scene(scene, sky)
+        ctx.build_accel(rtb.ACCEL_BVH)
+        ctx.upload(rtb.BUF_CAMERA, cam)
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((5.0, 6.0)))
+        ctx.dispatch(rtb.PASS_FRAME)
+        return ctx
+
+    single = render(0, 1)
+    want = single.readback(rtb.TGT_RGBA8)
+    single.close()
+    import torch
+    parts = [render(r, 3) for r in range(3)]
+    slots = max(p.device_ptr(rtb.TGT_RGBA8_TILED)[1] // 4 for p in parts)
+    gathered = torch.zeros(3 * slots, dtype=torch.int32, device="cuda")
+    for r, p in enumerate(parts):
+        ptr, nbytes = p.device_ptr(rtb.TGT_RGBA8_TILED)
+        p.sync()
+        tmp = np.zeros(nbytes // 4, np.uint32)
+        p.readback_into(rtb.TGT_RGBA8_TILED, tmp.ctypes.data, nbytes)
+        gathered[r * slots: r * slots + tmp.size] = torch.from_numpy(tmp.view(np.int32)).cuda()
+    out = torch.zeros(h * w, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    parts[0].untile(gathered.data_ptr(), 3, slots, out.data_ptr())
+    parts[0].sync()
+    got = out.cpu().numpy().view(np.uint32).reshape(h, w)
+    for p in parts:
+        p.close()
+    assert np.array_equal(got, want)
