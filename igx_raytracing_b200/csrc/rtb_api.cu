@@ -69,7 +69,7 @@ struct rtb_ctx {
     // rays-in scratch
     DevBuf<RayRec> rinRays; DevBuf<TriHit> rinHits; DevBuf<uint32_t> rinObj; DevBuf<float> rinT; DevBuf<float2> rinUv; DevBuf<uint8_t> rinOcc, rinOcc2;
 
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // frame-phase boundaries
     bool frameTimed = false;
 };
 
@@ -110,7 +110,7 @@ int allocFrame(rtb_ctx* c) {
     RTB_CUDA(c, c->dirT.alloc(px)); RTB_CUDA(c, c->uvN.alloc(px)); RTB_CUDA(c, c->accum.alloc(px));
     RTB_CUDA(c, c->lighting.alloc(px)); RTB_CUDA(c, c->rgba8.alloc(px));
     RTB_CUDA(c, c->bits.alloc(shadowWords(c->width, c->height, c->samples)));
-    RTB_CUDA(c, c->rgba8Tiled.alloc(c->fm.localSlots));
+    RTB_CUDA(c, c->rgba8Tiled.alloc((size_t)((c->fm.blocksX * c->fm.blocksY + c->fm.nranks - 1) / c->fm.nranks) * 1024u));
     RTB_CUDA(c, c->rays.alloc((size_t)c->fm.localSlots * (c->samples ? c->samples : 1)));
     RTB_CUDA(c, c->hits.alloc(c->fm.localSlots));
     // pixels owned by other ranks are never written: keep them defined
@@ -136,17 +136,21 @@ int checkReady(rtb_ctx* c) {
     return RTB_OK;
 }
 
-int passRaygen(rtb_ctx* c) {
+// `mark` (frame dispatch only) records an event after each phase so the traversal launches can be timed alone
+int passRaygen(rtb_ctx* c, bool mark) {
     const SceneView sv = sceneView(c);
     launch_raygen(c->fm, &c->camera, c->seed.p, c->rays.p, c->stream);
+    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     launch_trace_closest(sv, c->rays.p, c->fm.localSlots, c->hits.p, c->workCounter.p, c->countersOn ? c->counters.p : nullptr, c->stream);
+    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     launch_finish_primary(c->fm, sv, c->rays.p, c->hits.p, c->dirT.p, c->uvN.p, c->stream);
     return RTB_OK;
 }
-int passShadow(rtb_ctx* c) {
+int passShadow(rtb_ctx* c, bool mark) {
     const SceneView sv = sceneView(c);
     RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, c->samples) * 4, c->stream));
     launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, c->stream);
+    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     launch_trace_any_bits(c->fm, sv, c->rays.p, c->fm.localSlots * c->samples, c->bits.p, c->workCounter.p, c->countersOn ? c->counters.p + 1 : nullptr, c->stream);
     return RTB_OK;
 }
@@ -341,8 +345,8 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
     int rc = RTB_OK;
     switch (pass) {
         case RTB_PASS_INIT: launch_init(c->seed.p, c->stream); break;
-        case RTB_PASS_RAYGEN: rc = passRaygen(c); break;
-        case RTB_PASS_SHADOW: rc = passShadow(c); break;
+        case RTB_PASS_RAYGEN: rc = passRaygen(c, false); break;
+        case RTB_PASS_SHADOW: rc = passShadow(c, false); break;
         case RTB_PASS_LIGHTING: rc = passShade(c, SHADE_LIGHTING); break;
         case RTB_PASS_COMPOSITE: rc = passShade(c, SHADE_COMPOSITE); break;
         case RTB_PASS_FRAME:
@@ -350,12 +354,12 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
             RTB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
             launch_init(c->seed.p, c->stream);
             RTB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-            if ((rc = passRaygen(c))) return rc;
-            RTB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-            if ((rc = passShadow(c))) return rc;
-            RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
-            if ((rc = passShade(c, SHADE_BOTH))) return rc;
+            if ((rc = passRaygen(c, true))) return rc;
             RTB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+            if ((rc = passShadow(c, true))) return rc;
+            RTB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+            if ((rc = passShade(c, SHADE_BOTH))) return rc;
+            RTB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
             c->frameTimed = true;
             break;
         default: return fail(c, RTB_ERR_ARG, "rtb_dispatch: unknown pass");
@@ -377,7 +381,7 @@ int rtb_device_ptr(rtb_ctx* c, rtb_target t, void** out, size_t* bytes) {
         case RTB_TGT_ACCUM: p = c->accum.p; n = px * 16; break;
         case RTB_TGT_RGBA8: p = c->rgba8.p; n = px * 4; break;
         case RTB_TGT_SEED: p = c->seed.p; n = sizeof(SeedRec); break;
-        case RTB_TGT_RGBA8_TILED: p = c->rgba8Tiled.p; n = (size_t)c->fm.localSlots * 4; break;
+        case RTB_TGT_RGBA8_TILED: p = c->rgba8Tiled.p; n = (size_t)((c->fm.blocksX * c->fm.blocksY + c->fm.nranks - 1) / c->fm.nranks) * 4096u; break;
         default: return fail(c, RTB_ERR_ARG, "unknown target");
     }
     if (t != RTB_TGT_SEED && !px) return fail(c, RTB_ERR_STATE, "no frame resources before rtb_resize");
@@ -428,13 +432,13 @@ int rtb_counters_get(rtb_ctx* c, rtb_counters* out) {
     return RTB_OK;
 }
 
-int rtb_last_frame_ms(rtb_ctx* c, float ms[5]) {
+int rtb_last_frame_ms(rtb_ctx* c, float ms[8]) {
     if (!c || !ms) return RTB_ERR_ARG;
     RTB_BIND(c);
     if (!c->frameTimed) return fail(c, RTB_ERR_STATE, "no RTB_PASS_FRAME has been dispatched yet");
-    RTB_CUDA(c, cudaEventSynchronize(c->ev[4]));
-    for (int i = 0; i < 4; ++i) RTB_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
-    RTB_CUDA(c, cudaEventElapsedTime(&ms[4], c->ev[0], c->ev[4]));
+    RTB_CUDA(c, cudaEventSynchronize(c->ev[7]));
+    for (int i = 0; i < 7; ++i) RTB_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    RTB_CUDA(c, cudaEventElapsedTime(&ms[7], c->ev[0], c->ev[7]));
     return RTB_OK;
 }
 

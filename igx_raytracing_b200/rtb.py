@@ -76,7 +76,7 @@ def lib() -> C.CDLL:
         L.rtb_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
         L.rtb_sync.argtypes = [vp]
         L.rtb_counters_get.argtypes = [vp, C.POINTER(Counters)]
-        L.rtb_last_frame_ms.argtypes = [vp, C.POINTER(f * 5)]
+        L.rtb_last_frame_ms.argtypes = [vp, C.POINTER(f * 8)]
         L.rtb_trace_rays.argtypes = [vp, vp, u64, vp, vp, vp, vp]
         L.rtb_occlusion_rays.argtypes = [vp, vp, u64, vp, vp, vp]
         L.rtb_untile.argtypes = [vp, vp, u32, u32, vp]
@@ -290,7 +290,7 @@ class Context:
         return c
 
     def last_frame_ms(self):
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * 8)()
         self._ck(self.L.rtb_last_frame_ms(self.h, C.byref(ms)))
         return list(ms)
 

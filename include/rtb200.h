@@ -76,7 +76,7 @@ typedef enum rtb_target {
     RTB_TGT_ACCUM = 4,        /* rgba32f  w*h*16 B   ref: src/rt/task/composite_task.cpp:20-22 */
     RTB_TGT_RGBA8 = 5,        /* rgba8    w*h*4 B    (what presentToCpu copies out) */
     RTB_TGT_SEED = 6,         /* 24 B: the Seed buffer after K0 */
-    RTB_TGT_RGBA8_TILED = 7,  /* multi-GPU only: this rank's pixels in wavefront-slot order, local_slots*4 B (see rtb_untile) */
+    RTB_TGT_RGBA8_TILED = 7,  /* multi-GPU only: this rank's pixels in wavefront-slot order; ceil(blocks/n)*4096 B on every rank (see rtb_untile) */
     RTB_TGT_COUNT = 8
 } rtb_target;
 
@@ -157,9 +157,9 @@ int  rtb_untile(rtb_ctx* ctx, const void* tiled_all_device, uint32_t nranks, uin
 /* replaces Graphics::wait (ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:546-595) */
 int  rtb_sync(rtb_ctx* ctx);
 int  rtb_counters_get(rtb_ctx* ctx, rtb_counters* out);
-/* milliseconds spent in each pass of the last RTB_PASS_FRAME (CUDA events): init, raygen(+nearest hit),
- * shadow, lighting+composite, total.  Synchronises. */
-int  rtb_last_frame_ms(rtb_ctx* ctx, float out_ms[5]);
+/* milliseconds spent in each phase of the last RTB_PASS_FRAME (CUDA events on the context's stream): init, ray generation,
+ * nearest-hit traversal, G-buffer finish, shadow-ray set-up, occlusion traversal, lighting+composite, total.  Synchronises. */
+int  rtb_last_frame_ms(rtb_ctx* ctx, float out_ms[8]);
 
 /* ---- rays-in mode (parity harness: same traversal, explicit rays) --------------------------------- */
 /* rays: n * 6 floats (origin, dir) in HOST memory; prev: n object ids to exclude or NULL (= none).

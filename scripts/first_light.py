@@ -8,6 +8,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 w = int(sys.argv[2]) if len(sys.argv) > 2 else 3840
 h = int(sys.argv[3]) if len(sys.argv) > 3 else 2160
 frames = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+ez = float(sys.argv[5]) if len(sys.argv) > 5 else 13.9
 t0 = time.time()
 tris = rtb.gen_soup(n)
 mat = rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0)
@@ -20,7 +21,7 @@ t1 = time.time()
 ctx.build_accel(rtb.ACCEL_BVH)
 info = ctx.accel_info()
 print(f"gen+upload {t1 - t0:.2f}s  build {info.build_ms:.0f} ms nodes {info.node_count} leaves {info.leaf_count} depth {info.max_depth} sah {info.sah_cost:.1f}", flush=True)
-ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 30)))
+ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, ez)))
 ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
 ctx.set_option(rtb.OPT_COUNTERS, 1)
 ctx.dispatch(rtb.PASS_FRAME); ctx.sync()
@@ -33,4 +34,4 @@ rays = c.primary_rays + c.shadow_rays
 for i in range(frames):
     ctx.dispatch(rtb.PASS_FRAME)
     ms = ctx.last_frame_ms()
-    print(f"frame {i}: init {ms[0]:.3f} raygen+trace {ms[1]:.3f} shadow {ms[2]:.3f} shade {ms[3]:.3f} total {ms[4]:.3f} ms -> {rays / ms[4] / 1e3:.1f} Mrays/s", flush=True)
+    print(f"frame {i}: init {ms[0]:.3f} raygen {ms[1]:.3f} trace {ms[2]:.3f} finish {ms[3]:.3f} shgen {ms[4]:.3f} shtrace {ms[5]:.3f} shade {ms[6]:.3f} total {ms[7]:.3f} ms -> {rays / ms[7] / 1e3:.1f} Mrays/s", flush=True)

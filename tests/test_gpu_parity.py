@@ -169,7 +169,7 @@ def test_soup_rays_in(rtb, oracle, accel):
     n_tri, n_rays = 50_000, 8192
     scene = soup_scene(rtb, n_tri)
     rng = np.random.default_rng(1)
-    rays = camera_rays(oracle, 512, 288, n_rays, (0, 0, 30), rng)
+    rays = camera_rays(oracle, 512, 288, n_rays, (0, 0, 13.9), rng)   # every ray enters the soup volume
     osc = to_oracle_scene(scene)
     oid, ot, ouv, _, flags = oracle.trace_rays(osc, rays, want_flags=True)
     ctx = rtb.Context(max_triangles=n_tri)
@@ -177,7 +177,7 @@ def test_soup_rays_in(rtb, oracle, accel):
     ctx.build_accel(rtb.ACCEL_BVH if accel == "bvh" else rtb.ACCEL_BRUTE)
     gid, gt, guv = ctx.trace_rays(rays)
     ctx.close()
-    assert (oid != NO_RAY_HIT).mean() > 0.3, "the sample must hit something"
+    assert (oid != NO_RAY_HIT).mean() > 0.05, "the sample must hit something"
     unflagged = flags == 0
     assert unflagged.mean() > 0.97, f"flagged fraction {1 - unflagged.mean():.4f} is implausibly high"
     assert np.array_equal(gid[unflagged], oid[unflagged]), f"{int((gid[unflagged] != oid[unflagged]).sum())} unflagged ids differ"
@@ -244,7 +244,7 @@ def test_soup_full_size_bvh_equals_brute(rtb):
     out = {}
     for mode in (rtb.ACCEL_BVH, rtb.ACCEL_BRUTE):
         ctx = make_ctx(rtb, scene, None, w, h, 1, mode, max_triangles=n_tri)
-        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 30)))
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 13.9)))
         ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
         ctx.dispatch(rtb.PASS_FRAME)
         out[mode] = (ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8))
