@@ -213,7 +213,10 @@ def main():
     w, h, samples = wl["width"], wl["height"], wl["samples"]
     scene, limits = build_scene(rtb, wl)
     ctx = rtb.Context(device=local_rank, **limits)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream, made current: the library launches on it, so torch.cuda.Event timing and the
+    # NCCL gather see the kernels (the legacy default stream has handle 0, which rtb_set_stream reads as "own stream")
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_option(rtb.OPT_TILE_COUNT, world)
     ctx.set_option(rtb.OPT_TILE_RANK, rank)

@@ -362,6 +362,9 @@ public:
 
     const SceneGraphInfo& getInfo() const { return info; }
     const SceneGraphInfo& getLimits() const { return limits; }
+    // CPU mirrors (what the reference keeps in Object::cpuData / materialByObject)
+    const List<u32>& getMaterialIndices() const { return materialByObject; }
+    const u8* getCpuData(SceneObjectType t) const { return objects[u8(t)].cpuData.data(); }
     Device& getDevice() const { return device; }
     int error() const { return lastError; }
     rtb_accel_mode accelMode = RTB_ACCEL_BVH;
@@ -393,6 +396,7 @@ private:
         Object& obj = objects[u8(type)];
         const usz stride = strides[u8(type)];
         u32& count = info.objectCount[u8(type)];
+        if (!count) return;
         u8* cpuPtr = obj.cpuData.data();
         u8* gpuPtr = obj.gpuData.data();
         bool needsRemap = false;
@@ -457,7 +461,7 @@ private:
 
     List<bool> materialSent;
     bool materialUploaded(u32 g) { if (materialSent.size() <= g) materialSent.resize(usz(g) + 1, false); return materialSent[g]; }
-    void markMaterialUploaded(u32 g) { materialSent[g] = true; }
+    void markMaterialUploaded(u32 g) { if (materialSent.size() <= g) materialSent.resize(usz(g) + 1, false); materialSent[g] = true; }
 };
 
 // ---- RenderTask hierarchy (ref: igx/include/helpers/render_task.hpp:21-65) -------------------------------------

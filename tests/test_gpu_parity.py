@@ -166,7 +166,7 @@ def camera_rays(oracle, w, h, n, eye, rng):
 @pytest.mark.parametrize("accel", ["brute", "bvh"])
 def test_soup_rays_in(rtb, oracle, accel):
     """Random-soup triangles, explicit rays: ids exact on unflagged rays, t bit-exact where ids agree."""
-    n_tri, n_rays = 50_000, 8192
+    n_tri, n_rays = 300_000, 8192
     scene = soup_scene(rtb, n_tri)
     rng = np.random.default_rng(1)
     rays = camera_rays(oracle, 512, 288, n_rays, (0, 0, 13.9), rng)   # every ray enters the soup volume
@@ -303,3 +303,26 @@ def test_tile_partition_matches_single(rtb, sky):
     for p in parts:
         p.close()
     assert np.array_equal(got, want)
+
+
+def test_cpp_facade_renders_like_the_oracle(rtb, oracle, tmp_path):
+    """The C++ host side (include/igx_rt.hpp: SceneGraph + RaytracingInterface + tasks) drives the same frame through the
+    C ABI: NielsScene built with add(), one sphere moved with update<T>() (dirty-range upload, accel rebuild), readPixels."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "scene_graph_check")
+    libdir = os.path.dirname(rtb.LIB_PATH)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-ffp-contract=off", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "scene_graph_check.cpp"), "-L", libdir, "-lrtb200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    out = str(tmp_path / "frame.bin")
+    r = subprocess.run([exe, "render", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "OK render" in r.stdout, r.stdout
+    got = np.fromfile(out, np.uint32).reshape(360, 640)
+    scene = rtb.niels_scene(0.0)
+    sph = scene["spheres"].view(np.float32).reshape(7, 4).copy()
+    sph[5] = [-4, 2.5, 0, 1]
+    scene["spheres"] = sph.view(np.uint8).reshape(-1)
+    ref = oracle.frame(to_oracle_scene(scene), oracle.camera(640, 360, eye=(6, 5, 12)), oracle.seed((0.0, 0.0)), 1)
+    d = np.abs(got.view(np.uint8).astype(np.int32) - ref["rgba8"].view(np.uint8).reshape(-1).astype(np.int32).reshape(got.view(np.uint8).shape))
+    assert int((d > 1).sum()) <= 4 and int((d > 0).sum()) <= 64, f"{int((d > 0).sum())} channel values differ"
