@@ -52,7 +52,7 @@ struct rtb_ctx {
     std::vector<uint8_t> triangleMirror;   // host copy of the triangle buffer: the BVH is built on the host
 
     // acceleration structure
-    DevBuf<BvhNode> nodes; DevBuf<TravTri> travTris;
+    DevBuf<BvhNode> nodes; DevBuf<Node8> nodes8; DevBuf<TravTri> travTris;
     uint32_t nodeCount = 0; rtb_accel_mode accelMode = RTB_ACCEL_BRUTE; bool accelValid = false;
     BvhStats stats;
 
@@ -87,8 +87,8 @@ SceneView sceneView(const rtb_ctx* c) {
     v.lights = c->lights.p; v.materials = c->materials.p; v.materialIndices = c->materialIndices.p;
     v.skybox = c->skyW ? c->skybox.p : nullptr; v.skyW = c->skyW; v.skyH = c->skyH;
     v.info = c->info;
-    v.nodes = c->nodes.p; v.travTris = c->travTris.p; v.nodeCount = c->nodeCount;
-    v.useBvh = (c->accelMode == RTB_ACCEL_BVH && c->accelValid) ? 1u : 0u;
+    v.nodes = c->nodes.p; v.nodes8 = c->nodes8.p; v.travTris = c->travTris.p; v.nodeCount = c->nodeCount;
+    v.useBvh = !c->accelValid ? ACCEL_KIND_BRUTE : (c->accelMode == RTB_ACCEL_BVH ? ACCEL_KIND_CWBVH : (c->accelMode == RTB_ACCEL_BVH2 ? ACCEL_KIND_BVH2 : ACCEL_KIND_BRUTE));
     return v;
 }
 
@@ -128,7 +128,7 @@ int checkReady(rtb_ctx* c) {
     if (!c->cameraSet) return fail(c, RTB_ERR_STATE, "rtb_dispatch before the camera was uploaded");
     if (c->camera.width != c->width || c->camera.height != c->height)
         return fail(c, RTB_ERR_STATE, "camera.width/height differ from the size given to rtb_resize");
-    if (c->accelMode == RTB_ACCEL_BVH && !c->accelValid && c->info.triangleCount)
+    if (c->accelMode != RTB_ACCEL_BRUTE && !c->accelValid && c->info.triangleCount)
         return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
     if (c->info.triangleCount > c->limits.max_triangles || c->info.sphereCount > c->limits.max_spheres || c->info.cubeCount > c->limits.max_cubes ||
         c->info.planeCount > c->limits.max_planes || c->info.lightCount > c->limits.max_lights || c->info.materialCount > c->limits.max_materials)
@@ -208,7 +208,7 @@ void rtb_destroy(rtb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->triangles.release(); c->spheres.release(); c->cubes.release(); c->planes.release(); c->lights.release(); c->materials.release();
-    c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->travTris.release();
+    c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->rays.release(); c->hits.release(); c->workCounter.release(); c->counters.release();
     c->rinRays.release(); c->rinHits.release(); c->rinObj.release(); c->rinT.release(); c->rinUv.release(); c->rinOcc.release(); c->rinOcc2.release();
@@ -313,27 +313,40 @@ int rtb_upload_skybox(rtb_ctx* c, uint32_t w, uint32_t h, const uint16_t* px) {
 int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
-    if (mode != RTB_ACCEL_BRUTE && mode != RTB_ACCEL_BVH) return fail(c, RTB_ERR_ARG, "rtb_build_accel: unknown mode");
+    if (mode != RTB_ACCEL_BRUTE && mode != RTB_ACCEL_BVH && mode != RTB_ACCEL_BVH2) return fail(c, RTB_ERR_ARG, "rtb_build_accel: unknown mode");
     c->accelMode = mode;
     c->stats = BvhStats();
     c->nodeCount = 0;
     if (mode == RTB_ACCEL_BRUTE) { c->accelValid = true; return RTB_OK; }
     if (c->info.triangleCount > c->limits.max_triangles) return fail(c, RTB_ERR_CAPACITY, "triangleCount exceeds max_triangles");
-    std::vector<BvhNode> nodes; std::vector<TravTri> tt;
-    buildBvh(reinterpret_cast<const TriangleRec*>(c->triangleMirror.data()), c->info.triangleCount, 256, 0, nodes, tt, c->stats);
-    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
-    RTB_CUDA(c, c->nodes.alloc(nodes.size()));
+    std::vector<TravTri> tt;
+    const TriangleRec* tris = reinterpret_cast<const TriangleRec*>(c->triangleMirror.data());
+    if (mode == RTB_ACCEL_BVH) {
+        std::vector<Node8> nodes;
+        buildCwbvh(tris, c->info.triangleCount, 0, nodes, tt, c->stats);
+        // every level can leave a node group and a postponed triangle group on the traversal stack (64 entries)
+        if (c->stats.maxDepth * 2 + 2 > 64) return fail(c, RTB_ERR_CAPACITY, "rtb_build_accel: 8-wide tree deeper than the traversal stack allows; use RTB_ACCEL_BVH2");
+        RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+        RTB_CUDA(c, c->nodes8.alloc(nodes.size()));
+        if (!nodes.empty()) RTB_CUDA(c, cudaMemcpy(c->nodes8.p, nodes.data(), nodes.size() * sizeof(Node8), cudaMemcpyHostToDevice));
+        c->nodeCount = (uint32_t)nodes.size();
+    } else {
+        std::vector<BvhNode> nodes;
+        buildBvh(tris, c->info.triangleCount, 256, 0, nodes, tt, c->stats);
+        RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+        RTB_CUDA(c, c->nodes.alloc(nodes.size()));
+        if (!nodes.empty()) RTB_CUDA(c, cudaMemcpy(c->nodes.p, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+        c->nodeCount = (uint32_t)nodes.size();
+    }
     RTB_CUDA(c, c->travTris.alloc(tt.size()));
-    if (!nodes.empty()) RTB_CUDA(c, cudaMemcpy(c->nodes.p, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
     if (!tt.empty()) RTB_CUDA(c, cudaMemcpy(c->travTris.p, tt.data(), tt.size() * sizeof(TravTri), cudaMemcpyHostToDevice));
-    c->nodeCount = (uint32_t)nodes.size();
     c->accelValid = true;
     return RTB_OK;
 }
 
 int rtb_accel_info_get(const rtb_ctx* c, rtb_accel_info* out) {
     if (!c || !out) return RTB_ERR_ARG;
-    out->mode = c->accelMode; out->node_count = c->nodeCount; out->node_bytes = sizeof(BvhNode); out->leaf_count = c->stats.leafCount;
+    out->mode = c->accelMode; out->node_count = c->nodeCount; out->node_bytes = c->accelMode == RTB_ACCEL_BVH ? sizeof(Node8) : sizeof(BvhNode); out->leaf_count = c->stats.leafCount;
     out->max_depth = c->stats.maxDepth; out->tri_record_bytes = sizeof(TravTri); out->sah_cost = c->stats.sahCost; out->build_ms = c->stats.buildMs;
     return RTB_OK;
 }
@@ -460,7 +473,7 @@ int rtb_trace_rays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* pr
     if (!c || (!rays && n)) return RTB_ERR_ARG;
     RTB_BIND(c);
     if (n > 0x7FFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_trace_rays: too many rays");
-    if (c->accelMode == RTB_ACCEL_BVH && !c->accelValid && c->info.triangleCount) return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
+    if (c->accelMode != RTB_ACCEL_BRUTE && !c->accelValid && c->info.triangleCount) return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
     if (!n) return RTB_OK;
     int rc = stageRays(c, rays, n, prev, nullptr);
     if (rc) return rc;
@@ -480,7 +493,7 @@ int rtb_occlusion_rays(rtb_ctx* c, const float* rays, uint64_t n, const float* m
     if (!c || (!rays && n) || (!occluded && n)) return RTB_ERR_ARG;
     RTB_BIND(c);
     if (n > 0x7FFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_occlusion_rays: too many rays");
-    if (c->accelMode == RTB_ACCEL_BVH && !c->accelValid && c->info.triangleCount) return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
+    if (c->accelMode != RTB_ACCEL_BRUTE && !c->accelValid && c->info.triangleCount) return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
     if (!n) return RTB_OK;
     int rc = stageRays(c, rays, n, prev, maxDist);
     if (rc) return rc;

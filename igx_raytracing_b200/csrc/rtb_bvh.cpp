@@ -1,4 +1,10 @@
-// rtb_bvh.cpp — multi-threaded binned-SAH BVH builder (host).  See rtb_bvh.h.
+// rtb_bvh.cpp — host-side acceleration-structure builders (new functionality; the reference has none).
+//
+//   buildBinary  multi-threaded binned-SAH binary tree over padded triangle boxes (temporary form)
+//   buildBvh     -> 64-byte two-box nodes (BvhNode), breadth-first prefix then depth-first
+//   buildCwbvh   -> 80-byte 8-wide compressed nodes (Node8) after Ylitie, Karras, Laine, "Efficient Incoherent Ray
+//                   Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017): greedy surface-area collapse of the
+//                   binary tree, octant-ordered child slots, 8-bit child boxes on a per-node power-of-two grid
 #include "rtb_bvh.h"
 
 #include <algorithm>
@@ -27,19 +33,30 @@ struct Box {
 
 struct Prim { Box b; float c[3]; };
 
-// temporary node: links >= 0 index the owning vector, < 0 are leaf codes ~((first << 3) | (count - 1))
+// temporary binary node: links >= 0 index the owning vector, < 0 are leaf codes ~((first << 3) | (count - 1))
 struct TNode { Box b0, b1; int32_t c0, c1; };
+
+struct BinaryTree {
+    std::vector<TNode> all;        // inner nodes
+    int32_t root = 0;              // link of the root (a leaf code when the whole scene is one leaf)
+    std::vector<uint32_t> idx;     // triangle order: every leaf owns a contiguous range
+    Box rootBox;
+    uint32_t maxDepth = 0;
+};
 
 constexpr int BINS = 16;
 constexpr float C_TRAV = 1.0f;
 
 inline int32_t leafLink(uint32_t first, uint32_t count) { return (int32_t)~((first << 3) | (count - 1u)); }
+inline uint32_t leafFirst(int32_t link) { return (~(uint32_t)link) >> 3; }
+inline uint32_t leafCount(int32_t link) { return ((~(uint32_t)link) & 7u) + 1u; }
 
 struct Split { int axis; int bin; float cost; Box left, right; uint32_t nLeft; float cbLo, scale; };
 
 struct Builder {
     const Prim* prims;
     uint32_t* idx;
+    uint32_t maxLeaf;
 
     Box boundsOf(uint32_t b, uint32_t e) const { Box r; r.reset(); for (uint32_t i = b; i < e; ++i) r.grow(prims[idx[i]].b); return r; }
 
@@ -88,9 +105,9 @@ struct Builder {
         const uint32_t n = e - b;
         makeLeaf = false;
         Split s;
-        const bool forceMedian = depth >= 32;
+        const bool forceMedian = depth >= 32;   // bounds the depth: 32 SAH levels + log2(n) median levels
         if (!forceMedian && findSplit(b, e, s)) {
-            if (n <= BVH_MAX_LEAF) {
+            if (n <= maxLeaf) {
                 const float leafCost = (float)n * box.area();
                 if (leafCost <= C_TRAV * box.area() + s.cost) { makeLeaf = true; return b; }
             }
@@ -103,8 +120,7 @@ struct Builder {
             const uint32_t m = (uint32_t)(mid - idx);
             if (m > b && m < e) { lb = s.left; rb = s.right; return m; }
         }
-        if (n <= BVH_MAX_LEAF && !forceMedian) { makeLeaf = true; return b; }
-        if (n <= BVH_MAX_LEAF && forceMedian) { makeLeaf = true; return b; }
+        if (n <= maxLeaf) { makeLeaf = true; return b; }
         // object median along the widest axis of the box
         int axis = 0;
         for (int a = 1; a < 3; ++a) if (box.hi[a] - box.lo[a] > box.hi[axis] - box.lo[axis]) axis = a;
@@ -148,17 +164,8 @@ void parallelFor(int threads, uint32_t n, uint32_t chunk, F&& body) {
     for (auto& t : pool) t.join();
 }
 
-}  // namespace
-
-void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int threads, std::vector<BvhNode>& nodes,
-              std::vector<TravTri>& travTris, BvhStats& stats) {
-    const auto t0 = std::chrono::steady_clock::now();
-    nodes.clear(); travTris.clear();
-    stats = BvhStats();
-    if (count == 0) return;
-    if (threads <= 0) { threads = (int)std::thread::hardware_concurrency(); if (threads <= 0) threads = 1; }
-
-    // ---- primitive boxes, padded -------------------------------------------------------------------------
+void buildBinary(const TriangleRec* tris, uint32_t count, int threads, uint32_t maxLeaf, BinaryTree& out) {
+    // ---- primitive boxes, padded ---------------------------------------------------------------------------
     float maxAbs = 0.0f;
     for (uint32_t i = 0; i < count; ++i) {
         const TriangleRec& t = tris[i];
@@ -167,7 +174,8 @@ void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int th
     if (!(maxAbs < std::numeric_limits<float>::infinity())) maxAbs = 1.0f;
     const float pad = std::max(maxAbs * 3.814697265625e-6f /* 2^-18 */, 1e-30f);
     std::vector<Prim> prims(count);
-    std::vector<uint32_t> idx(count);
+    out.idx.resize(count);
+    uint32_t* idx = out.idx.data();
     parallelFor(threads, count, 1u << 16, [&](uint32_t b, uint32_t e) {
         for (uint32_t i = b; i < e; ++i) {
             const TriangleRec& t = tris[i];
@@ -181,19 +189,15 @@ void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int th
             idx[i] = i;
         }
     });
-    Builder bl{prims.data(), idx.data()};
+    Builder bl{prims.data(), idx, maxLeaf};
 
-    // ---- top of the tree, sequential: split the largest open range until there is enough parallel work -----
+    // ---- top of the tree, sequential: split the largest open range until there is enough parallel work -------
     struct Open { uint32_t b, e, depth; Box box; int32_t parent; int side; };
     std::vector<TNode> top;
     std::vector<Open> open;
-    int32_t rootLink;
-    {
-        Box rootBox = bl.boundsOf(0, count);
-        open.push_back({0, count, 0, rootBox, -1, 0});
-    }
+    out.rootBox = bl.boundsOf(0, count);
+    open.push_back({0, count, 0, out.rootBox, -1, 0});
     const size_t wantRanges = threads > 1 ? (size_t)threads * 8 : 1;
-    std::vector<Open> done;   // ranges that became leaves during the top phase
     while (open.size() < wantRanges) {
         size_t big = 0;
         for (size_t i = 1; i < open.size(); ++i) if (open[i].e - open[i].b > open[big].e - open[big].b) big = i;
@@ -201,7 +205,7 @@ void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int th
         if (o.e - o.b <= 4096) break;
         Box lb, rb; bool makeLeaf;
         const uint32_t m = bl.partition(o.b, o.e, o.depth, o.box, lb, rb, makeLeaf);
-        if (makeLeaf) break;   // cannot happen for > BVH_MAX_LEAF primitives
+        if (makeLeaf) break;   // cannot happen for > maxLeaf primitives
         const int32_t self = (int32_t)top.size();
         top.emplace_back();
         top[(size_t)self].b0 = lb; top[(size_t)self].b1 = rb; top[(size_t)self].c0 = 0; top[(size_t)self].c1 = 0;
@@ -210,7 +214,7 @@ void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int th
         open.push_back({m, o.e, o.depth + 1, rb, self, 1});
     }
 
-    // ---- subtrees in parallel ---------------------------------------------------------------------------
+    // ---- subtrees in parallel -----------------------------------------------------------------------------
     std::vector<std::vector<TNode>> sub(open.size());
     std::vector<int32_t> subRoot(open.size());
     {
@@ -229,34 +233,78 @@ void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int th
         for (auto& t : pool) t.join();
     }
 
-    // ---- merge into one temporary array -------------------------------------------------------------------
-    std::vector<TNode> all;
-    {
-        size_t total = top.size();
-        for (auto& s : sub) total += s.size();
-        all.reserve(total + 1);
-        all = top;
-        for (size_t i = 0; i < open.size(); ++i) {
-            const int32_t off = (int32_t)all.size();
-            for (TNode t : sub[i]) { if (t.c0 >= 0) t.c0 += off; if (t.c1 >= 0) t.c1 += off; all.push_back(t); }
-            const int32_t link = subRoot[i] >= 0 ? subRoot[i] + off : subRoot[i];
-            if (open[i].parent >= 0) (open[i].side ? all[(size_t)open[i].parent].c1 : all[(size_t)open[i].parent].c0) = link;
-            else rootLink = link;
-            std::vector<TNode>().swap(sub[i]);
-        }
-        if (open.size() > 1 || top.size() > 0) rootLink = 0;
+    // ---- merge into one temporary array ---------------------------------------------------------------------
+    std::vector<TNode>& all = out.all;
+    size_t total = top.size();
+    for (auto& s : sub) total += s.size();
+    all.reserve(total + 1);
+    all = top;
+    int32_t rootLink = 0;
+    for (size_t i = 0; i < open.size(); ++i) {
+        const int32_t off = (int32_t)all.size();
+        for (TNode t : sub[i]) { if (t.c0 >= 0) t.c0 += off; if (t.c1 >= 0) t.c1 += off; all.push_back(t); }
+        const int32_t link = subRoot[i] >= 0 ? subRoot[i] + off : subRoot[i];
+        if (open[i].parent >= 0) (open[i].side ? all[(size_t)open[i].parent].c1 : all[(size_t)open[i].parent].c0) = link;
+        else rootLink = link;
+        std::vector<TNode>().swap(sub[i]);
     }
-    // a scene that is a single leaf still gets an inner root: child 1 is an empty box no ray can enter
+    if (!top.empty()) rootLink = 0;
+    out.root = rootLink;
+
+    // depth
+    out.maxDepth = 0;
+    if (rootLink >= 0) {
+        std::vector<std::pair<int32_t, uint32_t>> st; st.push_back({rootLink, 1});
+        while (!st.empty()) {
+            auto [t, d] = st.back(); st.pop_back();
+            out.maxDepth = std::max(out.maxDepth, d);
+            if (all[(size_t)t].c0 >= 0) st.push_back({all[(size_t)t].c0, d + 1});
+            if (all[(size_t)t].c1 >= 0) st.push_back({all[(size_t)t].c1, d + 1});
+        }
+    }
+}
+
+void fillTravTris(const TriangleRec* tris, const std::vector<uint32_t>& order, int threads, std::vector<TravTri>& travTris) {
+    travTris.resize(order.size());
+    parallelFor(threads, (uint32_t)order.size(), 1u << 16, [&](uint32_t b, uint32_t e) {
+        for (uint32_t k = b; k < e; ++k) {
+            const uint32_t id = order[k];
+            const TriangleRec& t = tris[id];
+            TravTri& o = travTris[k];
+            for (int a = 0; a < 3; ++a) { o.p0[a] = t.p0[a]; o.e1[a] = t.p1[a] - t.p0[a]; o.e2[a] = t.p2[a] - t.p0[a]; }
+            o.id = id; o.pad1 = 0; o.pad2 = 0;
+        }
+    });
+}
+
+int resolveThreads(int threads) {
+    if (threads <= 0) { threads = (int)std::thread::hardware_concurrency(); if (threads <= 0) threads = 1; }
+    return threads;
+}
+
+}  // namespace
+
+void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int threads, std::vector<BvhNode>& nodes,
+              std::vector<TravTri>& travTris, BvhStats& stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    nodes.clear(); travTris.clear();
+    stats = BvhStats();
+    if (count == 0) return;
+    threads = resolveThreads(threads);
+    BinaryTree bt;
+    buildBinary(tris, count, threads, BVH_MAX_LEAF, bt);
+    std::vector<TNode>& all = bt.all;
+    int32_t rootLink = bt.root;
+    // a scene that is a single leaf still gets an inner root: both children are that leaf (a triangle tested twice is harmless)
     if (rootLink < 0) {
         TNode r;
-        r.b0 = bl.boundsOf(0, count);
-        r.b1.reset();
-        r.c0 = rootLink; r.c1 = leafLink(0, 1);
+        r.b0 = bt.rootBox; r.b1 = bt.rootBox;
+        r.c0 = rootLink; r.c1 = rootLink;
         all.clear(); all.push_back(r);
         rootLink = 0;
     }
 
-    // ---- final order: breadth-first prefix of `topNodes`, then depth-first --------------------------------
+    // ---- final order: breadth-first prefix of `topNodes`, then depth-first ----------------------------------
     const size_t nNodes = all.size();
     std::vector<int32_t> order; order.reserve(nNodes);          // temp index by final position
     std::vector<int32_t> finalOf(nNodes, -1);
@@ -292,39 +340,136 @@ void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int th
             n.pad0 = 0; n.pad1 = 0;
         }
     });
+    fillTravTris(tris, bt.idx, threads, travTris);
 
-    // ---- traversal triangles in leaf order ----------------------------------------------------------------
-    travTris.resize(count);
-    parallelFor(threads, count, 1u << 16, [&](uint32_t b, uint32_t e) {
-        for (uint32_t k = b; k < e; ++k) {
-            const uint32_t id = idx[k];
-            const TriangleRec& t = tris[id];
-            TravTri& o = travTris[k];
-            for (int a = 0; a < 3; ++a) { o.p0[a] = t.p0[a]; o.e1[a] = t.p1[a] - t.p0[a]; o.e2[a] = t.p2[a] - t.p0[a]; }
-            o.id = id; o.pad1 = 0; o.pad2 = 0;
-        }
-    });
-
-    // ---- statistics ---------------------------------------------------------------------------------------
+    // ---- statistics -------------------------------------------------------------------------------------------
     {
-        Box root; root = all[(size_t)rootLink].b0; root.grow(all[(size_t)rootLink].b1);
-        const float rootArea = std::max(root.area(), 1e-30f);
+        const float rootArea = std::max(bt.rootBox.area(), 1e-30f);
         double cost = C_TRAV;   // the root itself
-        uint32_t leaves = 0, maxDepth = 0;
-        std::vector<std::pair<int32_t, uint32_t>> st; st.push_back({rootLink, 1});
-        while (!st.empty()) {
-            auto [t, d] = st.back(); st.pop_back();
-            maxDepth = std::max(maxDepth, d);
-            const TNode& n = all[(size_t)t];
+        uint32_t leaves = 0;
+        for (const TNode& n : all) {
             const Box* bx[2] = {&n.b0, &n.b1}; const int32_t ch[2] = {n.c0, n.c1};
             for (int s = 0; s < 2; ++s) {
                 const float rel = bx[s]->area() / rootArea;
-                if (ch[s] >= 0) { cost += C_TRAV * rel; st.push_back({ch[s], d + 1}); }
-                else { cost += rel * (float)((~(uint32_t)ch[s] & 7u) + 1u); leaves++; }
+                if (ch[s] >= 0) cost += C_TRAV * rel;
+                else { cost += rel * (float)leafCount(ch[s]); leaves++; }
             }
         }
-        stats.nodeCount = (uint32_t)nodes.size(); stats.leafCount = leaves; stats.maxDepth = maxDepth; stats.sahCost = (float)cost;
+        stats.nodeCount = (uint32_t)nodes.size(); stats.leafCount = leaves; stats.maxDepth = std::max(bt.maxDepth, 1u); stats.sahCost = (float)cost;
     }
+    stats.buildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 8-wide compressed BVH
+// ------------------------------------------------------------------------------------------------------------
+void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vector<Node8>& nodes, std::vector<TravTri>& travTris, BvhStats& stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    nodes.clear(); travTris.clear();
+    stats = BvhStats();
+    if (count == 0) return;
+    threads = resolveThreads(threads);
+    BinaryTree bt;
+    buildBinary(tris, count, threads, CWBVH_MAX_LEAF, bt);
+    const std::vector<TNode>& all = bt.all;
+
+    struct Child { int32_t link; Box box; };
+    struct Work { int32_t bin; uint32_t node8; Box box; uint32_t depth; };   // bin < 0: the whole scene is one leaf
+    std::vector<uint32_t> triOrder; triOrder.reserve(count);
+    std::deque<Work> queue;
+    nodes.emplace_back();
+    queue.push_back({bt.root, 0u, bt.rootBox, 1u});
+    const float rootArea = std::max(bt.rootBox.area(), 1e-30f);
+    double cost = 0.0;
+    uint32_t leaves = 0, maxDepth = 0;
+
+    while (!queue.empty()) {
+        const Work w = queue.front(); queue.pop_front();
+        maxDepth = std::max(maxDepth, w.depth);
+        Child ch[8]; int n = 0;
+        if (w.bin < 0) { ch[0] = {w.bin, w.box}; n = 1; }
+        else {
+            ch[0] = {all[(size_t)w.bin].c0, all[(size_t)w.bin].b0}; ch[1] = {all[(size_t)w.bin].c1, all[(size_t)w.bin].b1}; n = 2;
+            // greedy collapse: open the inner child with the largest surface area until 8 children
+            while (n < 8) {
+                int pick = -1; float bestArea = -1.0f;
+                for (int i = 0; i < n; ++i) if (ch[i].link >= 0) { const float ar = ch[i].box.area(); if (ar > bestArea) { bestArea = ar; pick = i; } }
+                if (pick < 0) break;
+                const TNode& t = all[(size_t)ch[pick].link];
+                ch[pick] = {t.c0, t.b0};
+                ch[n++] = {t.c1, t.b1};
+            }
+        }
+        Box nb; nb.reset();
+        for (int i = 0; i < n; ++i) nb.grow(ch[i].box);
+        cost += C_TRAV * (nb.area() / rootArea);
+
+        // ---- slot assignment: child i -> slot s maximising dot(centre_i - centre_node, d_s), d_s = (+-1,+-1,+-1) by the bits of s
+        int slotOf[8]; bool slotUsed[8] = {false, false, false, false, false, false, false, false}; bool done[8] = {false, false, false, false, false, false, false, false};
+        float costTab[8][8];
+        for (int i = 0; i < n; ++i)
+            for (int s = 0; s < 8; ++s) {
+                float d = 0.0f;
+                for (int a = 0; a < 3; ++a) {
+                    const float cc = 0.5f * (ch[i].box.lo[a] + ch[i].box.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
+                    d += ((s >> a) & 1) ? cc : -cc;
+                }
+                costTab[i][s] = d;
+            }
+        for (int k = 0; k < n; ++k) {
+            int bi = -1, bs = -1; float bc = -std::numeric_limits<float>::infinity();
+            for (int i = 0; i < n; ++i) if (!done[i]) for (int s = 0; s < 8; ++s) if (!slotUsed[s] && costTab[i][s] > bc) { bc = costTab[i][s]; bi = i; bs = s; }
+            if (bi < 0) { for (int i = 0; i < n && bi < 0; ++i) if (!done[i]) bi = i; for (int s = 0; s < 8 && bs < 0; ++s) if (!slotUsed[s]) bs = s; }   // NaN costs
+            done[bi] = true; slotUsed[bs] = true; slotOf[bi] = bs;
+        }
+        int childAt[8]; for (int s = 0; s < 8; ++s) childAt[s] = -1;
+        for (int i = 0; i < n; ++i) childAt[slotOf[i]] = i;
+
+        // ---- quantisation grid: origin = box lo, per-axis power-of-two step with extent / step <= 254 -------------
+        Node8 out;
+        std::memset(&out, 0, sizeof out);
+        int ex[3]; double step[3];
+        for (int a = 0; a < 3; ++a) {
+            out.p[a] = nb.lo[a];
+            const double ext = (double)nb.hi[a] - (double)nb.lo[a];
+            int e = ext > 0.0 ? (int)std::ceil(std::log2(ext / 254.0)) : -100;
+            e = std::max(-100, std::min(100, e));
+            while (ext / std::ldexp(1.0, e) > 254.0 && e < 100) ++e;
+            ex[a] = e; step[a] = std::ldexp(1.0, e);
+            out.e[a] = (uint8_t)(e + 127);
+        }
+        out.childBase = (uint32_t)nodes.size();
+        out.triBase = (uint32_t)triOrder.size();
+        uint32_t triOffset = 0, innerCount = 0;
+        for (int s = 0; s < 8; ++s) {
+            const int i = childAt[s];
+            if (i < 0) { out.qlo[0][s] = out.qlo[1][s] = out.qlo[2][s] = 255; out.qhi[0][s] = out.qhi[1][s] = out.qhi[2][s] = 0; out.meta[s] = 0; continue; }
+            for (int a = 0; a < 3; ++a) {
+                const double lo = ((double)ch[i].box.lo[a] - (double)out.p[a]) / step[a], hi = ((double)ch[i].box.hi[a] - (double)out.p[a]) / step[a];
+                const double ql = std::floor(lo - 0.02), qh = std::ceil(hi + 0.02);
+                out.qlo[a][s] = (uint8_t)std::max(0.0, std::min(255.0, ql));
+                out.qhi[a][s] = (uint8_t)std::max(0.0, std::min(255.0, qh));
+            }
+            const float rel = ch[i].box.area() / rootArea;
+            if (ch[i].link >= 0) {
+                out.imask |= (uint8_t)(1u << s);
+                out.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+                const uint32_t id8 = (uint32_t)nodes.size() + innerCount;   // consecutive, in slot order
+                ++innerCount;
+                queue.push_back({ch[i].link, id8, ch[i].box, w.depth + 1});
+            } else {
+                const uint32_t first = leafFirst(ch[i].link), cnt = leafCount(ch[i].link);
+                out.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | triOffset);   // unary count in the top 3 bits, offset below
+                for (uint32_t k = 0; k < cnt; ++k) triOrder.push_back(bt.idx[first + k]);
+                triOffset += cnt;
+                cost += rel * (float)cnt; ++leaves;
+            }
+        }
+        nodes[w.node8] = out;
+        for (uint32_t k = 0; k < innerCount; ++k) nodes.emplace_back();
+    }
+    fillTravTris(tris, triOrder, threads, travTris);
+    stats.nodeCount = (uint32_t)nodes.size(); stats.leafCount = leaves; stats.maxDepth = maxDepth; stats.sahCost = (float)cost;
     stats.buildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 

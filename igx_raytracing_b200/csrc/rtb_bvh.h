@@ -20,6 +20,12 @@ struct BvhStats {
 void buildBvh(const TriangleRec* tris, uint32_t count, uint32_t topNodes, int threads,
               std::vector<BvhNode>& nodes, std::vector<TravTri>& travTris, BvhStats& stats);
 
+// 8-wide compressed BVH (80-byte Node8 records, breadth-first so the children of a node are consecutive) and its
+// traversal triangles (children's triangles consecutive per node).  Same padded boxes as buildBvh, rounded outwards
+// onto each node's 8-bit grid.
+void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vector<Node8>& nodes, std::vector<TravTri>& travTris, BvhStats& stats);
+
+constexpr uint32_t CWBVH_MAX_LEAF = 3;    // triangles per leaf slot (unary count in 3 bits)
 constexpr uint32_t BVH_MAX_LEAF = 4;      // triangles per leaf (the link encodes count-1 in 3 bits)
 constexpr uint32_t BVH_MAX_DEPTH = 60;    // traversal stack holds 64 entries
 

@@ -80,7 +80,7 @@ enum { MODE_CLOSEST = 0, MODE_ANY_BITS = 1, MODE_ANY_BYTES = 2 };
 
 struct TraceArgs {
     const RayRec* rays; uint32_t n;
-    const float4* nodes; const float4* tris; uint32_t nodeCount;
+    const float4* nodes; const uint4* nodes8; const float4* tris; uint32_t nodeCount;
     TriHit* hits;               // MODE_CLOSEST
     uint32_t* bits; FrameMap fm;// MODE_ANY_BITS
     uint8_t* bytes;             // MODE_ANY_BYTES
@@ -241,21 +241,32 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) 
     }
 }
 
+}  // namespace rtb
+#include "rtb_trace8.cuh"
+namespace rtb {
+
+// persistent grid: one resident wave (SM count x blocks that fit per SM), fewer when the wavefront is small
 static int g_traceBlocks = 0;
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool WIDE>
 static void launchTraceBvh(const TraceArgs& a, cudaStream_t st) {
     static int blocks = 0;
+    auto kernel = WIDE ? k_trace_cwbvh<MODE, COUNT> : k_trace_bvh<MODE, COUNT>;
     if (!blocks) {
         int dev = 0, sms = 0, perSm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace_bvh<MODE, COUNT>, TRACE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TRACE_THREADS, 0);
         blocks = sms * (perSm > 0 ? perSm : 1);
-        if (!COUNT) g_traceBlocks = blocks;
+        if (!COUNT && MODE == MODE_CLOSEST) g_traceBlocks = blocks;
     }
     cudaMemsetAsync(a.workCounter, 0, sizeof(uint32_t), st);
     const uint32_t warpsNeeded = (a.n + 31u) / 32u, blocksNeeded = (warpsNeeded + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32);
-    k_trace_bvh<MODE, COUNT><<<min((uint32_t)blocks, blocksNeeded ? blocksNeeded : 1u), TRACE_THREADS, 0, st>>>(a);
+    kernel<<<min((uint32_t)blocks, blocksNeeded ? blocksNeeded : 1u), TRACE_THREADS, 0, st>>>(a);
+}
+template <int MODE>
+static void launchTrace(const SceneView& sv, const TraceArgs& a, bool count, cudaStream_t st) {
+    if (sv.useBvh == ACCEL_KIND_CWBVH) { if (count) launchTraceBvh<MODE, true, true>(a, st); else launchTraceBvh<MODE, false, true>(a, st); }
+    else { if (count) launchTraceBvh<MODE, true, false>(a, st); else launchTraceBvh<MODE, false, false>(a, st); }
 }
 int trace_grid_blocks() { return g_traceBlocks; }
 
@@ -321,7 +332,8 @@ __global__ void k_fill_miss(TriHit* hits, uint32_t n) {
 static TraceArgs makeArgs(const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* workCounter, TraceCounters* counters) {
     TraceArgs a{};
     a.rays = rays; a.n = n;
-    a.nodes = reinterpret_cast<const float4*>(sv.nodes); a.tris = reinterpret_cast<const float4*>(sv.travTris); a.nodeCount = sv.nodeCount;
+    a.nodes = reinterpret_cast<const float4*>(sv.nodes); a.nodes8 = reinterpret_cast<const uint4*>(sv.nodes8);
+    a.tris = reinterpret_cast<const float4*>(sv.travTris); a.nodeCount = sv.nodeCount;
     a.workCounter = workCounter; a.counters = counters;
     return a;
 }
@@ -333,7 +345,7 @@ void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, T
     if (sv.useBvh) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
         a.hits = hits;
-        if (counters) launchTraceBvh<MODE_CLOSEST, true>(a, st); else launchTraceBvh<MODE_CLOSEST, false>(a, st);
+        launchTrace<MODE_CLOSEST>(sv, a, counters != nullptr, st);
     } else {
         FrameMap fm{};
         k_trace_brute<MODE_CLOSEST><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, hits, nullptr, fm, nullptr);
@@ -346,7 +358,7 @@ void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec
     if (sv.useBvh) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
         a.bits = bits; a.fm = fm;
-        if (counters) launchTraceBvh<MODE_ANY_BITS, true>(a, st); else launchTraceBvh<MODE_ANY_BITS, false>(a, st);
+        launchTrace<MODE_ANY_BITS>(sv, a, counters != nullptr, st);
     } else {
         k_trace_brute<MODE_ANY_BITS><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, bits, fm, nullptr);
     }
@@ -358,7 +370,7 @@ void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n,
     if (sv.useBvh) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, nullptr);
         a.bytes = occluded;
-        launchTraceBvh<MODE_ANY_BYTES, false>(a, st);
+        launchTrace<MODE_ANY_BYTES>(sv, a, false, st);
     } else {
         FrameMap fm{};
         k_trace_brute<MODE_ANY_BYTES><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, nullptr, fm, occluded);

@@ -20,8 +20,10 @@ struct SceneView {
     const LightRec* lights; const MaterialRec* materials; const uint32_t* materialIndices;
     const uint2* skybox; uint32_t skyW, skyH;
     SceneInfoRec info;            // host mirror of the reference's SceneData UBO, passed by value
-    const BvhNode* nodes; const TravTri* travTris; uint32_t nodeCount; uint32_t useBvh;
+    const BvhNode* nodes; const Node8* nodes8; const TravTri* travTris; uint32_t nodeCount;   // of the structure in use
+    uint32_t useBvh;              // ACCEL_KIND_*
 };
+enum : uint32_t { ACCEL_KIND_BRUTE = 0, ACCEL_KIND_CWBVH = 1, ACCEL_KIND_BVH2 = 2 };
 
 struct TraceCounters { unsigned long long rays, nodes, tris, hits; };
 

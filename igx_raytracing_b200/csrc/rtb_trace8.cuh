@@ -1,0 +1,227 @@
+// rtb_trace8.cuh — persistent traversal of the 8-wide compressed BVH (included by rtb_kernels.cu).
+//
+// One warp = 32 rays in flight.  Per iteration, in lock-step:
+//   A  every lane whose current node group still has hit inner children takes the nearest one (highest bit of the
+//      octant-permuted hit mask), fetches its 80-byte record (5 x LDG.128, or shared memory for the top of the tree)
+//      and tests the 8 quantised child boxes; the result is a new node group and a triangle group;
+//   B  triangle groups are drained with Möller–Trumbore (the reference's arithmetic, SH/primitive.glsl:239-284);
+//      when only a few lanes hold triangles and they still have node work, they postpone the group onto their stack;
+//   C  lanes with nothing left in their group pop their stack, or retire the ray;
+//   D  when fewer than REFILL8 lanes are still busy the idle lanes take new rays from the wavefront with one
+//      warp-aggregated atomic (ballot + shfl).
+// The per-lane stack holds 8-byte (base, mask) groups: the first SM_STACK entries in shared memory ([entry][thread],
+// conflict-free for any mix of depths), the rest in local memory.
+#pragma once
+
+namespace rtb {
+
+constexpr int TOP8_NODES = 192;      // 15 KB of shared memory: the breadth-first top of the tree
+constexpr int SM_STACK = 8;          // 16 KB of shared memory per 256-thread block
+constexpr int LOCAL_STACK = 56;      // the builder refuses trees that could need more than SM_STACK + LOCAL_STACK entries
+constexpr int REFILL8 = 22;
+constexpr int POSTPONE8 = 8;
+
+// byte j of w as 1 + b * 2^-15 (one PRMT): with K = 2^15 * step / d and C = (p - o) / d - K, fma(f, K, C) = (p + b * step - o) / d
+template <int J>
+RTB_DI float byteFrac(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (J << 4))); }
+
+template <int J>
+RTB_DI void testChild(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float kx, float ky, float kz,
+                      float cx, float cy, float cz, float best, uint32_t childBits4, uint32_t bitIndex4, uint32_t& hitmask) {
+    const float tnx = fmaf(byteFrac<J>(nx), kx, cx), tny = fmaf(byteFrac<J>(ny), ky, cy), tnz = fmaf(byteFrac<J>(nz), kz, cz);
+    const float tfx = fmaf(byteFrac<J>(fx), kx, cx), tfy = fmaf(byteFrac<J>(fy), ky, cy), tfz = fmaf(byteFrac<J>(fz), kz, cz);
+    const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, best));
+    if (cmin <= cmax) hitmask |= ((childBits4 >> (8 * J)) & 0xFFu) << ((bitIndex4 >> (8 * J)) & 0xFFu);
+}
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArgs a) {
+    __shared__ uint4 sTop[TOP8_NODES * 5];
+    __shared__ uint2 sStack[SM_STACK][TRACE_THREADS];
+    const int topN = min((int)a.nodeCount, TOP8_NODES);
+    for (int i = threadIdx.x; i < topN * 5; i += TRACE_THREADS) sTop[i] = __ldg(a.nodes8 + i);
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lanesBelow = (1u << lane) - 1u;
+    uint2 lstack[LOCAL_STACK];
+
+    bool active = false, exhausted = false;
+    uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT, octinv4 = 0;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
+    float best = 0, bu = 0, bv = 0;
+    uint2 G = make_uint2(0u, 0u);
+    int sp = 0;
+    unsigned long long cRays = 0, cNodes = 0, cTris = 0, cHits = 0;
+
+    auto push = [&](uint2 e) { if (sp < SM_STACK) sStack[sp][threadIdx.x] = e; else lstack[sp - SM_STACK] = e; ++sp; };
+    auto pop = [&]() { --sp; return sp < SM_STACK ? sStack[sp][threadIdx.x] : lstack[sp - SM_STACK]; };
+
+    for (;;) {
+        // ---- D: refill ------------------------------------------------------------------------------------
+        const unsigned busy = __ballot_sync(0xFFFFFFFFu, active);
+        if (!exhausted && __popc(busy) < REFILL8) {
+            const unsigned need = ~busy;
+            uint32_t base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(a.workCounter, (uint32_t)__popc(need));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            exhausted = base + (uint32_t)__popc(need) >= a.n;
+            if (!active) {
+                slot = base + (uint32_t)__popc(need & lanesBelow);
+                if (slot < a.n) {
+                    const float4 o = __ldg(reinterpret_cast<const float4*>(a.rays + slot));
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(a.rays + slot) + 1);
+                    if (d.w >= 0.0f) {
+                        ox = o.x; oy = o.y; oz = o.z; prev = fbits(o.w);
+                        dx = d.x; dy = d.y; dz = d.z; best = d.w;
+                        const float tiny = 8.271806e-25f;   // 2^-80: keeps 1/d finite for axis-parallel rays
+                        idx = 1.0f / (fabsf(dx) > tiny ? dx : copysignf(tiny, dx));
+                        idy = 1.0f / (fabsf(dy) > tiny ? dy : copysignf(tiny, dy));
+                        idz = 1.0f / (fabsf(dz) > tiny ? dz : copysignf(tiny, dz));
+                        // bit set = the ray travels towards + on that axis; slot s ^ octinv orders children far -> near
+                        octinv4 = ((idx < 0.0f ? 0u : 1u) | (idy < 0.0f ? 0u : 2u) | (idz < 0.0f ? 0u : 4u)) * 0x01010101u;
+                        bestId = NO_RAY_HIT; bu = 0.0f; bv = 0.0f;
+                        sp = 0; G = make_uint2(0u, 0x80000000u);   // the root as a one-node group
+                        active = true;
+                        if (COUNT) cRays++;
+                    } else if (MODE == MODE_CLOSEST) {
+                        TriHit h; h.t = NO_HIT; h.id = NO_RAY_HIT; h.u = 0.0f; h.v = 0.0f;
+                        *reinterpret_cast<float4*>(a.hits + slot) = *reinterpret_cast<float4*>(&h);
+                    } else if (MODE == MODE_ANY_BYTES) {
+                        a.bytes[slot] = 0;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- A: one node per lane -----------------------------------------------------------------------------
+        uint2 T = make_uint2(0u, 0u);   // triangle group
+        if (active) {
+            if (G.y & 0xFF000000u) {
+                const uint32_t hits = G.y;
+                const uint32_t bit = 31u - (uint32_t)__clz(hits);
+                const uint32_t childSlot = (bit - 24u) ^ (octinv4 & 7u);
+                const uint32_t rel = (uint32_t)__popc(hits & 0xFFu & ~(0xFFFFFFFFu << childSlot));
+                const uint32_t nodeIdx = G.x + rel;
+                G.y &= ~(1u << bit);
+                if (G.y & 0xFF000000u) push(G);
+                uint4 n0, n1, n2, n3, n4;
+                if ((int)nodeIdx < topN) {
+                    const uint4* p = sTop + nodeIdx * 5;
+                    n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3]; n4 = p[4];
+                } else {
+                    const uint4* p = a.nodes8 + (size_t)nodeIdx * 5;
+                    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); n4 = __ldg(p + 4);
+                }
+                if (COUNT) cNodes++;
+                const float kx = __uint_as_float(((n0.w & 0xFFu) + 15u) << 23) * idx;
+                const float ky = __uint_as_float((((n0.w >> 8) & 0xFFu) + 15u) << 23) * idy;
+                const float kz = __uint_as_float((((n0.w >> 16) & 0xFFu) + 15u) << 23) * idz;
+                const float cx = (__uint_as_float(n0.x) - ox) * idx - kx;
+                const float cy = (__uint_as_float(n0.y) - oy) * idy - ky;
+                const float cz = (__uint_as_float(n0.z) - oz) * idz - kz;
+                const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
+                uint32_t hitmask = 0;
+                {
+                    const uint32_t meta4 = n1.z;
+                    const uint32_t innerMask4 = (((meta4 & (meta4 << 1)) & 0x10101010u) >> 4) * 0xFFu;
+                    const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
+                    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                    const uint32_t nx = negx ? n3.z : n2.x, fx = negx ? n2.x : n3.z;
+                    const uint32_t ny = negy ? n4.x : n2.z, fy = negy ? n2.z : n4.x;
+                    const uint32_t nz = negz ? n4.z : n3.x, fz = negz ? n3.x : n4.z;
+                    testChild<0>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                    testChild<1>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                    testChild<2>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                    testChild<3>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                }
+                {
+                    const uint32_t meta4 = n1.w;
+                    const uint32_t innerMask4 = (((meta4 & (meta4 << 1)) & 0x10101010u) >> 4) * 0xFFu;
+                    const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
+                    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                    const uint32_t nx = negx ? n3.w : n2.y, fx = negx ? n2.y : n3.w;
+                    const uint32_t ny = negy ? n4.y : n2.w, fy = negy ? n2.w : n4.y;
+                    const uint32_t nz = negz ? n4.w : n3.y, fz = negz ? n3.y : n4.w;
+                    testChild<0>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                    testChild<1>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                    testChild<2>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                    testChild<3>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                }
+                G = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
+                T = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
+            } else {
+                T = G;                     // a popped triangle group
+                G = make_uint2(0u, 0u);
+            }
+        }
+
+        // ---- B: triangles -------------------------------------------------------------------------------------
+        for (;;) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, T.y != 0u);
+            if (!m) break;
+            if (T.y != 0u && __popc(m) < POSTPONE8 && (G.y & 0xFF000000u)) { push(T); T.y = 0u; }   // postpone: this lane has node work
+            if (T.y != 0u) {
+                const uint32_t bit = 31u - (uint32_t)__clz(T.y);
+                T.y &= ~(1u << bit);
+                const float4* tp = a.tris + (size_t)(T.x + bit) * 3;
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                if (COUNT) cTris++;
+                float u, v, t, aa;
+                if (triCandidate(mk3(ox, oy, oz), mk3(dx, dy, dz), mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), u, v, t, aa)) {
+                    const uint32_t id = fbits(t0.w);
+                    if (t > 0.0f && id != prev) {
+                        if (MODE == MODE_CLOSEST) {
+                            // reference: strict t < hitT in index order => on equal t the lower index wins
+                            if (t < best || (t == best && id < bestId)) { best = t; bestId = id; bu = u; bv = v; }
+                        } else if (t < best) {
+                            bestId = id; T.y = 0u; G = make_uint2(0u, 0u); sp = 0;   // any hit ends the ray
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- C: pop or retire -----------------------------------------------------------------------------------
+        if (active && !(G.y & 0xFF000000u)) {
+            if (sp > 0) G = pop();
+            else {
+                active = false;
+                if (MODE == MODE_CLOSEST) {
+                    TriHit h; h.t = bestId == NO_RAY_HIT ? NO_HIT : best; h.id = bestId; h.u = bu; h.v = bv;
+                    *reinterpret_cast<float4*>(a.hits + slot) = *reinterpret_cast<float4*>(&h);
+                    if (COUNT && bestId != NO_RAY_HIT) cHits++;
+                } else if (MODE == MODE_ANY_BITS) {
+                    if (bestId != NO_RAY_HIT) {
+                        const uint32_t sample = slot / a.fm.localSlots, i = slot - sample * a.fm.localSlots;
+                        uint32_t x, y;
+                        slotToPixel(a.fm, i, x, y);
+                        atomicOr(a.bits + indexToLight(x, y, a.fm.w, a.fm.h, sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
+                        if (COUNT) cHits++;
+                    }
+                } else {
+                    a.bytes[slot] = bestId != NO_RAY_HIT ? 1 : 0;
+                }
+            }
+        }
+    }
+
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            cRays += __shfl_xor_sync(0xFFFFFFFFu, cRays, o); cNodes += __shfl_xor_sync(0xFFFFFFFFu, cNodes, o);
+            cTris += __shfl_xor_sync(0xFFFFFFFFu, cTris, o); cHits += __shfl_xor_sync(0xFFFFFFFFu, cHits, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.counters->rays, cRays); atomicAdd(&a.counters->nodes, cNodes);
+            atomicAdd(&a.counters->tris, cTris); atomicAdd(&a.counters->hits, cHits);
+        }
+    }
+}
+
+}  // namespace rtb

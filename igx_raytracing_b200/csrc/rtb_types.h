@@ -60,6 +60,21 @@ struct alignas(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BVH node is 64 bytes");
 
+// 8-wide compressed node, 80 bytes = five 16-byte vector loads (layout after Ylitie et al. 2017):
+//   p, e        origin and per-axis exponent (biased by 127) of the node's quantisation grid
+//   imask       bit s set: child slot s is an inner node
+//   childBase   index of the first inner child (inner children are consecutive, in slot order)
+//   triBase     index of the first triangle of the leaf children (consecutive, in slot order, at most 24)
+//   meta[s]     empty 0 | inner (1 << 5) | (24 + s) | leaf (unary triangle count << 5) | triangle offset
+//   qlo, qhi    child boxes on the grid: lo = p + qlo * 2^e, hi = p + qhi * 2^e (rounded outwards)
+struct alignas(16) Node8 {
+    float p[3]; uint8_t e[3]; uint8_t imask;
+    uint32_t childBase, triBase; uint8_t meta[8];
+    uint8_t qlo[3][8];
+    uint8_t qhi[3][8];
+};
+static_assert(sizeof(Node8) == 80, "CWBVH node is 80 bytes");
+
 // Traversal triangle, in leaf order: p0, e1 = p1 - p0, e2 = p2 - p0 (the same float subtractions the
 // reference shader performs per test, done once), and the triangle's index in the uploaded array.
 struct alignas(16) TravTri {

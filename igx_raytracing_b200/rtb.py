@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "librtb200.so")
  BUF_MATERIALS, BUF_MATERIAL_INDICES) = range(11)
 PASS_INIT, PASS_RAYGEN, PASS_SHADOW, PASS_LIGHTING, PASS_COMPOSITE, PASS_FRAME = range(6)
 TGT_DIR_T, TGT_UV_NORMAL, TGT_SHADOW_BITS, TGT_LIGHTING, TGT_ACCUM, TGT_RGBA8, TGT_SEED, TGT_RGBA8_TILED = range(8)
-ACCEL_BRUTE, ACCEL_BVH = 0, 1
+ACCEL_BRUTE, ACCEL_BVH, ACCEL_BVH2 = 0, 1, 2
 OPT_COUNTERS, OPT_TILE_RANK, OPT_TILE_COUNT = 0, 1, 2
 NO_RAY_HIT = 0xFFFFFFFF
 NO_HIT = np.float32(3.4028235e38)

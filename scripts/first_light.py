@@ -9,6 +9,7 @@ w = int(sys.argv[2]) if len(sys.argv) > 2 else 3840
 h = int(sys.argv[3]) if len(sys.argv) > 3 else 2160
 frames = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 ez = float(sys.argv[5]) if len(sys.argv) > 5 else 13.9
+mode = int(sys.argv[6]) if len(sys.argv) > 6 else 1   # 1 = 8-wide compressed BVH, 2 = binary BVH
 t0 = time.time()
 tris = rtb.gen_soup(n)
 mat = rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0)
@@ -18,7 +19,7 @@ ctx = rtb.Context(max_triangles=n)
 ctx.resize(w, h, 1)
 ctx.upload_scene(scene, None)
 t1 = time.time()
-ctx.build_accel(rtb.ACCEL_BVH)
+ctx.build_accel(mode)
 info = ctx.accel_info()
 print(f"gen+upload {t1 - t0:.2f}s  build {info.build_ms:.0f} ms nodes {info.node_count} leaves {info.leaf_count} depth {info.max_depth} sah {info.sah_cost:.1f}", flush=True)
 ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, ez)))

@@ -33,6 +33,70 @@ static bool tri(V ro, V rd, V p0, V e1, V e2, float& t) {
     return t > 0.0f;
 }
 
+
+// ---- CPU mirror of k_trace_cwbvh (rtb_trace8.cuh): same octant ordering, byte decode (1 + b * 2^-15), fma planes ----
+static float byteFrac(uint32_t w, int j) { uint32_t b = (w >> (8 * j)) & 0xFFu; uint32_t u = 0x3F800000u | (b << 8); float f; std::memcpy(&f, &u, 4); return f; }
+static float expo(uint32_t e) { uint32_t u = (e + 15u) << 23; float f; std::memcpy(&f, &u, 4); return f; }
+static uint32_t fbitsU(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+
+static bool walk8(const std::vector<Node8>& nodes, const std::vector<TravTri>& tt, V ro, V rd, float& best, uint32_t& bestId, int& maxSp) {
+    const float tiny = 8.271806e-25f;
+    const float idx = 1.0f / (std::fabs(rd.x) > tiny ? rd.x : std::copysign(tiny, rd.x));
+    const float idy = 1.0f / (std::fabs(rd.y) > tiny ? rd.y : std::copysign(tiny, rd.y));
+    const float idz = 1.0f / (std::fabs(rd.z) > tiny ? rd.z : std::copysign(tiny, rd.z));
+    const uint32_t octinv = (idx < 0 ? 0u : 1u) | (idy < 0 ? 0u : 2u) | (idz < 0 ? 0u : 4u), octinv4 = octinv * 0x01010101u;
+    best = 3.4028235e38f; bestId = 0xFFFFFFFFu;
+    struct G2 { uint32_t x, y; };
+    G2 stack[64]; int sp = 0; G2 G = {0u, 0x80000000u};
+    for (;;) {
+        G2 T = {0u, 0u};
+        if (G.y & 0xFF000000u) {
+            const uint32_t hits = G.y;
+            const uint32_t bit = 31u - (uint32_t)__builtin_clz(hits);
+            const uint32_t childSlot = (bit - 24u) ^ octinv;
+            const uint32_t rel = (uint32_t)__builtin_popcount(hits & 0xFFu & ~(0xFFFFFFFFu << childSlot));
+            const uint32_t ni = G.x + rel;
+            G.y &= ~(1u << bit);
+            if (G.y & 0xFF000000u) { if (sp >= 64) return false; stack[sp++] = G; }
+            if (ni >= nodes.size()) return false;
+            const Node8& n = nodes[ni];
+            uint32_t w[20]; std::memcpy(w, &n, 80);
+            const float kx = expo(n.e[0]) * idx, ky = expo(n.e[1]) * idy, kz = expo(n.e[2]) * idz;
+            const float cx = (n.p[0] - ro.x) * idx - kx, cy = (n.p[1] - ro.y) * idy - ky, cz = (n.p[2] - ro.z) * idz - kz;
+            uint32_t hitmask = 0;
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t meta4 = w[6 + half];
+                const uint32_t innerMask4 = (((meta4 & (meta4 << 1)) & 0x10101010u) >> 4) * 0xFFu;
+                const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
+                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t lox = w[8 + half], loy = w[10 + half], loz = w[12 + half], hix = w[14 + half], hiy = w[16 + half], hiz = w[18 + half];
+                const uint32_t nx = idx < 0 ? hix : lox, fx = idx < 0 ? lox : hix, ny = idy < 0 ? hiy : loy, fy = idy < 0 ? loy : hiy, nz = idz < 0 ? hiz : loz, fz = idz < 0 ? loz : hiz;
+                for (int j = 0; j < 4; ++j) {
+                    const float tnx = std::fma(byteFrac(nx, j), kx, cx), tny = std::fma(byteFrac(ny, j), ky, cy), tnz = std::fma(byteFrac(nz, j), kz, cz);
+                    const float tfx = std::fma(byteFrac(fx, j), kx, cx), tfy = std::fma(byteFrac(fy, j), ky, cy), tfz = std::fma(byteFrac(fz, j), kz, cz);
+                    const float cmin = std::fmax(std::fmax(tnx, tny), std::fmax(tnz, 0.0f)), cmax = std::fmin(std::fmin(tfx, tfy), std::fmin(tfz, best));
+                    if (cmin <= cmax) hitmask |= ((childBits4 >> (8 * j)) & 0xFFu) << ((bitIndex4 >> (8 * j)) & 0xFFu);
+                }
+            }
+            G = {n.childBase, (hitmask & 0xFF000000u) | n.imask};
+            T = {n.triBase, hitmask & 0x00FFFFFFu};
+        } else { T = G; G = {0u, 0u}; }
+        while (T.y) {
+            const uint32_t bit = 31u - (uint32_t)__builtin_clz(T.y);
+            T.y &= ~(1u << bit);
+            if (T.x + bit >= tt.size()) return false;
+            const TravTri& t = tt[T.x + bit];
+            float tv;
+            if (tri(ro, rd, V{t.p0[0], t.p0[1], t.p0[2]}, V{t.e1[0], t.e1[1], t.e1[2]}, V{t.e2[0], t.e2[1], t.e2[2]}, tv))
+                if (tv < best || (tv == best && t.id < bestId)) { best = tv; bestId = t.id; }
+        }
+        maxSp = std::max(maxSp, sp);
+        if (!(G.y & 0xFF000000u)) { if (sp == 0) break; G = stack[--sp]; }
+    }
+    (void)fbitsU;
+    return true;
+}
+
 int main(int argc, char** argv) {
     const uint32_t n = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 20000;
     const int threads = argc > 2 ? std::atoi(argv[2]) : 0;
@@ -52,6 +116,11 @@ int main(int argc, char** argv) {
     for (auto& t : tt) { if (t.id >= n || seen[t.id]) { std::printf("FAIL permutation\n"); return 1; } seen[t.id] = 1; }
     if (st.maxDepth > BVH_MAX_DEPTH) { std::printf("FAIL depth %u\n", st.maxDepth); return 1; }
 
+    std::vector<Node8> nodes8; std::vector<TravTri> tt8; BvhStats st8;
+    buildCwbvh(tris.data(), n, threads, nodes8, tt8, st8);
+    if (tt8.size() != n) { std::printf("FAIL cwbvh travTris %zu\n", tt8.size()); return 1; }
+    { std::vector<uint8_t> seen8(n, 0); for (auto& t : tt8) { if (t.id >= n || seen8[t.id]) { std::printf("FAIL cwbvh permutation\n"); return 1; } seen8[t.id] = 1; } }
+    int maxSp = 0;
     uint32_t hits = 0;
     for (uint32_t r = 0; r < nRays; ++r) {
         V ro = {rnd() * 24 - 12, rnd() * 24 - 12, 30.0f};
@@ -102,8 +171,12 @@ int main(int argc, char** argv) {
             }
         }
         if (id2 != bestId || (bestId != 0xFFFFFFFFu && b2 != best)) { std::printf("FAIL ray %u: linear (%u, %g) bvh (%u, %g)\n", r, bestId, best, id2, b2); return 1; }
+        float b8; uint32_t id8;
+        if (!walk8(nodes8, tt8, ro, rd, b8, id8, maxSp)) { std::printf("FAIL ray %u: cwbvh walk out of range\n", r); return 1; }
+        if (id8 != bestId || (bestId != 0xFFFFFFFFu && b8 != best)) { std::printf("FAIL ray %u: linear (%u, %g) cwbvh (%u, %g)\n", r, bestId, best, id8, b8); return 1; }
         hits += bestId != 0xFFFFFFFFu;
     }
-    std::printf("OK %u %u %u %.3f %.1f hits=%u\n", st.nodeCount, st.leafCount, st.maxDepth, st.sahCost, st.buildMs, hits);
+    std::printf("OK %u %u %u %.3f %.1f hits=%u | cwbvh nodes %u leaves %u depth %u sah %.3f %.1f ms maxsp %d\n", st.nodeCount, st.leafCount, st.maxDepth, st.sahCost,
+                st.buildMs, hits, st8.nodeCount, st8.leafCount, st8.maxDepth, st8.sahCost, st8.buildMs, maxSp);
     return 0;
 }
