@@ -208,7 +208,7 @@ def test_soup_occlusion_rays(rtb, oracle):
         got = ctx.occlusion_rays(rays, max_dist, prev)
         assert int((got != want).sum()) <= 2, f"mode {mode}: {int((got != want).sum())} occlusion results differ"
     ctx.close()
-    assert 0.05 < want.mean() < 0.95
+    assert 0.01 < want.mean() < 0.95
 
 
 def test_niels_occlusion_rays_all_primitives(rtb, oracle):
