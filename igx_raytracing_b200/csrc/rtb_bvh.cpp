@@ -443,7 +443,7 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
         uint32_t triOffset = 0, innerCount = 0;
         for (int s = 0; s < 8; ++s) {
             const int i = childAt[s];
-            if (i < 0) { out.qlo[0][s] = out.qlo[1][s] = out.qlo[2][s] = 255; out.qhi[0][s] = out.qhi[1][s] = out.qhi[2][s] = 0; out.meta[s] = 0; continue; }
+            if (i < 0) { out.qlo[0][s] = out.qlo[1][s] = out.qlo[2][s] = 255; out.qhi[0][s] = out.qhi[1][s] = out.qhi[2][s] = 0; continue; }
             for (int a = 0; a < 3; ++a) {
                 const double lo = ((double)ch[i].box.lo[a] - (double)out.p[a]) / step[a], hi = ((double)ch[i].box.hi[a] - (double)out.p[a]) / step[a];
                 const double ql = std::floor(lo - 0.02), qh = std::ceil(hi + 0.02);
@@ -453,18 +453,18 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
             const float rel = ch[i].box.area() / rootArea;
             if (ch[i].link >= 0) {
                 out.imask |= (uint8_t)(1u << s);
-                out.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
                 const uint32_t id8 = (uint32_t)nodes.size() + innerCount;   // consecutive, in slot order
                 ++innerCount;
                 queue.push_back({ch[i].link, id8, ch[i].box, w.depth + 1});
             } else {
                 const uint32_t first = leafFirst(ch[i].link), cnt = leafCount(ch[i].link);
-                out.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | triOffset);   // unary count in the top 3 bits, offset below
+                out.valid |= ((1u << cnt) - 1u) << (3 * s);   // unary count at the slot's three bits
                 for (uint32_t k = 0; k < cnt; ++k) triOrder.push_back(bt.idx[first + k]);
                 triOffset += cnt;
                 cost += rel * (float)cnt; ++leaves;
             }
         }
+        out.valid |= (uint32_t)out.imask << 24;
         nodes[w.node8] = out;
         for (uint32_t k = 0; k < innerCount; ++k) nodes.emplace_back();
     }

@@ -21,18 +21,28 @@ constexpr int LOCAL_STACK = 56;      // the builder refuses trees that could nee
 constexpr int REFILL8 = 22;
 constexpr int POSTPONE8 = 8;
 
-// byte j of w as 1 + b * 2^-15 (one PRMT): with K = 2^15 * step / d and C = (p - o) / d - K, fma(f, K, C) = (p + b * step - o) / d
+// byte J of w as 1 + b * 2^-15 (one PRMT with an immediate selector; `one` = 0x3F800000 held in a register): with
+// K = 2^15 * step / d and C = (p - o) / d - K, fma(f, K, C) = (p + b * step - o) / d
 template <int J>
-RTB_DI float byteFrac(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (J << 4))); }
+RTB_DI float byteFrac(uint32_t w, uint32_t one) {
+    uint32_t r;
+    if (J == 0) asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(w), "r"(one));
+    else if (J == 1) asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(w), "r"(one));
+    else if (J == 2) asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(r) : "r"(w), "r"(one));
+    else asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(w), "r"(one));
+    return __uint_as_float(r);
+}
 
-template <int J>
+// child slot S = 4 * HALF + J: a hit sets the slot's inner bit (24 + S) and its three triangle bits (3S .. 3S+2);
+// the node's valid mask removes what the slot does not hold
+template <int J, int S>
 RTB_DI void testChild(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float kx, float ky, float kz,
-                      float cx, float cy, float cz, float best, uint32_t childBits4, uint32_t bitIndex4, uint32_t& hitmask) {
-    const float tnx = fmaf(byteFrac<J>(nx), kx, cx), tny = fmaf(byteFrac<J>(ny), ky, cy), tnz = fmaf(byteFrac<J>(nz), kz, cz);
-    const float tfx = fmaf(byteFrac<J>(fx), kx, cx), tfy = fmaf(byteFrac<J>(fy), ky, cy), tfz = fmaf(byteFrac<J>(fz), kz, cz);
+                      float cx, float cy, float cz, float best, uint32_t one, uint32_t& hitmask) {
+    const float tnx = fmaf(byteFrac<J>(nx, one), kx, cx), tny = fmaf(byteFrac<J>(ny, one), ky, cy), tnz = fmaf(byteFrac<J>(nz, one), kz, cz);
+    const float tfx = fmaf(byteFrac<J>(fx, one), kx, cx), tfy = fmaf(byteFrac<J>(fy, one), ky, cy), tfz = fmaf(byteFrac<J>(fz, one), kz, cz);
     const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
     const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, best));
-    if (cmin <= cmax) hitmask |= ((childBits4 >> (8 * J)) & 0xFFu) << ((bitIndex4 >> (8 * J)) & 0xFFu);
+    if (cmin <= cmax) hitmask |= (1u << (24 + S)) | (7u << (3 * S));
 }
 
 template <int MODE, bool COUNT>
@@ -46,6 +56,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArg
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
     uint2 lstack[LOCAL_STACK];
+    uint32_t one;
+    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one));   // kept in a register so PRMT can take its selector as an immediate
 
     bool active = false, exhausted = false;
     uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT, octinv4 = 0;
@@ -101,7 +113,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArg
         }
 
         // ---- A: one node per lane -----------------------------------------------------------------------------
-        uint2 T = make_uint2(0u, 0u);   // triangle group
+        uint2 T = make_uint2(0u, 0u);   // triangle group: (first triangle of the node, hit bits at 3 * slot + k)
+        uint32_t P = 0u;                // triangles present in the node, same bit positions: index = base + popc(P below the bit)
         if (active) {
             if (G.y & 0xFF000000u) {
                 const uint32_t hits = G.y;
@@ -129,36 +142,37 @@ __global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArg
                 const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
                 uint32_t hitmask = 0;
                 {
-                    const uint32_t meta4 = n1.z;
-                    const uint32_t innerMask4 = (((meta4 & (meta4 << 1)) & 0x10101010u) >> 4) * 0xFFu;
-                    const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
-                    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
                     const uint32_t nx = negx ? n3.z : n2.x, fx = negx ? n2.x : n3.z;
                     const uint32_t ny = negy ? n4.x : n2.z, fy = negy ? n2.z : n4.x;
                     const uint32_t nz = negz ? n4.z : n3.x, fz = negz ? n3.x : n4.z;
-                    testChild<0>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
-                    testChild<1>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
-                    testChild<2>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
-                    testChild<3>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                    testChild<0, 0>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
+                    testChild<1, 1>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
+                    testChild<2, 2>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
+                    testChild<3, 3>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
                 }
                 {
-                    const uint32_t meta4 = n1.w;
-                    const uint32_t innerMask4 = (((meta4 & (meta4 << 1)) & 0x10101010u) >> 4) * 0xFFu;
-                    const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
-                    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
                     const uint32_t nx = negx ? n3.w : n2.y, fx = negx ? n2.y : n3.w;
                     const uint32_t ny = negy ? n4.y : n2.w, fy = negy ? n2.w : n4.y;
                     const uint32_t nz = negz ? n4.w : n3.y, fz = negz ? n3.y : n4.w;
-                    testChild<0>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
-                    testChild<1>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
-                    testChild<2>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
-                    testChild<3>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, childBits4, bitIndex4, hitmask);
+                    testChild<0, 4>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
+                    testChild<1, 5>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
+                    testChild<2, 6>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
+                    testChild<3, 7>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
                 }
+                hitmask &= n1.z;   // valid: imask << 24 | the triangle bits the leaf slots own
+                // inner bits from slot order to traversal order: bit 24 + s -> 24 + (s ^ octinv)
+                uint32_t top = hitmask >> 24;
+                if (octinv4 & 1u) top = ((top & 0x55u) << 1) | ((top >> 1) & 0x55u);
+                if (octinv4 & 2u) top = ((top & 0x33u) << 2) | ((top >> 2) & 0x33u);
+                if (octinv4 & 4u) top = ((top & 0x0Fu) << 4) | (top >> 4);
+                P = n1.z & 0x00FFFFFFu;
+                hitmask = (hitmask & 0x00FFFFFFu) | (top << 24);
                 G = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
                 T = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
             } else {
-                T = G;                     // a popped triangle group
+                T = G;                     // a postponed triangle group: its presence mask was pushed beneath it
                 G = make_uint2(0u, 0u);
+                P = pop().x;
             }
         }
 
@@ -166,11 +180,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArg
         for (;;) {
             const unsigned m = __ballot_sync(0xFFFFFFFFu, T.y != 0u);
             if (!m) break;
-            if (T.y != 0u && __popc(m) < POSTPONE8 && (G.y & 0xFF000000u)) { push(T); T.y = 0u; }   // postpone: this lane has node work
+            if (T.y != 0u && __popc(m) < POSTPONE8 && (G.y & 0xFF000000u)) { push(make_uint2(P, 0u)); push(T); T.y = 0u; }   // postpone: this lane has node work
             if (T.y != 0u) {
                 const uint32_t bit = 31u - (uint32_t)__clz(T.y);
                 T.y &= ~(1u << bit);
-                const float4* tp = a.tris + (size_t)(T.x + bit) * 3;
+                const float4* tp = a.tris + (size_t)(T.x + (uint32_t)__popc(P & ~(0xFFFFFFFFu << bit))) * 3;
                 const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
                 if (COUNT) cTris++;
                 float u, v, t, aa;

@@ -65,11 +65,12 @@ static_assert(sizeof(BvhNode) == 64, "BVH node is 64 bytes");
 //   imask       bit s set: child slot s is an inner node
 //   childBase   index of the first inner child (inner children are consecutive, in slot order)
 //   triBase     index of the first triangle of the leaf children (consecutive, in slot order, at most 24)
-//   meta[s]     empty 0 | inner (1 << 5) | (24 + s) | leaf (unary triangle count << 5) | triangle offset
+//   valid       imask << 24 | triangle presence: leaf slot s holding c <= 3 triangles sets bits 3s .. 3s+c-1; the
+//               triangle at bit b is triBase + popcount(presence bits below b)
 //   qlo, qhi    child boxes on the grid: lo = p + qlo * 2^e, hi = p + qhi * 2^e (rounded outwards)
 struct alignas(16) Node8 {
     float p[3]; uint8_t e[3]; uint8_t imask;
-    uint32_t childBase, triBase; uint8_t meta[8];
+    uint32_t childBase, triBase, valid, reserved;
     uint8_t qlo[3][8];
     uint8_t qhi[3][8];
 };

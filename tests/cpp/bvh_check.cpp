@@ -49,7 +49,7 @@ static bool walk8(const std::vector<Node8>& nodes, const std::vector<TravTri>& t
     struct G2 { uint32_t x, y; };
     G2 stack[64]; int sp = 0; G2 G = {0u, 0x80000000u};
     for (;;) {
-        G2 T = {0u, 0u};
+        G2 T = {0u, 0u}; uint32_t P = 0;
         if (G.y & 0xFF000000u) {
             const uint32_t hits = G.y;
             const uint32_t bit = 31u - (uint32_t)__builtin_clz(hits);
@@ -65,27 +65,32 @@ static bool walk8(const std::vector<Node8>& nodes, const std::vector<TravTri>& t
             const float cx = (n.p[0] - ro.x) * idx - kx, cy = (n.p[1] - ro.y) * idy - ky, cz = (n.p[2] - ro.z) * idz - kz;
             uint32_t hitmask = 0;
             for (int half = 0; half < 2; ++half) {
-                const uint32_t meta4 = w[6 + half];
-                const uint32_t innerMask4 = (((meta4 & (meta4 << 1)) & 0x10101010u) >> 4) * 0xFFu;
-                const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
-                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
                 const uint32_t lox = w[8 + half], loy = w[10 + half], loz = w[12 + half], hix = w[14 + half], hiy = w[16 + half], hiz = w[18 + half];
                 const uint32_t nx = idx < 0 ? hix : lox, fx = idx < 0 ? lox : hix, ny = idy < 0 ? hiy : loy, fy = idy < 0 ? loy : hiy, nz = idz < 0 ? hiz : loz, fz = idz < 0 ? loz : hiz;
                 for (int j = 0; j < 4; ++j) {
+                    const int sl = 4 * half + j;
                     const float tnx = std::fma(byteFrac(nx, j), kx, cx), tny = std::fma(byteFrac(ny, j), ky, cy), tnz = std::fma(byteFrac(nz, j), kz, cz);
                     const float tfx = std::fma(byteFrac(fx, j), kx, cx), tfy = std::fma(byteFrac(fy, j), ky, cy), tfz = std::fma(byteFrac(fz, j), kz, cz);
                     const float cmin = std::fmax(std::fmax(tnx, tny), std::fmax(tnz, 0.0f)), cmax = std::fmin(std::fmin(tfx, tfy), std::fmin(tfz, best));
-                    if (cmin <= cmax) hitmask |= ((childBits4 >> (8 * j)) & 0xFFu) << ((bitIndex4 >> (8 * j)) & 0xFFu);
+                    if (cmin <= cmax) hitmask |= (1u << (24 + sl)) | (7u << (3 * sl));
                 }
             }
+            hitmask &= n.valid;
+            uint32_t top = hitmask >> 24;
+            if (octinv & 1u) top = ((top & 0x55u) << 1) | ((top >> 1) & 0x55u);
+            if (octinv & 2u) top = ((top & 0x33u) << 2) | ((top >> 2) & 0x33u);
+            if (octinv & 4u) top = ((top & 0x0Fu) << 4) | (top >> 4);
+            hitmask = (hitmask & 0x00FFFFFFu) | (top << 24);
+            P = n.valid & 0x00FFFFFFu;
             G = {n.childBase, (hitmask & 0xFF000000u) | n.imask};
             T = {n.triBase, hitmask & 0x00FFFFFFu};
-        } else { T = G; G = {0u, 0u}; }
+        } else { return false; /* the CPU mirror never postpones */ }
         while (T.y) {
             const uint32_t bit = 31u - (uint32_t)__builtin_clz(T.y);
             T.y &= ~(1u << bit);
-            if (T.x + bit >= tt.size()) return false;
-            const TravTri& t = tt[T.x + bit];
+            const uint32_t ti = T.x + (uint32_t)__builtin_popcount(P & ~(0xFFFFFFFFu << bit));
+            if (ti >= tt.size()) return false;
+            const TravTri& t = tt[ti];
             float tv;
             if (tri(ro, rd, V{t.p0[0], t.p0[1], t.p0[2]}, V{t.e1[0], t.e1[1], t.e1[2]}, V{t.e2[0], t.e2[1], t.e2[2]}, tv))
                 if (tv < best || (tv == best && t.id < bestId)) { best = tv; bestId = t.id; }
