@@ -370,7 +370,7 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
     if (count == 0) return;
     threads = resolveThreads(threads);
     BinaryTree bt;
-    buildBinary(tris, count, threads, CWBVH_MAX_LEAF, bt);
+    buildBinary(tris, count, threads, 1, bt);   // down to single triangles: the collapse below decides the leaves
     const std::vector<TNode>& all = bt.all;
 
     struct Child { int32_t link; Box box; };
@@ -383,21 +383,69 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
     double cost = 0.0;
     uint32_t leaves = 0, maxDepth = 0;
 
+    // ---- which binary nodes become 8-wide nodes: the SAH-optimal collapse of Ylitie et al. (section 3.1) -----------
+    //   c(n, i)  = cheapest way to represent subtree n with at most i roots (each root = one child slot of the parent)
+    //   c(n, 1)  = min(leaf: A_n * P_n * C_PRIM if P_n <= 3,  inner: distribute(n, 8) + A_n * C_NODE)
+    //   c(n, i)  = min(distribute(n, i), c(n, i - 1));   distribute(n, j) = min_k c(left, k) + c(right, j - k)
+    // evaluated bottom-up (children always have larger indices than their parent), decisions replayed top-down.
+    constexpr float C_NODE = 1.0f, C_PRIM = 0.3f;
+    const size_t nInner = all.size();
+    struct Dp { float c[8]; uint8_t split[9]; uint8_t dec[8]; uint32_t triFirst, triCnt; };
+    std::vector<Dp> dp(nInner);
+    auto linkCost = [&](int32_t link, const Box& box, int i) { return link >= 0 ? dp[(size_t)link].c[i] : box.area() * (float)leafCount(link) * C_PRIM; };
+    auto linkFirst = [&](int32_t link) { return link >= 0 ? dp[(size_t)link].triFirst : leafFirst(link); };
+    auto linkCnt = [&](int32_t link) { return link >= 0 ? dp[(size_t)link].triCnt : leafCount(link); };
+    for (size_t r = nInner; r-- > 0;) {
+        const TNode& t = all[r];
+        Dp& d = dp[r];
+        Box nb; nb = t.b0; nb.grow(t.b1);
+        const float A = nb.area();
+        d.triFirst = std::min(linkFirst(t.c0), linkFirst(t.c1));
+        d.triCnt = linkCnt(t.c0) + linkCnt(t.c1);
+        float dist[9];
+        for (int j = 2; j <= 8; ++j) {
+            dist[j] = std::numeric_limits<float>::infinity(); d.split[j] = 1;
+            for (int k = std::max(1, j - 7); k <= std::min(7, j - 1); ++k) {
+                const float v = linkCost(t.c0, t.b0, k) + linkCost(t.c1, t.b1, j - k);
+                if (v < dist[j]) { dist[j] = v; d.split[j] = (uint8_t)k; }
+            }
+        }
+        const float cInner = dist[8] + A * C_NODE;
+        const float cLeaf = d.triCnt <= CWBVH_MAX_LEAF ? A * (float)d.triCnt * C_PRIM : std::numeric_limits<float>::infinity();
+        d.c[0] = 0.0f; d.dec[0] = 0;
+        d.c[1] = std::min(cLeaf, cInner); d.dec[1] = cInner < cLeaf ? 1 : 0;
+        for (int i = 2; i <= 7; ++i) {
+            if (dist[i] < d.c[i - 1]) { d.c[i] = dist[i]; d.dec[i] = 1; } else { d.c[i] = d.c[i - 1]; d.dec[i] = 0; }
+        }
+    }
+
     while (!queue.empty()) {
         const Work w = queue.front(); queue.pop_front();
         maxDepth = std::max(maxDepth, w.depth);
         Child ch[8]; int n = 0;
         if (w.bin < 0) { ch[0] = {w.bin, w.box}; n = 1; }
         else {
-            ch[0] = {all[(size_t)w.bin].c0, all[(size_t)w.bin].b0}; ch[1] = {all[(size_t)w.bin].c1, all[(size_t)w.bin].b1}; n = 2;
-            // greedy collapse: open the inner child with the largest surface area until 8 children
-            while (n < 8) {
-                int pick = -1; float bestArea = -1.0f;
-                for (int i = 0; i < n; ++i) if (ch[i].link >= 0) { const float ar = ch[i].box.area(); if (ar > bestArea) { bestArea = ar; pick = i; } }
-                if (pick < 0) break;
-                const TNode& t = all[(size_t)ch[pick].link];
-                ch[pick] = {t.c0, t.b0};
-                ch[n++] = {t.c1, t.b1};
+            // replay the decisions: the 8 slots of this node are distributed over the two binary children
+            struct Item { int32_t link; Box box; int i; };
+            Item st[16]; int sn = 0;
+            const TNode& top = all[(size_t)w.bin];
+            const int k0 = dp[(size_t)w.bin].split[8];
+            st[sn++] = {top.c1, top.b1, 8 - k0};
+            st[sn++] = {top.c0, top.b0, k0};
+            while (sn > 0) {
+                const Item it = st[--sn];
+                if (it.link < 0) { ch[n++] = {it.link, it.box}; continue; }
+                const Dp& d = dp[(size_t)it.link];
+                if (it.i == 1) {
+                    if (d.dec[1]) ch[n++] = {it.link, it.box};                                  // a new 8-wide node
+                    else ch[n++] = {leafLink(d.triFirst, d.triCnt), it.box};                     // the whole subtree as one leaf slot
+                    continue;
+                }
+                if (!d.dec[it.i]) { st[sn++] = {it.link, it.box, it.i - 1}; continue; }
+                const TNode& t = all[(size_t)it.link];
+                const int k = d.split[it.i];
+                st[sn++] = {t.c1, t.b1, it.i - k};
+                st[sn++] = {t.c0, t.b0, k};
             }
         }
         Box nb; nb.reset();
