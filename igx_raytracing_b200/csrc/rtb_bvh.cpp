@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -388,7 +389,8 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
     //   c(n, 1)  = min(leaf: A_n * P_n * C_PRIM if P_n <= 3,  inner: distribute(n, 8) + A_n * C_NODE)
     //   c(n, i)  = min(distribute(n, i), c(n, i - 1));   distribute(n, j) = min_k c(left, k) + c(right, j - k)
     // evaluated bottom-up (children always have larger indices than their parent), decisions replayed top-down.
-    constexpr float C_NODE = 1.0f, C_PRIM = 0.3f;
+    float C_NODE = 1.0f, C_PRIM = 1.0f;   // measured on B200: a triangle test costs the traversal about what a node costs
+    if (const char* e = std::getenv("RTB_CPRIM")) C_PRIM = (float)std::atof(e);   // tuning hook
     const size_t nInner = all.size();
     struct Dp { float c[8]; uint8_t split[9]; uint8_t dec[8]; uint32_t triFirst, triCnt; };
     std::vector<Dp> dp(nInner);
@@ -491,12 +493,36 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
         uint32_t triOffset = 0, innerCount = 0;
         for (int s = 0; s < 8; ++s) {
             const int i = childAt[s];
-            if (i < 0) { out.qlo[0][s] = out.qlo[1][s] = out.qlo[2][s] = 255; out.qhi[0][s] = out.qhi[1][s] = out.qhi[2][s] = 0; continue; }
+            // bf16 bits of a non-negative grid coordinate, rounded towards -inf / +inf
+            auto valueOf = [](uint32_t t) { float f; std::memcpy(&f, &t, 4); return (double)f; };
+            auto bf16Down = [&](double g) {
+                g = std::max(0.0, g);
+                const float f = (float)g; uint32_t b; std::memcpy(&b, &f, 4);
+                uint32_t t = b & 0xFFFF0000u;                      // truncation = towards zero
+                if (valueOf(t) > g && t >= 0x10000u) t -= 0x10000u;  // (float)g rounded up onto a bf16 value
+                return t >> 16;
+            };
+            auto bf16Up = [&](double g) {
+                g = std::max(0.0, g);
+                const float f = (float)g; uint32_t b; std::memcpy(&b, &f, 4);
+                uint32_t t = b & 0xFFFF0000u;
+                if (valueOf(t) < g) t += 0x10000u;
+                return t >> 16;
+            };
+            const bool upper = (s & 1) == 0;   // even slots live in the upper half of their word and are read without decoding
+            const int word = s >> 1, shift = upper ? 16 : 0;
+            if (i < 0) {   // empty slot: an inverted box (the valid mask removes its bits anyway)
+                for (int a = 0; a < 3; ++a) { out.lo[a][word] |= 0x4380u << shift; /* 256.0 */ }
+                continue;
+            }
             for (int a = 0; a < 3; ++a) {
-                const double lo = ((double)ch[i].box.lo[a] - (double)out.p[a]) / step[a], hi = ((double)ch[i].box.hi[a] - (double)out.p[a]) / step[a];
-                const double ql = std::floor(lo - 0.02), qh = std::ceil(hi + 0.02);
-                out.qlo[a][s] = (uint8_t)std::max(0.0, std::min(255.0, ql));
-                out.qhi[a][s] = (uint8_t)std::max(0.0, std::min(255.0, qh));
+                const double lo = ((double)ch[i].box.lo[a] - (double)out.p[a]) / step[a] - 0.02, hi = ((double)ch[i].box.hi[a] - (double)out.p[a]) / step[a] + 0.02;
+                uint32_t ql = bf16Down(lo), qh = bf16Up(hi);
+                // an upper-half value is read together with the 16 bits below it: it may appear up to one bf16 step larger.
+                // Harmless for hi planes (a larger box); lo planes are stored one step lower to stay conservative.
+                if (upper && ql > 0) ql -= 1;
+                out.lo[a][word] |= ql << shift;
+                out.hi[a][word] |= qh << shift;
             }
             const float rel = ch[i].box.area() / rootArea;
             if (ch[i].link >= 0) {

@@ -2,65 +2,68 @@
 //
 // One warp = 32 rays in flight.  Per iteration, in lock-step:
 //   A  every lane whose current node group still has hit inner children takes the nearest one (highest bit of the
-//      octant-permuted hit mask), fetches its 80-byte record (5 x LDG.128, or shared memory for the top of the tree)
-//      and tests the 8 quantised child boxes; the result is a new node group and a triangle group;
+//      octant-permuted hit mask), fetches its 128-byte record (8 x 16-byte vector loads from one cache line, or
+//      shared memory for the top of the tree) and tests the 8 child boxes; the result is a new node group and a
+//      triangle group;
 //   B  triangle groups are drained with Möller–Trumbore (the reference's arithmetic, SH/primitive.glsl:239-284);
 //      when only a few lanes hold triangles and they still have node work, they postpone the group onto their stack;
 //   C  lanes with nothing left in their group pop their stack, or retire the ray;
 //   D  when fewer than REFILL8 lanes are still busy the idle lanes take new rays from the wavefront with one
 //      warp-aggregated atomic (ballot + shfl).
+//
+// Box planes are bf16 grid coordinates packed two per word (Node8 in rtb_types.h).  The plane in the upper half is
+// used as it stands (the word read as a float), the one in the lower half costs one shift; which of the lo / hi
+// vectors is "near" is decided once per ray and applied as a load offset, so decoding takes no ALU-pipe work and the
+// slab arithmetic is 48 FFMA per node.
+//
 // The per-lane stack holds 8-byte (base, mask) groups: the first SM_STACK entries in shared memory ([entry][thread],
 // conflict-free for any mix of depths), the rest in local memory.
 #pragma once
 
 namespace rtb {
 
-constexpr int TOP8_NODES = 192;      // 15 KB of shared memory: the breadth-first top of the tree
+constexpr int TOP8_NODES = 128;      // 16 KB of shared memory: the breadth-first top of the tree
 constexpr int SM_STACK = 8;          // 16 KB of shared memory per 256-thread block
-constexpr int LOCAL_STACK = 56;      // the builder refuses trees that could need more than SM_STACK + LOCAL_STACK entries
+constexpr int LOCAL_STACK = 56;      // rtb_build_accel refuses trees that could need more than SM_STACK + LOCAL_STACK entries
 constexpr int REFILL8 = 22;
 constexpr int POSTPONE8 = 8;
+constexpr uint32_t PLANES_LO = 32u, PLANES_HI = 80u;   // byte offsets of lo[3][4] and hi[3][4] in Node8
 
-// byte J of w as 1 + b * 2^-15 (one PRMT with an immediate selector; `one` = 0x3F800000 held in a register): with
-// K = 2^15 * step / d and C = (p - o) / d - K, fma(f, K, C) = (p + b * step - o) / d
-template <int J>
-RTB_DI float byteFrac(uint32_t w, uint32_t one) {
-    uint32_t r;
-    if (J == 0) asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(w), "r"(one));
-    else if (J == 1) asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(w), "r"(one));
-    else if (J == 2) asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(r) : "r"(w), "r"(one));
-    else asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(w), "r"(one));
-    return __uint_as_float(r);
-}
-
-// child slot S = 4 * HALF + J: a hit sets the slot's inner bit (24 + S) and its three triangle bits (3S .. 3S+2);
-// the node's valid mask removes what the slot does not hold
-template <int J, int S>
-RTB_DI void testChild(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float kx, float ky, float kz,
-                      float cx, float cy, float cz, float best, uint32_t one, uint32_t& hitmask) {
-    const float tnx = fmaf(byteFrac<J>(nx, one), kx, cx), tny = fmaf(byteFrac<J>(ny, one), ky, cy), tnz = fmaf(byteFrac<J>(nz, one), kz, cz);
-    const float tfx = fmaf(byteFrac<J>(fx, one), kx, cx), tfy = fmaf(byteFrac<J>(fy, one), ky, cy), tfz = fmaf(byteFrac<J>(fz, one), kz, cz);
-    const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-    const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, best));
-    if (cmin <= cmax) hitmask |= (1u << (24 + S)) | (7u << (3 * S));
+// children S (upper halves) and S + 1 (lower halves) of one word triple per axis
+template <int S>
+RTB_DI void testPair(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float kx, float ky, float kz,
+                     float cx, float cy, float cz, float best, uint32_t& hitmask) {
+    {
+        const float tnx = fmaf(__uint_as_float(nx), kx, cx), tny = fmaf(__uint_as_float(ny), ky, cy), tnz = fmaf(__uint_as_float(nz), kz, cz);
+        const float tfx = fmaf(__uint_as_float(fx), kx, cx), tfy = fmaf(__uint_as_float(fy), ky, cy), tfz = fmaf(__uint_as_float(fz), kz, cz);
+        const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+        const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, best));
+        if (cmin <= cmax) hitmask |= (1u << (24 + S)) | (7u << (3 * S));
+    }
+    {
+        const float tnx = fmaf(__uint_as_float(nx << 16), kx, cx), tny = fmaf(__uint_as_float(ny << 16), ky, cy), tnz = fmaf(__uint_as_float(nz << 16), kz, cz);
+        const float tfx = fmaf(__uint_as_float(fx << 16), kx, cx), tfy = fmaf(__uint_as_float(fy << 16), ky, cy), tfz = fmaf(__uint_as_float(fz << 16), kz, cz);
+        const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+        const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, best));
+        if (cmin <= cmax) hitmask |= (1u << (25 + S)) | (7u << (3 * S + 3));
+    }
 }
 
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArgs a) {
-    __shared__ uint4 sTop[TOP8_NODES * 5];
+    __shared__ uint4 sTop[TOP8_NODES * 8];
     __shared__ uint2 sStack[SM_STACK][TRACE_THREADS];
     const int topN = min((int)a.nodeCount, TOP8_NODES);
-    for (int i = threadIdx.x; i < topN * 5; i += TRACE_THREADS) sTop[i] = __ldg(a.nodes8 + i);
+    for (int i = threadIdx.x; i < topN * 8; i += TRACE_THREADS) sTop[i] = __ldg(a.nodes8 + i);
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
     uint2 lstack[LOCAL_STACK];
-    uint32_t one;
-    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one));   // kept in a register so PRMT can take its selector as an immediate
 
     bool active = false, exhausted = false;
-    uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT, octinv4 = 0;
+    uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT, octinv = 0;
+    uint32_t nearX = 0, nearY = 0, nearZ = 0;   // byte offsets of the near-plane vectors inside a node, per ray
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
     float best = 0, bu = 0, bv = 0;
     uint2 G = make_uint2(0u, 0u);
@@ -93,7 +96,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArg
                         idy = 1.0f / (fabsf(dy) > tiny ? dy : copysignf(tiny, dy));
                         idz = 1.0f / (fabsf(dz) > tiny ? dz : copysignf(tiny, dz));
                         // bit set = the ray travels towards + on that axis; slot s ^ octinv orders children far -> near
-                        octinv4 = ((idx < 0.0f ? 0u : 1u) | (idy < 0.0f ? 0u : 2u) | (idz < 0.0f ? 0u : 4u)) * 0x01010101u;
+                        octinv = (idx < 0.0f ? 0u : 1u) | (idy < 0.0f ? 0u : 2u) | (idz < 0.0f ? 0u : 4u);
+                        nearX = idx < 0.0f ? PLANES_HI : PLANES_LO;
+                        nearY = (idy < 0.0f ? PLANES_HI : PLANES_LO) + 16u;
+                        nearZ = (idz < 0.0f ? PLANES_HI : PLANES_LO) + 32u;
                         bestId = NO_RAY_HIT; bu = 0.0f; bv = 0.0f;
                         sp = 0; G = make_uint2(0u, 0x80000000u);   // the root as a one-node group
                         active = true;
@@ -119,55 +125,45 @@ __global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArg
             if (G.y & 0xFF000000u) {
                 const uint32_t hits = G.y;
                 const uint32_t bit = 31u - (uint32_t)__clz(hits);
-                const uint32_t childSlot = (bit - 24u) ^ (octinv4 & 7u);
+                const uint32_t childSlot = (bit - 24u) ^ octinv;
                 const uint32_t rel = (uint32_t)__popc(hits & 0xFFu & ~(0xFFFFFFFFu << childSlot));
                 const uint32_t nodeIdx = G.x + rel;
                 G.y &= ~(1u << bit);
                 if (G.y & 0xFF000000u) push(G);
-                uint4 n0, n1, n2, n3, n4;
+                uint4 n0, n1, wnx, wny, wnz, wfx, wfy, wfz;
+                const uint32_t farX = (PLANES_LO + PLANES_HI) - nearX, farY = (PLANES_LO + PLANES_HI + 32u) - nearY, farZ = (PLANES_LO + PLANES_HI + 64u) - nearZ;
                 if ((int)nodeIdx < topN) {
-                    const uint4* p = sTop + nodeIdx * 5;
-                    n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3]; n4 = p[4];
+                    const char* p = reinterpret_cast<const char*>(sTop) + nodeIdx * 128u;
+                    n0 = *reinterpret_cast<const uint4*>(p); n1 = *reinterpret_cast<const uint4*>(p + 16);
+                    wnx = *reinterpret_cast<const uint4*>(p + nearX); wny = *reinterpret_cast<const uint4*>(p + nearY); wnz = *reinterpret_cast<const uint4*>(p + nearZ);
+                    wfx = *reinterpret_cast<const uint4*>(p + farX); wfy = *reinterpret_cast<const uint4*>(p + farY); wfz = *reinterpret_cast<const uint4*>(p + farZ);
                 } else {
-                    const uint4* p = a.nodes8 + (size_t)nodeIdx * 5;
-                    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); n4 = __ldg(p + 4);
+                    const char* p = reinterpret_cast<const char*>(a.nodes8) + (size_t)nodeIdx * 128u;
+                    n0 = __ldg(reinterpret_cast<const uint4*>(p)); n1 = __ldg(reinterpret_cast<const uint4*>(p + 16));
+                    wnx = __ldg(reinterpret_cast<const uint4*>(p + nearX)); wny = __ldg(reinterpret_cast<const uint4*>(p + nearY)); wnz = __ldg(reinterpret_cast<const uint4*>(p + nearZ));
+                    wfx = __ldg(reinterpret_cast<const uint4*>(p + farX)); wfy = __ldg(reinterpret_cast<const uint4*>(p + farY)); wfz = __ldg(reinterpret_cast<const uint4*>(p + farZ));
                 }
                 if (COUNT) cNodes++;
-                const float kx = __uint_as_float(((n0.w & 0xFFu) + 15u) << 23) * idx;
-                const float ky = __uint_as_float((((n0.w >> 8) & 0xFFu) + 15u) << 23) * idy;
-                const float kz = __uint_as_float((((n0.w >> 16) & 0xFFu) + 15u) << 23) * idz;
-                const float cx = (__uint_as_float(n0.x) - ox) * idx - kx;
-                const float cy = (__uint_as_float(n0.y) - oy) * idy - ky;
-                const float cz = (__uint_as_float(n0.z) - oz) * idz - kz;
-                const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
+                // plane at grid coordinate g along x: t = (p.x + g * 2^e - o.x) / d.x = g * kx + cx
+                const float kx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
+                const float ky = __uint_as_float((n0.w << 15) & 0x7F800000u) * idy;
+                const float kz = __uint_as_float((n0.w << 7) & 0x7F800000u) * idz;
+                const float cx = (__uint_as_float(n0.x) - ox) * idx;
+                const float cy = (__uint_as_float(n0.y) - oy) * idy;
+                const float cz = (__uint_as_float(n0.z) - oz) * idz;
                 uint32_t hitmask = 0;
-                {
-                    const uint32_t nx = negx ? n3.z : n2.x, fx = negx ? n2.x : n3.z;
-                    const uint32_t ny = negy ? n4.x : n2.z, fy = negy ? n2.z : n4.x;
-                    const uint32_t nz = negz ? n4.z : n3.x, fz = negz ? n3.x : n4.z;
-                    testChild<0, 0>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
-                    testChild<1, 1>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
-                    testChild<2, 2>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
-                    testChild<3, 3>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
-                }
-                {
-                    const uint32_t nx = negx ? n3.w : n2.y, fx = negx ? n2.y : n3.w;
-                    const uint32_t ny = negy ? n4.y : n2.w, fy = negy ? n2.w : n4.y;
-                    const uint32_t nz = negz ? n4.w : n3.y, fz = negz ? n3.y : n4.w;
-                    testChild<0, 4>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
-                    testChild<1, 5>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
-                    testChild<2, 6>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
-                    testChild<3, 7>(nx, ny, nz, fx, fy, fz, kx, ky, kz, cx, cy, cz, best, one, hitmask);
-                }
+                testPair<0>(wnx.x, wny.x, wnz.x, wfx.x, wfy.x, wfz.x, kx, ky, kz, cx, cy, cz, best, hitmask);
+                testPair<2>(wnx.y, wny.y, wnz.y, wfx.y, wfy.y, wfz.y, kx, ky, kz, cx, cy, cz, best, hitmask);
+                testPair<4>(wnx.z, wny.z, wnz.z, wfx.z, wfy.z, wfz.z, kx, ky, kz, cx, cy, cz, best, hitmask);
+                testPair<6>(wnx.w, wny.w, wnz.w, wfx.w, wfy.w, wfz.w, kx, ky, kz, cx, cy, cz, best, hitmask);
                 hitmask &= n1.z;   // valid: imask << 24 | the triangle bits the leaf slots own
                 // inner bits from slot order to traversal order: bit 24 + s -> 24 + (s ^ octinv)
                 uint32_t top = hitmask >> 24;
-                if (octinv4 & 1u) top = ((top & 0x55u) << 1) | ((top >> 1) & 0x55u);
-                if (octinv4 & 2u) top = ((top & 0x33u) << 2) | ((top >> 2) & 0x33u);
-                if (octinv4 & 4u) top = ((top & 0x0Fu) << 4) | (top >> 4);
+                if (octinv & 1u) top = ((top & 0x55u) << 1) | ((top >> 1) & 0x55u);
+                if (octinv & 2u) top = ((top & 0x33u) << 2) | ((top >> 2) & 0x33u);
+                if (octinv & 4u) top = ((top & 0x0Fu) << 4) | (top >> 4);
                 P = n1.z & 0x00FFFFFFu;
-                hitmask = (hitmask & 0x00FFFFFFu) | (top << 24);
-                G = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
+                G = make_uint2(n1.x, (top << 24) | (n0.w >> 24));
                 T = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
             } else {
                 T = G;                     // a postponed triangle group: its presence mask was pushed beneath it

@@ -60,21 +60,25 @@ struct alignas(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BVH node is 64 bytes");
 
-// 8-wide compressed node, 80 bytes = five 16-byte vector loads (layout after Ylitie et al. 2017):
-//   p, e        origin and per-axis exponent (biased by 127) of the node's quantisation grid
+// 8-wide compressed node, 128 bytes = one cache line = eight 16-byte vector loads.  The topology fields follow
+// Ylitie et al. 2017; the box encoding is ours:
+//   p, e        origin and per-axis exponent (biased by 127) of the node's grid: world = p + g * 2^e
 //   imask       bit s set: child slot s is an inner node
 //   childBase   index of the first inner child (inner children are consecutive, in slot order)
 //   triBase     index of the first triangle of the leaf children (consecutive, in slot order, at most 24)
 //   valid       imask << 24 | triangle presence: leaf slot s holding c <= 3 triangles sets bits 3s .. 3s+c-1; the
 //               triangle at bit b is triBase + popcount(presence bits below b)
-//   qlo, qhi    child boxes on the grid: lo = p + qlo * 2^e, hi = p + qhi * 2^e (rounded outwards)
-struct alignas(16) Node8 {
+//   lo, hi      child box planes as bf16 grid coordinates g in [0, 256), two children per word: slot 2k in the
+//               upper half, slot 2k+1 in the lower half.  The traversal reads the upper value by taking the whole
+//               word as a float (no decode), which can only enlarge it by less than one bf16 step, so the builder
+//               rounds upper-half lo planes down by one extra step; every stored box contains the true box.
+struct alignas(128) Node8 {
     float p[3]; uint8_t e[3]; uint8_t imask;
     uint32_t childBase, triBase, valid, reserved;
-    uint8_t qlo[3][8];
-    uint8_t qhi[3][8];
+    uint32_t lo[3][4];
+    uint32_t hi[3][4];
 };
-static_assert(sizeof(Node8) == 80, "CWBVH node is 80 bytes");
+static_assert(sizeof(Node8) == 128, "CWBVH node is 128 bytes");
 
 // Traversal triangle, in leaf order: p0, e1 = p1 - p0, e2 = p2 - p0 (the same float subtractions the
 // reference shader performs per test, done once), and the triangle's index in the uploaded array.

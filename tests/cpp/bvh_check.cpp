@@ -34,9 +34,7 @@ static bool tri(V ro, V rd, V p0, V e1, V e2, float& t) {
 }
 
 
-// ---- CPU mirror of k_trace_cwbvh (rtb_trace8.cuh): same octant ordering, byte decode (1 + b * 2^-15), fma planes ----
-static float byteFrac(uint32_t w, int j) { uint32_t b = (w >> (8 * j)) & 0xFFu; uint32_t u = 0x3F800000u | (b << 8); float f; std::memcpy(&f, &u, 4); return f; }
-static float expo(uint32_t e) { uint32_t u = (e + 15u) << 23; float f; std::memcpy(&f, &u, 4); return f; }
+// ---- CPU mirror of k_trace_cwbvh (rtb_trace8.cuh): same octant ordering, bf16 plane decode (upper half undecoded), fma planes ----
 static uint32_t fbitsU(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 
 static bool walk8(const std::vector<Node8>& nodes, const std::vector<TravTri>& tt, V ro, V rd, float& best, uint32_t& bestId, int& maxSp) {
@@ -60,17 +58,18 @@ static bool walk8(const std::vector<Node8>& nodes, const std::vector<TravTri>& t
             if (G.y & 0xFF000000u) { if (sp >= 64) return false; stack[sp++] = G; }
             if (ni >= nodes.size()) return false;
             const Node8& n = nodes[ni];
-            uint32_t w[20]; std::memcpy(w, &n, 80);
-            const float kx = expo(n.e[0]) * idx, ky = expo(n.e[1]) * idy, kz = expo(n.e[2]) * idz;
-            const float cx = (n.p[0] - ro.x) * idx - kx, cy = (n.p[1] - ro.y) * idy - ky, cz = (n.p[2] - ro.z) * idz - kz;
+            auto asf = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+            const float kx = asf((uint32_t)n.e[0] << 23) * idx, ky = asf((uint32_t)n.e[1] << 23) * idy, kz = asf((uint32_t)n.e[2] << 23) * idz;
+            const float cx = (n.p[0] - ro.x) * idx, cy = (n.p[1] - ro.y) * idy, cz = (n.p[2] - ro.z) * idz;
             uint32_t hitmask = 0;
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t lox = w[8 + half], loy = w[10 + half], loz = w[12 + half], hix = w[14 + half], hiy = w[16 + half], hiz = w[18 + half];
-                const uint32_t nx = idx < 0 ? hix : lox, fx = idx < 0 ? lox : hix, ny = idy < 0 ? hiy : loy, fy = idy < 0 ? loy : hiy, nz = idz < 0 ? hiz : loz, fz = idz < 0 ? loz : hiz;
-                for (int j = 0; j < 4; ++j) {
-                    const int sl = 4 * half + j;
-                    const float tnx = std::fma(byteFrac(nx, j), kx, cx), tny = std::fma(byteFrac(ny, j), ky, cy), tnz = std::fma(byteFrac(nz, j), kz, cz);
-                    const float tfx = std::fma(byteFrac(fx, j), kx, cx), tfy = std::fma(byteFrac(fy, j), ky, cy), tfz = std::fma(byteFrac(fz, j), kz, cz);
+            for (int word = 0; word < 4; ++word) {
+                const uint32_t nx = idx < 0 ? n.hi[0][word] : n.lo[0][word], fx = idx < 0 ? n.lo[0][word] : n.hi[0][word];
+                const uint32_t ny = idy < 0 ? n.hi[1][word] : n.lo[1][word], fy = idy < 0 ? n.lo[1][word] : n.hi[1][word];
+                const uint32_t nz = idz < 0 ? n.hi[2][word] : n.lo[2][word], fz = idz < 0 ? n.lo[2][word] : n.hi[2][word];
+                for (int half = 0; half < 2; ++half) {   // half 0: upper 16 bits read as the whole word; half 1: lower 16 bits shifted up
+                    const int sl = 2 * word + half, sh = half ? 16 : 0;
+                    const float tnx = std::fma(asf(nx << sh), kx, cx), tny = std::fma(asf(ny << sh), ky, cy), tnz = std::fma(asf(nz << sh), kz, cz);
+                    const float tfx = std::fma(asf(fx << sh), kx, cx), tfy = std::fma(asf(fy << sh), ky, cy), tfz = std::fma(asf(fz << sh), kz, cz);
                     const float cmin = std::fmax(std::fmax(tnx, tny), std::fmax(tnz, 0.0f)), cmax = std::fmin(std::fmin(tfx, tfy), std::fmin(tfz, best));
                     if (cmin <= cmax) hitmask |= (1u << (24 + sl)) | (7u << (3 * sl));
                 }
