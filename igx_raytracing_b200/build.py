@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "librtb200.so")
+LIB = os.environ.get("RTB_LIB_OUT", os.path.join(HERE, "librtb200.so"))   # RTB_LIB_OUT / RTB_NVCC_EXTRA: tuning variants
 SOURCES = ["rtb_api.cu", "rtb_kernels.cu", "rtb_bvh.cpp", "rtb_host.cpp"]
 HEADERS = ["rtb_types.h", "rtb_math.cuh", "rtb_kernels.cuh", "rtb_bvh.h",
            os.path.join(ROOT, "include", "rtb200.h"), os.path.join(ROOT, "include", "igx_rt.hpp")]
@@ -46,13 +46,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build", os.path.splitext(os.path.basename(LIB))[0])
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for s in SOURCES:
         obj = os.path.join(build_dir, os.path.splitext(s)[0] + ".o")
         objs.append(obj)
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-x", "cu" if s.endswith(".cu") else "c++",
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("RTB_NVCC_EXTRA", "").split() + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-x", "cu" if s.endswith(".cu") else "c++",
                                         "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []

@@ -50,7 +50,10 @@ RTB_DI void testPair(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_
 }
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(TRACE_THREADS, 2) k_trace_cwbvh(const TraceArgs a) {
+#ifndef RTB_CW_MINBLOCKS
+#define RTB_CW_MINBLOCKS 4   // 64 registers: measured 6.27 ms (2 blocks/SM) -> 5.37 (3) -> 5.33 (4) on the 4K soup frame
+#endif
+__global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh(const TraceArgs a) {
     __shared__ uint4 sTop[TOP8_NODES * 8];
     __shared__ uint2 sStack[SM_STACK][TRACE_THREADS];
     const int topN = min((int)a.nodeCount, TOP8_NODES);

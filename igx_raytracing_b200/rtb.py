@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librtb200.so")
+LIB_PATH = os.environ.get("RTB_LIB", os.path.join(HERE, "librtb200.so"))   # RTB_LIB: load a tuning variant built by build.py
 
 # enums of rtb200.h
 (BUF_CAMERA, BUF_SEED, BUF_SCENE_INFO, BUF_SHADOW_PROPS, BUF_TRIANGLES, BUF_SPHERES, BUF_CUBES, BUF_PLANES, BUF_LIGHTS,
