@@ -310,6 +310,10 @@ def test_tile_partition_matches_single(rtb, sky):
     for p in parts:
         p.close()
     assert np.array_equal(got, want)
+    # the host mirror of the partition (used by the gloo tests and bench.py) agrees with the CUDA side
+    from igx_raytracing_b200 import tiles
+    assert slots == tiles.slots_per_rank(w, h, 3)
+    assert np.array_equal(tiles.untile(gathered.cpu().numpy().view(np.uint32).reshape(3, slots), w, h, 3), want)
 
 
 def test_cpp_facade_renders_like_the_oracle(rtb, oracle, tmp_path):
