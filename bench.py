@@ -335,7 +335,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                "kernel": "k_trace_bvh (nearest-hit + occlusion launches of one frame)", "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+                "kernel": "k_trace_cwbvh (nearest-hit + occlusion launches of one frame)", "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                 "algorithmic_bytes_per_frame_rank0": local_alg_bytes, "trace_ms_per_frame": t_trace * 1e3,
                 "nodes_per_primary_ray": tot[2] / max(tot[0], 1), "tris_per_primary_ray": tot[3] / max(tot[0], 1),
                 "nodes_per_shadow_ray": tot[4] / max(tot[1], 1), "tris_per_shadow_ray": tot[5] / max(tot[1], 1)}
@@ -353,7 +353,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "rays_per_frame": rays_per_frame, "hit_fraction": tot[6] / (w * h),
-                   "l2": "no explicit flush: each frame streams ~0.9 GB of ray / G-buffer data plus the 111 MB BVH through the 126 MB L2",
+                   "l2": "no explicit flush: each frame streams ~0.9 GB of ray / G-buffer data through the 126 MB L2 between traversal launches; the BVH (nodes + triangles) stays resident as it would in steady-state rendering",
                    "partition": f"{world} ranks x interleaved 32x32-pixel blocks, scene+BVH replicated, NCCL gather of rgba8 tiles to rank 0" if world > 1 else "single GPU",
                    "bvh": {"nodes": info.node_count, "node_bytes": info.node_bytes, "leaves": info.leaf_count, "depth": info.max_depth,
                            "sah_cost": info.sah_cost, "build_ms": info.build_ms},
