@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.environ.get("RTB_LIB_OUT", os.path.join(HERE, "librtb200.so"))   # RTB_LIB_OUT / RTB_NVCC_EXTRA: tuning variants
 SOURCES = ["rtb_api.cu", "rtb_kernels.cu", "rtb_bvh.cpp", "rtb_host.cpp"]
-HEADERS = ["rtb_types.h", "rtb_math.cuh", "rtb_kernels.cuh", "rtb_bvh.h",
+HEADERS = ["rtb_types.h", "rtb_math.cuh", "rtb_kernels.cuh", "rtb_trace8.cuh", "rtb_bvh.h",
            os.path.join(ROOT, "include", "rtb200.h"), os.path.join(ROOT, "include", "igx_rt.hpp")]
 
 NVCC_FLAGS = [
