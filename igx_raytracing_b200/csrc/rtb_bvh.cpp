@@ -512,7 +512,7 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
             const bool upper = (s & 1) == 0;   // even slots live in the upper half of their word and are read without decoding
             const int word = s >> 1, shift = upper ? 16 : 0;
             if (i < 0) {   // empty slot: an inverted box (the valid mask removes its bits anyway)
-                for (int a = 0; a < 3; ++a) { out.lo[a][word] |= 0x4380u << shift; /* 256.0 */ }
+                for (int a = 0; a < 3; ++a) { out.lo(a)[word] |= 0x4380u << shift; /* 256.0 */ }
                 continue;
             }
             for (int a = 0; a < 3; ++a) {
@@ -521,8 +521,8 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
                 // an upper-half value is read together with the 16 bits below it: it may appear up to one bf16 step larger.
                 // Harmless for hi planes (a larger box); lo planes are stored one step lower to stay conservative.
                 if (upper && ql > 0) ql -= 1;
-                out.lo[a][word] |= ql << shift;
-                out.hi[a][word] |= qh << shift;
+                out.lo(a)[word] |= ql << shift;
+                out.hi(a)[word] |= qh << shift;
             }
             const float rel = ch[i].box.area() / rootArea;
             if (ch[i].link >= 0) {

@@ -81,6 +81,7 @@ enum { MODE_CLOSEST = 0, MODE_ANY_BITS = 1, MODE_ANY_BYTES = 2 };
 struct TraceArgs {
     const RayRec* rays; uint32_t n;
     const float4* nodes; const uint4* nodes8; const float4* tris; uint32_t nodeCount;
+    const uint4* nodes8Alias;   // == nodes8, a second name the compiler cannot prove equal (rtb_trace8.cuh, ldg256swap)
     TriHit* hits;               // MODE_CLOSEST
     uint32_t* bits; FrameMap fm;// MODE_ANY_BITS
     uint8_t* bytes;             // MODE_ANY_BYTES
@@ -332,7 +333,7 @@ __global__ void k_fill_miss(TriHit* hits, uint32_t n) {
 static TraceArgs makeArgs(const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* workCounter, TraceCounters* counters) {
     TraceArgs a{};
     a.rays = rays; a.n = n;
-    a.nodes = reinterpret_cast<const float4*>(sv.nodes); a.nodes8 = reinterpret_cast<const uint4*>(sv.nodes8);
+    a.nodes = reinterpret_cast<const float4*>(sv.nodes); a.nodes8 = reinterpret_cast<const uint4*>(sv.nodes8); a.nodes8Alias = a.nodes8;
     a.tris = reinterpret_cast<const float4*>(sv.travTris); a.nodeCount = sv.nodeCount;
     a.workCounter = workCounter; a.counters = counters;
     return a;

@@ -2,7 +2,7 @@
 //
 // One warp = 32 rays in flight.  Per iteration, in lock-step:
 //   A  every lane whose current node group still has hit inner children takes the nearest one (highest bit of the
-//      octant-permuted hit mask), fetches its 128-byte record (8 x 16-byte vector loads from one cache line, or
+//      octant-permuted hit mask), fetches its 128-byte record (4 x 256-bit vector loads from one cache line, or
 //      shared memory for the top of the tree) and tests the 8 child boxes; the result is a new node group and a
 //      triangle group;
 //   B  triangle groups are drained with Möller–Trumbore (the reference's arithmetic, SH/primitive.glsl:239-284);
@@ -14,7 +14,9 @@
 // Box planes are bf16 grid coordinates packed two per word (Node8 in rtb_types.h).  The plane in the upper half is
 // used as it stands (the word read as a float), the one in the lower half costs one shift; which of the lo / hi
 // vectors is "near" is decided once per ray and applied as a load offset, so decoding takes no ALU-pipe work and the
-// slab arithmetic is 48 FFMA per node.
+// slab arithmetic is 48 FFMA per node.  The kernel is bound by L1 data-pipe wavefronts (profiles/r1c_*: 96 % of
+// peak with 8 x LDG.128 per node), so a node is fetched with four LDG.256: header, and one granule per axis holding
+// (lo, hi); the near / far assignment is a pair of complementary predicated loads with swapped destinations.
 //
 // The per-lane stack holds 8-byte (base, mask) groups: the first SM_STACK entries in shared memory ([entry][thread],
 // conflict-free for any mix of depths), the rest in local memory.
@@ -22,14 +24,31 @@
 
 namespace rtb {
 
-constexpr int TOP8_NODES = 128;      // 16 KB of shared memory: the breadth-first top of the tree
+#ifndef RTB_CW_TOP_NODES
+#define RTB_CW_TOP_NODES 0     // measured with 256-bit node loads: staging the top of the tree is 1-4 % slower than leaving it to L1
+#endif
+constexpr int TOP8_NODES = RTB_CW_TOP_NODES;   // 16 KB of shared memory: the breadth-first top of the tree (0 = not staged)
 constexpr int SM_STACK = 8;          // 16 KB of shared memory per 256-thread block
 constexpr int LOCAL_STACK = 56;      // rtb_build_accel refuses trees that could need more than SM_STACK + LOCAL_STACK entries
 constexpr int REFILL8 = 22;
 constexpr int POSTPONE8 = 8;
-constexpr uint32_t PLANES_LO = 32u, PLANES_HI = 80u;   // byte offsets of lo[3][4] and hi[3][4] in Node8
 
-// children S (upper halves) and S + 1 (lower halves) of one word triple per axis
+// 32 bytes from global memory through the read-only path in one instruction (LDG.E.256, sm_100)
+RTB_DI void ldg256(const char* p, uint4& a, uint4& b) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+// the same, first half -> a and second half -> b, or the other way round when swap != 0 (per lane): two complementary
+// predicated loads, so the near / far choice costs no ALU work and no extra L1 wavefronts.  p2 == p, computed from a
+// second kernel parameter holding the same base: given one address ptxas merges the pair into a single load followed
+// by 16 predicated moves.
+RTB_DI void ldg256swap(const char* p, const char* p2, uint32_t swap, uint4& a, uint4& b) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %10, 0;\n\t"
+        "@!q ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+        "@q ld.global.nc.v8.u32 {%4,%5,%6,%7,%0,%1,%2,%3}, [%9];\n\t}"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p), "l"(p2), "r"(swap));
+}
+
 template <int S>
 RTB_DI void testPair(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float kx, float ky, float kz,
                      float cx, float cy, float cz, float best, uint32_t& hitmask) {
@@ -51,14 +70,16 @@ RTB_DI void testPair(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_
 
 template <int MODE, bool COUNT>
 #ifndef RTB_CW_MINBLOCKS
-#define RTB_CW_MINBLOCKS 4   // 64 registers: measured 6.27 ms (2 blocks/SM) -> 5.37 (3) -> 5.33 (4) on the 4K soup frame
+#define RTB_CW_MINBLOCKS 3   // 80 registers: the 256-bit loads need aligned register octets; 4 blocks/SM (64 regs) spills in the loop (5.95 vs 5.03 ms)
 #endif
 __global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh(const TraceArgs a) {
-    __shared__ uint4 sTop[TOP8_NODES * 8];
+    __shared__ uint4 sTop[TOP8_NODES > 0 ? TOP8_NODES * 8 : 1];
     __shared__ uint2 sStack[SM_STACK][TRACE_THREADS];
     const int topN = min((int)a.nodeCount, TOP8_NODES);
-    for (int i = threadIdx.x; i < topN * 8; i += TRACE_THREADS) sTop[i] = __ldg(a.nodes8 + i);
-    __syncthreads();
+    if (TOP8_NODES > 0) {
+        for (int i = threadIdx.x; i < topN * 8; i += TRACE_THREADS) sTop[i] = __ldg(a.nodes8 + i);
+        __syncthreads();
+    }
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
@@ -66,7 +87,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh
 
     bool active = false, exhausted = false;
     uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT, octinv = 0;
-    uint32_t nearX = 0, nearY = 0, nearZ = 0;   // byte offsets of the near-plane vectors inside a node, per ray
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
     float best = 0, bu = 0, bv = 0;
     uint2 G = make_uint2(0u, 0u);
@@ -100,9 +120,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh
                         idz = 1.0f / (fabsf(dz) > tiny ? dz : copysignf(tiny, dz));
                         // bit set = the ray travels towards + on that axis; slot s ^ octinv orders children far -> near
                         octinv = (idx < 0.0f ? 0u : 1u) | (idy < 0.0f ? 0u : 2u) | (idz < 0.0f ? 0u : 4u);
-                        nearX = idx < 0.0f ? PLANES_HI : PLANES_LO;
-                        nearY = (idy < 0.0f ? PLANES_HI : PLANES_LO) + 16u;
-                        nearZ = (idz < 0.0f ? PLANES_HI : PLANES_LO) + 32u;
                         bestId = NO_RAY_HIT; bu = 0.0f; bv = 0.0f;
                         sp = 0; G = make_uint2(0u, 0x80000000u);   // the root as a one-node group
                         active = true;
@@ -134,17 +151,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh
                 G.y &= ~(1u << bit);
                 if (G.y & 0xFF000000u) push(G);
                 uint4 n0, n1, wnx, wny, wnz, wfx, wfy, wfz;
-                const uint32_t farX = (PLANES_LO + PLANES_HI) - nearX, farY = (PLANES_LO + PLANES_HI + 32u) - nearY, farZ = (PLANES_LO + PLANES_HI + 64u) - nearZ;
-                if ((int)nodeIdx < topN) {
+                // a ray travelling towards - on an axis meets the hi plane first: swap the two halves of that granule
+                const uint32_t negX = ~octinv & 1u, negY = ~octinv & 2u, negZ = ~octinv & 4u;
+                if (TOP8_NODES > 0 && (int)nodeIdx < topN) {
                     const char* p = reinterpret_cast<const char*>(sTop) + nodeIdx * 128u;
+                    const uint32_t nearX = 32u + (negX << 4), nearY = 64u + (negY << 3), nearZ = 96u + (negZ << 2);
                     n0 = *reinterpret_cast<const uint4*>(p); n1 = *reinterpret_cast<const uint4*>(p + 16);
                     wnx = *reinterpret_cast<const uint4*>(p + nearX); wny = *reinterpret_cast<const uint4*>(p + nearY); wnz = *reinterpret_cast<const uint4*>(p + nearZ);
-                    wfx = *reinterpret_cast<const uint4*>(p + farX); wfy = *reinterpret_cast<const uint4*>(p + farY); wfz = *reinterpret_cast<const uint4*>(p + farZ);
+                    wfx = *reinterpret_cast<const uint4*>(p + (nearX ^ 16u)); wfy = *reinterpret_cast<const uint4*>(p + (nearY ^ 16u)); wfz = *reinterpret_cast<const uint4*>(p + (nearZ ^ 16u));
                 } else {
                     const char* p = reinterpret_cast<const char*>(a.nodes8) + (size_t)nodeIdx * 128u;
-                    n0 = __ldg(reinterpret_cast<const uint4*>(p)); n1 = __ldg(reinterpret_cast<const uint4*>(p + 16));
-                    wnx = __ldg(reinterpret_cast<const uint4*>(p + nearX)); wny = __ldg(reinterpret_cast<const uint4*>(p + nearY)); wnz = __ldg(reinterpret_cast<const uint4*>(p + nearZ));
-                    wfx = __ldg(reinterpret_cast<const uint4*>(p + farX)); wfy = __ldg(reinterpret_cast<const uint4*>(p + farY)); wfz = __ldg(reinterpret_cast<const uint4*>(p + farZ));
+                    ldg256(p, n0, n1);
+                    const char* p2 = reinterpret_cast<const char*>(a.nodes8Alias) + (size_t)nodeIdx * 128u;
+                    ldg256swap(p + 32, p2 + 32, negX, wnx, wfx);
+                    ldg256swap(p + 64, p2 + 64, negY, wny, wfy);
+                    ldg256swap(p + 96, p2 + 96, negZ, wnz, wfz);
                 }
                 if (COUNT) cNodes++;
                 // plane at grid coordinate g along x: t = (p.x + g * 2^e - o.x) / d.x = g * kx + cx

@@ -68,15 +68,21 @@ static_assert(sizeof(BvhNode) == 64, "BVH node is 64 bytes");
 //   triBase     index of the first triangle of the leaf children (consecutive, in slot order, at most 24)
 //   valid       imask << 24 | triangle presence: leaf slot s holding c <= 3 triangles sets bits 3s .. 3s+c-1; the
 //               triangle at bit b is triBase + popcount(presence bits below b)
-//   lo, hi      child box planes as bf16 grid coordinates g in [0, 256), two children per word: slot 2k in the
+//   planes      child box planes as bf16 grid coordinates g in [0, 256), two children per word: slot 2k in the
 //               upper half, slot 2k+1 in the lower half.  The traversal reads the upper value by taking the whole
 //               word as a float (no decode), which can only enlarge it by less than one bf16 step, so the builder
 //               rounds upper-half lo planes down by one extra step; every stored box contains the true box.
+//               planes[axis][0] = lo, planes[axis][1] = hi: one 32-byte granule per axis, fetched with ONE 256-bit
+//               load whose two destination halves are swapped by the ray's direction sign (near / far).
+// The record is four 32-byte granules = four LDG.256 per visit (sm_100 has 256-bit global loads).
 struct alignas(128) Node8 {
     float p[3]; uint8_t e[3]; uint8_t imask;
     uint32_t childBase, triBase, valid, reserved;
-    uint32_t lo[3][4];
-    uint32_t hi[3][4];
+    uint32_t planes[3][2][4];
+    uint32_t* lo(int a) { return planes[a][0]; }
+    uint32_t* hi(int a) { return planes[a][1]; }
+    const uint32_t* lo(int a) const { return planes[a][0]; }
+    const uint32_t* hi(int a) const { return planes[a][1]; }
 };
 static_assert(sizeof(Node8) == 128, "CWBVH node is 128 bytes");
 

@@ -63,9 +63,9 @@ static bool walk8(const std::vector<Node8>& nodes, const std::vector<TravTri>& t
             const float cx = (n.p[0] - ro.x) * idx, cy = (n.p[1] - ro.y) * idy, cz = (n.p[2] - ro.z) * idz;
             uint32_t hitmask = 0;
             for (int word = 0; word < 4; ++word) {
-                const uint32_t nx = idx < 0 ? n.hi[0][word] : n.lo[0][word], fx = idx < 0 ? n.lo[0][word] : n.hi[0][word];
-                const uint32_t ny = idy < 0 ? n.hi[1][word] : n.lo[1][word], fy = idy < 0 ? n.lo[1][word] : n.hi[1][word];
-                const uint32_t nz = idz < 0 ? n.hi[2][word] : n.lo[2][word], fz = idz < 0 ? n.lo[2][word] : n.hi[2][word];
+                const uint32_t nx = idx < 0 ? n.hi(0)[word] : n.lo(0)[word], fx = idx < 0 ? n.lo(0)[word] : n.hi(0)[word];
+                const uint32_t ny = idy < 0 ? n.hi(1)[word] : n.lo(1)[word], fy = idy < 0 ? n.lo(1)[word] : n.hi(1)[word];
+                const uint32_t nz = idz < 0 ? n.hi(2)[word] : n.lo(2)[word], fz = idz < 0 ? n.lo(2)[word] : n.hi(2)[word];
                 for (int half = 0; half < 2; ++half) {   // half 0: upper 16 bits read as the whole word; half 1: lower 16 bits shifted up
                     const int sl = 2 * word + half, sh = half ? 16 : 0;
                     const float tnx = std::fma(asf(nx << sh), kx, cx), tny = std::fma(asf(ny << sh), ky, cy), tnz = std::fma(asf(nz << sh), kz, cz);
