@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="soup1m", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--packets", default="auto", choices=["off", "on", "auto"],
+                    help="camera rays as 8x4-pixel packets (RTB_OPT_PRIMARY_PACKETS); auto = the library's patch-size rule")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -220,10 +222,10 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     ctx.set_option(rtb.OPT_TILE_COUNT, world)
     ctx.set_option(rtb.OPT_TILE_RANK, rank)
+    ctx.set_option(rtb.OPT_PRIMARY_PACKETS, {"off": 0, "on": 1, "auto": 2}[args.packets])
     ctx.resize(w, h, samples)
     ctx.upload_scene(scene, None)
     ctx.build_accel(rtb.ACCEL_BVH)
-    info = ctx.accel_info()
     cam = rtb.pack_camera(w, h, **camera_kwargs(wl))
     seed0 = rtb.make_seed((0.0, 0.0))
 
@@ -266,7 +268,14 @@ def main():
     ctx.dispatch(rtb.PASS_FRAME)
     ctx.sync()
     c = ctx.counters()
+    ctx.set_option(rtb.OPT_COUNTERS, 2)   # what the kernels in use fetch (a packet fetch serves 32 rays and counts once)
+    ctx.dispatch(rtb.PASS_FRAME)
+    ctx.sync()
+    cf = ctx.counters()
     ctx.set_option(rtb.OPT_COUNTERS, 0)
+    ctx.dispatch(rtb.PASS_FRAME)
+    ctx.sync()
+    info = ctx.accel_info()   # after a plain frame: primary_packets says which nearest-hit kernel the timed frames run
     local = torch.tensor([c.primary_rays, c.shadow_rays, c.primary_nodes, c.primary_tris, c.shadow_nodes, c.shadow_tris, c.primary_hits,
                           c.shadow_occluded], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -337,7 +346,11 @@ def main():
         return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic.get(key),
                 "kernel": kernel, "algorithmic_bytes_per_launch_rank0": nbytes, "ms_per_launch": secs * 1e3}
 
-    roofline = roof("k_trace_cwbvh<MODE_CLOSEST> (nearest-hit launch, the dominant kernel)", bytes_primary, t_primary, "k_trace_cwbvh<0,0>")
+    if info.primary_packets:
+        roofline = roof("k_trace_cwbvh_packet (nearest-hit launch: one warp-cooperative traversal per 8x4-pixel patch)", bytes_primary, t_primary, "k_trace_cwbvh_packet")
+        roofline["fetched_bytes_per_launch_rank0"] = cf.primary_nodes * info.node_bytes + cf.primary_tris * info.tri_record_bytes
+    else:
+        roofline = roof("k_trace_cwbvh<MODE_CLOSEST> (nearest-hit launch, the dominant kernel)", bytes_primary, t_primary, "k_trace_cwbvh<0,0>")
     roofline.update({
         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
         "note": "the BVH (nodes + triangles, %.0f MB) is L2-resident, so algorithmic bytes per second can exceed the HBM copy peak; "
@@ -362,7 +375,8 @@ def main():
                    "l2": "no explicit flush: each frame streams ~0.9 GB of ray / G-buffer data through the 126 MB L2 between traversal launches; the BVH (nodes + triangles) stays resident as it would in steady-state rendering",
                    "partition": f"{world} ranks x interleaved 32x32-pixel blocks, scene+BVH replicated, NCCL gather of rgba8 tiles to rank 0" if world > 1 else "single GPU",
                    "bvh": {"nodes": info.node_count, "node_bytes": info.node_bytes, "leaves": info.leaf_count, "depth": info.max_depth,
-                           "sah_cost": info.sah_cost, "build_ms": info.build_ms},
+                           "sah_cost": info.sah_cost, "build_ms": info.build_ms, "leaf_node_extent": info.leaf_node_extent},
+                   "primary_packets": bool(info.primary_packets), "packets_option": args.packets,
                    "phase_ms_rank0": {k: float(v) for k, v in zip(["init", "raygen", "trace_primary", "finish", "shadowgen", "trace_shadow", "shade", "total"], phases)}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 168 * world, "d2h_bytes_per_step": w * h * 4,

@@ -55,6 +55,8 @@ struct rtb_ctx {
     DevBuf<BvhNode> nodes; DevBuf<Node8> nodes8; DevBuf<TravTri> travTris;
     uint32_t nodeCount = 0; rtb_accel_mode accelMode = RTB_ACCEL_BRUTE; bool accelValid = false;
     BvhStats stats;
+    DevBuf<float> nodeBox; DevBuf<uint32_t> maxBits;   // refit scratch: 6 floats per node, largest |coordinate|
+    uint32_t builtTriangles = 0, refits = 0;
 
     // frame resources
     uint32_t width = 0, height = 0, samples = 0;
@@ -65,6 +67,9 @@ struct rtb_ctx {
     DevBuf<uint32_t> workCounter;
     DevBuf<TraceCounters> counters;   // [0] primary, [1] shadow
     bool countersOn = false;
+    uint32_t countersMode = 0;        // 1: per-ray algorithmic counts (per-lane kernel); 2: what the kernels in use fetch
+    uint32_t packetsOpt = 2;          // RTB_OPT_PRIMARY_PACKETS: 0 off, 1 on, 2 auto
+    bool lastPrimaryPackets = false;
 
     // rays-in scratch
     DevBuf<RayRec> rinRays; DevBuf<TriHit> rinHits; DevBuf<uint32_t> rinObj; DevBuf<float> rinT; DevBuf<float2> rinUv; DevBuf<uint8_t> rinOcc, rinOcc2;
@@ -136,12 +141,38 @@ int checkReady(rtb_ctx* c) {
     return RTB_OK;
 }
 
+// Primary rays of an 8x4 pixel patch are walked through the 8-wide tree as one packet (rtb_trace8p.cuh) when the patch
+// is small against the tree's leaf nodes: its width at the distance of the scene centre, 8 pixels wide, must stay
+// below PACKET_RATIO leaf-node edges.  Above that the union of the nodes the 32 rays need grows faster than the
+// shared fetches save (measured on the 1M-triangle soup from two distances and on the 10M-triangle height field).
+constexpr float PACKET_RATIO = 1.0f;
+bool primaryPackets(const rtb_ctx* c) {
+    if (c->accelMode != RTB_ACCEL_BVH || !c->accelValid || !c->info.triangleCount) return false;
+    if (c->countersOn && c->countersMode == 1) return false;
+    if (c->packetsOpt != 2) return c->packetsOpt == 1;
+    const CameraRec& cam = c->camera;
+    if (cam.projectionType != 0 || !cam.width) return false;
+    float ctr[3], e2c = 0.0f, rad = 0.0f, pw = 0.0f, pd = 0.0f;
+    for (int a = 0; a < 3; ++a) {
+        ctr[a] = 0.5f * (c->stats.lo[a] + c->stats.hi[a]);
+        e2c += (ctr[a] - cam.eye[a]) * (ctr[a] - cam.eye[a]);
+        rad += 0.25f * (c->stats.hi[a] - c->stats.lo[a]) * (c->stats.hi[a] - c->stats.lo[a]);
+        pw += (cam.p1[a] - cam.p0[a]) * (cam.p1[a] - cam.p0[a]);
+        const float mid = 0.5f * (cam.p1[a] + cam.p2[a]) - cam.eye[a];   // centre of the screen plane
+        pd += mid * mid;
+    }
+    const float dist = std::max(std::sqrt(e2c), 0.5f * std::sqrt(rad));
+    const float patch = 8.0f * std::sqrt(pw) / (float)cam.width / std::max(std::sqrt(pd), 1e-20f) * dist;
+    return patch < PACKET_RATIO * c->stats.leafNodeExtent;
+}
+
 // `mark` (frame dispatch only) records an event after each phase so the traversal launches can be timed alone
 int passRaygen(rtb_ctx* c, bool mark) {
     const SceneView sv = sceneView(c);
     launch_raygen(c->fm, &c->camera, c->seed.p, c->rays.p, c->stream);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    launch_trace_closest(sv, c->rays.p, c->fm.localSlots, c->hits.p, c->workCounter.p, c->countersOn ? c->counters.p : nullptr, c->stream);
+    c->lastPrimaryPackets = primaryPackets(c);
+    launch_trace_closest(sv, c->rays.p, c->fm.localSlots, c->hits.p, c->workCounter.p, c->countersOn ? c->counters.p : nullptr, c->lastPrimaryPackets, c->stream);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     launch_finish_primary(c->fm, sv, c->rays.p, c->hits.p, c->dirT.p, c->uvN.p, c->stream);
     return RTB_OK;
@@ -222,7 +253,10 @@ const char* rtb_last_error(const rtb_ctx* c) { return c ? c->error.c_str() : g_c
 int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
     if (!c) return RTB_ERR_ARG;
     switch (opt) {
-        case RTB_OPT_COUNTERS: c->countersOn = value != 0; return RTB_OK;
+        case RTB_OPT_COUNTERS: c->countersOn = value != 0; c->countersMode = value; return RTB_OK;
+        case RTB_OPT_PRIMARY_PACKETS:
+            if (value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_PRIMARY_PACKETS: 0 off, 1 on, 2 auto");
+            c->packetsOpt = value; return RTB_OK;
         case RTB_OPT_TILE_RANK:
             c->tileRank = value;
             if (c->width) { RTB_BIND(c); return allocFrame(c); }
@@ -316,7 +350,7 @@ int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     if (mode != RTB_ACCEL_BRUTE && mode != RTB_ACCEL_BVH && mode != RTB_ACCEL_BVH2) return fail(c, RTB_ERR_ARG, "rtb_build_accel: unknown mode");
     c->accelMode = mode;
     c->stats = BvhStats();
-    c->nodeCount = 0;
+    c->nodeCount = 0; c->builtTriangles = 0; c->refits = 0;
     if (mode == RTB_ACCEL_BRUTE) { c->accelValid = true; return RTB_OK; }
     if (c->info.triangleCount > c->limits.max_triangles) return fail(c, RTB_ERR_CAPACITY, "triangleCount exceeds max_triangles");
     std::vector<TravTri> tt;
@@ -340,6 +374,25 @@ int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     }
     RTB_CUDA(c, c->travTris.alloc(tt.size()));
     if (!tt.empty()) RTB_CUDA(c, cudaMemcpy(c->travTris.p, tt.data(), tt.size() * sizeof(TravTri), cudaMemcpyHostToDevice));
+    c->builtTriangles = c->info.triangleCount;
+    c->accelValid = true;
+    return RTB_OK;
+}
+
+int rtb_refit_accel(rtb_ctx* c) {
+    if (!c) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (c->accelMode != RTB_ACCEL_BVH || !c->nodeCount || c->builtTriangles != c->info.triangleCount || c->stats.levelFirst.size() < 2)
+        return rtb_build_accel(c, c->accelMode);
+    RTB_CUDA(c, c->nodeBox.alloc((size_t)c->nodeCount * 6)); RTB_CUDA(c, c->maxBits.alloc(1));
+    launch_refit(c->triangles.p, c->info.triangleCount, c->travTris.p, c->info.triangleCount, c->nodes8.p, c->stats.levelFirst.data(),
+                 (uint32_t)c->stats.levelFirst.size() - 1, c->nodeBox.p, c->maxBits.p, c->stream);
+    RTB_CUDA(c, cudaGetLastError());
+    float root[6];   // scene bounds for the packet rule (primaryPackets)
+    RTB_CUDA(c, cudaMemcpyAsync(root, c->nodeBox.p, sizeof root, cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int a = 0; a < 3; ++a) { c->stats.lo[a] = root[a]; c->stats.hi[a] = root[3 + a]; }
+    ++c->refits;
     c->accelValid = true;
     return RTB_OK;
 }
@@ -348,6 +401,7 @@ int rtb_accel_info_get(const rtb_ctx* c, rtb_accel_info* out) {
     if (!c || !out) return RTB_ERR_ARG;
     out->mode = c->accelMode; out->node_count = c->nodeCount; out->node_bytes = c->accelMode == RTB_ACCEL_BVH ? sizeof(Node8) : sizeof(BvhNode); out->leaf_count = c->stats.leafCount;
     out->max_depth = c->stats.maxDepth; out->tri_record_bytes = sizeof(TravTri); out->sah_cost = c->stats.sahCost; out->build_ms = c->stats.buildMs;
+    out->leaf_node_extent = c->stats.leafNodeExtent; out->refits = c->refits; out->primary_packets = c->lastPrimaryPackets ? 1u : 0u;
     return RTB_OK;
 }
 
@@ -395,9 +449,13 @@ int rtb_device_ptr(rtb_ctx* c, rtb_target t, void** out, size_t* bytes) {
         case RTB_TGT_RGBA8: p = c->rgba8.p; n = px * 4; break;
         case RTB_TGT_SEED: p = c->seed.p; n = sizeof(SeedRec); break;
         case RTB_TGT_RGBA8_TILED: p = c->rgba8Tiled.p; n = (size_t)((c->fm.blocksX * c->fm.blocksY + c->fm.nranks - 1) / c->fm.nranks) * 4096u; break;
+        case RTB_TGT_ACCEL_NODES:
+            if (c->accelMode == RTB_ACCEL_BVH) { p = c->nodes8.p; n = (size_t)c->nodeCount * sizeof(Node8); } else { p = c->nodes.p; n = (size_t)c->nodeCount * sizeof(BvhNode); }
+            break;
+        case RTB_TGT_ACCEL_TRIANGLES: p = c->travTris.p; n = c->nodeCount ? (size_t)c->builtTriangles * sizeof(TravTri) : 0; break;
         default: return fail(c, RTB_ERR_ARG, "unknown target");
     }
-    if (t != RTB_TGT_SEED && !px) return fail(c, RTB_ERR_STATE, "no frame resources before rtb_resize");
+    if (t != RTB_TGT_SEED && t != RTB_TGT_ACCEL_NODES && t != RTB_TGT_ACCEL_TRIANGLES && !px) return fail(c, RTB_ERR_STATE, "no frame resources before rtb_resize");
     *out = p; if (bytes) *bytes = n;
     return RTB_OK;
 }
@@ -479,7 +537,7 @@ int rtb_trace_rays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* pr
     if (rc) return rc;
     RTB_CUDA(c, c->rinHits.alloc((size_t)n)); RTB_CUDA(c, c->rinObj.alloc((size_t)n)); RTB_CUDA(c, c->rinT.alloc((size_t)n)); RTB_CUDA(c, c->rinUv.alloc((size_t)n));
     const SceneView sv = sceneView(c);
-    launch_trace_closest(sv, c->rinRays.p, (uint32_t)n, c->rinHits.p, c->workCounter.p, nullptr, c->stream);
+    launch_trace_closest(sv, c->rinRays.p, (uint32_t)n, c->rinHits.p, c->workCounter.p, nullptr, c->packetsOpt == 1, c->stream);
     launch_finish_rays(sv, c->rinRays.p, c->rinHits.p, (uint32_t)n, c->rinObj.p, c->rinT.p, c->rinUv.p, c->stream);
     RTB_CUDA(c, cudaGetLastError());
     if (object) RTB_CUDA(c, cudaMemcpyAsync(object, c->rinObj.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));

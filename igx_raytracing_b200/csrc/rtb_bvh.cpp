@@ -6,6 +6,7 @@
 //                   Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017): greedy surface-area collapse of the
 //                   binary tree, octant-ordered child slots, 8-bit child boxes on a per-node power-of-two grid
 #include "rtb_bvh.h"
+#include "rtb_node8_encode.h"
 
 #include <algorithm>
 #include <atomic>
@@ -381,8 +382,9 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
     nodes.emplace_back();
     queue.push_back({bt.root, 0u, bt.rootBox, 1u});
     const float rootArea = std::max(bt.rootBox.area(), 1e-30f);
-    double cost = 0.0;
-    uint32_t leaves = 0, maxDepth = 0;
+    double cost = 0.0, leafExtentSum = 0.0;
+    uint32_t leaves = 0, maxDepth = 0, leafNodes = 0;
+    for (int a = 0; a < 3; ++a) { stats.lo[a] = bt.rootBox.lo[a]; stats.hi[a] = bt.rootBox.hi[a]; }
 
     // ---- which binary nodes become 8-wide nodes: the SAH-optimal collapse of Ylitie et al. (section 3.1) -----------
     //   c(n, i)  = cheapest way to represent subtree n with at most i roots (each root = one child slot of the parent)
@@ -423,6 +425,7 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
 
     while (!queue.empty()) {
         const Work w = queue.front(); queue.pop_front();
+        if (w.depth > maxDepth) stats.levelFirst.push_back(w.node8);   // breadth-first: every level is one index range
         maxDepth = std::max(maxDepth, w.depth);
         Child ch[8]; int n = 0;
         if (w.bin < 0) { ch[0] = {w.bin, w.box}; n = 1; }
@@ -475,55 +478,20 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
         int childAt[8]; for (int s = 0; s < 8; ++s) childAt[s] = -1;
         for (int i = 0; i < n; ++i) childAt[slotOf[i]] = i;
 
-        // ---- quantisation grid: origin = box lo, per-axis power-of-two step with extent / step <= 254 -------------
+        // ---- quantisation grid and child boxes: rtb_node8_encode.h (shared with the device refit) -------------------
         Node8 out;
         std::memset(&out, 0, sizeof out);
-        int ex[3]; double step[3];
-        for (int a = 0; a < 3; ++a) {
-            out.p[a] = nb.lo[a];
-            const double ext = (double)nb.hi[a] - (double)nb.lo[a];
-            int e = ext > 0.0 ? (int)std::ceil(std::log2(ext / 254.0)) : -100;
-            e = std::max(-100, std::min(100, e));
-            while (ext / std::ldexp(1.0, e) > 254.0 && e < 100) ++e;
-            ex[a] = e; step[a] = std::ldexp(1.0, e);
-            out.e[a] = (uint8_t)(e + 127);
-        }
+        double step[3];
+        Box6 nb6; for (int a = 0; a < 3; ++a) { nb6.lo[a] = nb.lo[a]; nb6.hi[a] = nb.hi[a]; }
+        node8Grid(nb6, out, step);
         out.childBase = (uint32_t)nodes.size();
         out.triBase = (uint32_t)triOrder.size();
-        uint32_t triOffset = 0, innerCount = 0;
+        uint32_t innerCount = 0;
         for (int s = 0; s < 8; ++s) {
             const int i = childAt[s];
-            // bf16 bits of a non-negative grid coordinate, rounded towards -inf / +inf
-            auto valueOf = [](uint32_t t) { float f; std::memcpy(&f, &t, 4); return (double)f; };
-            auto bf16Down = [&](double g) {
-                g = std::max(0.0, g);
-                const float f = (float)g; uint32_t b; std::memcpy(&b, &f, 4);
-                uint32_t t = b & 0xFFFF0000u;                      // truncation = towards zero
-                if (valueOf(t) > g && t >= 0x10000u) t -= 0x10000u;  // (float)g rounded up onto a bf16 value
-                return t >> 16;
-            };
-            auto bf16Up = [&](double g) {
-                g = std::max(0.0, g);
-                const float f = (float)g; uint32_t b; std::memcpy(&b, &f, 4);
-                uint32_t t = b & 0xFFFF0000u;
-                if (valueOf(t) < g) t += 0x10000u;
-                return t >> 16;
-            };
-            const bool upper = (s & 1) == 0;   // even slots live in the upper half of their word and are read without decoding
-            const int word = s >> 1, shift = upper ? 16 : 0;
-            if (i < 0) {   // empty slot: an inverted box (the valid mask removes its bits anyway)
-                for (int a = 0; a < 3; ++a) { out.lo(a)[word] |= 0x4380u << shift; /* 256.0 */ }
-                continue;
-            }
-            for (int a = 0; a < 3; ++a) {
-                const double lo = ((double)ch[i].box.lo[a] - (double)out.p[a]) / step[a] - 0.02, hi = ((double)ch[i].box.hi[a] - (double)out.p[a]) / step[a] + 0.02;
-                uint32_t ql = bf16Down(lo), qh = bf16Up(hi);
-                // an upper-half value is read together with the 16 bits below it: it may appear up to one bf16 step larger.
-                // Harmless for hi planes (a larger box); lo planes are stored one step lower to stay conservative.
-                if (upper && ql > 0) ql -= 1;
-                out.lo(a)[word] |= ql << shift;
-                out.hi(a)[word] |= qh << shift;
-            }
+            if (i < 0) { node8Child(out, s, nullptr, step); continue; }
+            Box6 cb; for (int a = 0; a < 3; ++a) { cb.lo[a] = ch[i].box.lo[a]; cb.hi[a] = ch[i].box.hi[a]; }
+            node8Child(out, s, &cb, step);
             const float rel = ch[i].box.area() / rootArea;
             if (ch[i].link >= 0) {
                 out.imask |= (uint8_t)(1u << s);
@@ -534,16 +502,18 @@ void buildCwbvh(const TriangleRec* tris, uint32_t count, int threads, std::vecto
                 const uint32_t first = leafFirst(ch[i].link), cnt = leafCount(ch[i].link);
                 out.valid |= ((1u << cnt) - 1u) << (3 * s);   // unary count at the slot's three bits
                 for (uint32_t k = 0; k < cnt; ++k) triOrder.push_back(bt.idx[first + k]);
-                triOffset += cnt;
                 cost += rel * (float)cnt; ++leaves;
             }
         }
         out.valid |= (uint32_t)out.imask << 24;
+        if (!innerCount) { leafExtentSum += ((double)(nb.hi[0] - nb.lo[0]) + (double)(nb.hi[1] - nb.lo[1]) + (double)(nb.hi[2] - nb.lo[2])) / 3.0; ++leafNodes; }
         nodes[w.node8] = out;
         for (uint32_t k = 0; k < innerCount; ++k) nodes.emplace_back();
     }
     fillTravTris(tris, triOrder, threads, travTris);
     stats.nodeCount = (uint32_t)nodes.size(); stats.leafCount = leaves; stats.maxDepth = maxDepth; stats.sahCost = (float)cost;
+    stats.leafNodeExtent = leafNodes ? (float)(leafExtentSum / leafNodes) : 0.0f;
+    stats.levelFirst.push_back((uint32_t)nodes.size());
     stats.buildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 

@@ -9,6 +9,9 @@ namespace rtb {
 struct BvhStats {
     uint32_t nodeCount = 0, leafCount = 0, maxDepth = 0;
     float sahCost = 0.0f, buildMs = 0.0f;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounds of the padded triangle boxes
+    float leafNodeExtent = 0.0f;                  // 8-wide tree: mean edge length of the nodes that hold only triangles
+    std::vector<uint32_t> levelFirst;             // 8-wide tree: first node of every level, then nodeCount (levels are index ranges)
 };
 
 // Binned-SAH binary BVH over `count` reference-layout triangles.

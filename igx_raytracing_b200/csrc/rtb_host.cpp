@@ -1,6 +1,8 @@
 // rtb_host.cpp — host-side entry points of the C ABI that need no GPU: the igx:: POD constructors
 // (through include/igx_rt.hpp, so the C++ facade and the C ABI cannot drift apart), the Radiance .hdr
 // loader, and the synthetic scene generators of BASELINE.json.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -220,6 +222,84 @@ void rtb_gen_heightfield(uint32_t grid, uint64_t seed, void* outTriangles) {
             out[2 * q + 1] = Triangle(bb, c, d, nb, nc, nd);
         }
     });
+}
+
+// ---- frame export: rgba8 -> PNG (ref: igx/igxi-tool/src/igxi/convert.cpp:747-781, stbiWrite: 4 channels, 8 bits, rows
+// flipped on write because row 0 of the frame is the bottom of the view) -----------------------------------------------
+namespace {
+uint32_t crc32Of(const uint8_t* p, size_t n, uint32_t crc) {
+    static uint32_t table[256];
+    static std::atomic<bool> ready{false};
+    if (!ready.load(std::memory_order_acquire)) {
+        for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+        ready.store(true, std::memory_order_release);
+    }
+    crc = ~crc;
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFFu] ^ (crc >> 8);
+    return ~crc;
+}
+void be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(uint8_t(x >> 24)); v.push_back(uint8_t(x >> 16)); v.push_back(uint8_t(x >> 8)); v.push_back(uint8_t(x)); }
+bool writeChunk(FILE* f, const char type[4], const uint8_t* data, size_t n) {
+    std::vector<uint8_t> head; be32(head, (uint32_t)n); head.insert(head.end(), type, type + 4);
+    uint32_t crc = crc32Of(head.data() + 4, 4, 0u);
+    if (n) crc = crc32Of(data, n, crc);
+    std::vector<uint8_t> tail; be32(tail, crc);
+    return std::fwrite(head.data(), 1, 8, f) == 8 && (!n || std::fwrite(data, 1, n, f) == n) && std::fwrite(tail.data(), 1, 4, f) == 4;
+}
+// zlib stream of `raw`: through libz when the process can load it (looked up at run time: no link dependency), otherwise
+// as stored deflate blocks (valid, just not compressed)
+std::vector<uint8_t> zlibStream(const std::vector<uint8_t>& raw) {
+    using compressBoundFn = unsigned long (*)(unsigned long);
+    using compress2Fn = int (*)(uint8_t*, unsigned long*, const uint8_t*, unsigned long, int);
+    static void* lib = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (lib) {
+        auto bound = reinterpret_cast<compressBoundFn>(dlsym(lib, "compressBound"));
+        auto comp = reinterpret_cast<compress2Fn>(dlsym(lib, "compress2"));
+        if (bound && comp) {
+            std::vector<uint8_t> out(bound((unsigned long)raw.size()));
+            unsigned long n = (unsigned long)out.size();
+            if (comp(out.data(), &n, raw.data(), (unsigned long)raw.size(), 1) == 0) { out.resize(n); return out; }
+        }
+    }
+    std::vector<uint8_t> out;
+    out.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+    out.push_back(0x78); out.push_back(0x01);
+    uint32_t a = 1, b = 0;
+    size_t pos = 0;
+    do {
+        const size_t n = std::min<size_t>(65535, raw.size() - pos);
+        out.push_back(pos + n == raw.size() ? 1 : 0);
+        out.push_back(uint8_t(n)); out.push_back(uint8_t(n >> 8)); out.push_back(uint8_t(~n)); out.push_back(uint8_t((~n) >> 8));
+        out.insert(out.end(), raw.begin() + pos, raw.begin() + pos + n);
+        for (size_t i = 0; i < n; ++i) { a += raw[pos + i]; if (a >= 65521) a -= 65521; b += a; if (b >= 65521) b -= 65521; }
+        pos += n;
+    } while (pos < raw.size());
+    be32(out, (b << 16) | a);
+    return out;
+}
+}  // namespace
+
+int rtb_write_png(const char* path, uint32_t width, uint32_t height, const void* rgba8, int flipVertically) {
+    if (!path || !rgba8 || !width || !height) return 1;
+    const uint8_t* px = static_cast<const uint8_t*>(rgba8);
+    const size_t row = (size_t)width * 4;
+    std::vector<uint8_t> raw((row + 1) * height);
+    for (uint32_t y = 0; y < height; ++y) {
+        const uint32_t src = flipVertically ? height - 1 - y : y;
+        raw[(row + 1) * y] = 0;   // filter type None
+        std::memcpy(raw.data() + (row + 1) * y + 1, px + row * src, row);
+    }
+    const std::vector<uint8_t> z = zlibStream(raw);
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return 2;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    std::vector<uint8_t> ihdr; be32(ihdr, width); be32(ihdr, height);
+    ihdr.push_back(8); ihdr.push_back(6); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);   // 8 bits, RGBA, deflate, adaptive, no interlace
+    bool ok = std::fwrite(sig, 1, 8, f) == 8 && writeChunk(f, "IHDR", ihdr.data(), ihdr.size());
+    for (size_t pos = 0; ok && pos < z.size(); pos += (size_t)1 << 30) ok = writeChunk(f, "IDAT", z.data() + pos, std::min<size_t>((size_t)1 << 30, z.size() - pos));
+    ok = ok && writeChunk(f, "IEND", nullptr, 0);
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? 0 : 3;
 }
 
 }  // extern "C"

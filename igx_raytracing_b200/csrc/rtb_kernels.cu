@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) 
 
 }  // namespace rtb
 #include "rtb_trace8.cuh"
+#include "rtb_trace8p.cuh"
 namespace rtb {
 
 // persistent grid: one resident wave (SM count x blocks that fit per SM), fewer when the wavefront is small
@@ -270,6 +271,22 @@ static void launchTrace(const SceneView& sv, const TraceArgs& a, bool count, cud
     else { if (count) launchTraceBvh<MODE, true, false>(a, st); else launchTraceBvh<MODE, false, false>(a, st); }
 }
 int trace_grid_blocks() { return g_traceBlocks; }
+
+template <bool COUNT>
+static void launchPacket(const TraceArgs& a, cudaStream_t st) {
+    static int blocks = 0;
+    auto kernel = k_trace_cwbvh_packet<COUNT>;
+    if (!blocks) {
+        int dev = 0, sms = 0, perSm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TRACE_THREADS, 0);
+        blocks = sms * (perSm > 0 ? perSm : 1);
+    }
+    cudaMemsetAsync(a.workCounter, 0, sizeof(uint32_t), st);
+    const uint32_t warpsNeeded = (a.n + 31u) / 32u, blocksNeeded = (warpsNeeded + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32);
+    kernel<<<min((uint32_t)blocks, blocksNeeded ? blocksNeeded : 1u), TRACE_THREADS, 0, st>>>(a);
+}
 
 // --------------------------------------------------------------------------------------------------------
 // brute force: the reference's triangle loop (SH/trace.glsl:25-29, :78-81), triangles staged through shared memory
@@ -340,10 +357,14 @@ static TraceArgs makeArgs(const SceneView& sv, const RayRec* rays, uint32_t n, u
 }
 
 void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
-                          TraceCounters* counters, cudaStream_t st) {
+                          TraceCounters* counters, bool packets, cudaStream_t st) {
     if (!n) return;
     if (sv.info.triangleCount == 0) { k_fill_miss<<<(n + 255) / 256, 256, 0, st>>>(hits, n); return; }
-    if (sv.useBvh) {
+    if (sv.useBvh == ACCEL_KIND_CWBVH && packets) {
+        TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
+        a.hits = hits;
+        if (counters) launchPacket<true>(a, st); else launchPacket<false>(a, st);
+    } else if (sv.useBvh) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
         a.hits = hits;
         launchTrace<MODE_CLOSEST>(sv, a, counters != nullptr, st);

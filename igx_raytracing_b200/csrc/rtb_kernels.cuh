@@ -29,9 +29,10 @@ struct TraceCounters { unsigned long long rays, nodes, tris, hits; };
 
 void launch_init(SeedRec* seed, cudaStream_t s);
 void launch_raygen(const FrameMap& fm, const CameraRec* cam, const SeedRec* seed, RayRec* rays, cudaStream_t s);
-// nearest triangle for every ray slot (BVH or brute force according to sv.useBvh)
+// nearest triangle for every ray slot (BVH or brute force according to sv.useBvh).  packets: 32 consecutive slots are a
+// coherent patch and the 8-wide tree is walked once per warp (rtb_trace8p.cuh); otherwise one traversal per lane.
 void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
-                          TraceCounters* counters, cudaStream_t s);
+                          TraceCounters* counters, bool packets, cudaStream_t s);
 // spheres, cubes, planes after the triangles, normal interpolation, G-buffer stores (raygen.comp:39-51)
 void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits,
                            float4* dirT, float4* uvN, cudaStream_t s);
@@ -55,6 +56,10 @@ void launch_finish_rays(const SceneView& sv, const RayRec* rays, const TriHit* h
 void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t s);
 // rank 0: gathered [nranks][slotsPerRank] tiled pixels -> scan-line rgba8
 void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsPerRank, uint32_t* rgba8, cudaStream_t s);
+
+// refit of the 8-wide tree from the current triangle buffer (rtb_refit.cu); levelFirst is a HOST array of levels + 1 entries
+void launch_refit(const TriangleRec* tris, uint32_t triCount, TravTri* tt, uint32_t ttCount, Node8* nodes, const uint32_t* levelFirst,
+                  uint32_t levels, float* nodeBox, uint32_t* maxBits, cudaStream_t s);
 
 int trace_grid_blocks();   // persistent grid size used by the traversal kernels (for reporting)
 

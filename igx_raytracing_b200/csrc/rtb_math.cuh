@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include "rtb_types.h"
+#include "rtb_crmath.h"
 
 namespace rtb {
 
@@ -55,8 +56,8 @@ RTB_DI vec3 vmin(vec3 a, vec3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), 
 RTB_DI float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
 // binary64 evaluation, one rounding
-RTB_DI float cr_sin(float x) { return (float)sin((double)x); }
-RTB_DI float cr_cos(float x) { return (float)cos((double)x); }
+RTB_DI float cr_sin(float x) { return cr_sin_f(x); }   // rtb_crmath.h: binary64 accuracy without the Payne-Hanek path
+RTB_DI float cr_cos(float x) { return cr_cos_f(x); }
 RTB_DI float cr_asin(float x) { return (float)asin((double)x); }
 RTB_DI float cr_acos(float x) { return (float)acos((double)x); }
 RTB_DI float cr_atan(float x) { return (float)atan((double)x); }
@@ -363,7 +364,7 @@ RTB_DI MatU unpackMaterial(const MaterialRec* m) {
 RTB_DI vec3 shade(const MatU& m, float NdotV, vec3 light, vec3 reflected) {
     vec3 F0 = mix(mk3(0.04f, 0.04f, 0.04f), m.albedo, m.metallic);
     float r1 = 1.0f - m.roughness;
-    vec3 kS = F0 + (vmax(F0, mk3(r1, r1, r1)) - F0) * cr_pow(1.0f - NdotV, 5.0f);
+    vec3 kS = F0 + (vmax(F0, mk3(r1, r1, r1)) - F0) * cr_pow5_f(1.0f - NdotV);
     vec3 kD = (1.0f - kS) * (1.0f - m.metallic);
     return (m.ambient + kD / PI_F) * m.albedo + kS * reflected + light + m.emissive;
 }

@@ -17,17 +17,17 @@ LIB_PATH = os.environ.get("RTB_LIB", os.path.join(HERE, "librtb200.so"))   # RTB
 (BUF_CAMERA, BUF_SEED, BUF_SCENE_INFO, BUF_SHADOW_PROPS, BUF_TRIANGLES, BUF_SPHERES, BUF_CUBES, BUF_PLANES, BUF_LIGHTS,
  BUF_MATERIALS, BUF_MATERIAL_INDICES) = range(11)
 PASS_INIT, PASS_RAYGEN, PASS_SHADOW, PASS_LIGHTING, PASS_COMPOSITE, PASS_FRAME = range(6)
-TGT_DIR_T, TGT_UV_NORMAL, TGT_SHADOW_BITS, TGT_LIGHTING, TGT_ACCUM, TGT_RGBA8, TGT_SEED, TGT_RGBA8_TILED = range(8)
+TGT_DIR_T, TGT_UV_NORMAL, TGT_SHADOW_BITS, TGT_LIGHTING, TGT_ACCUM, TGT_RGBA8, TGT_SEED, TGT_RGBA8_TILED, TGT_ACCEL_NODES, TGT_ACCEL_TRIANGLES = range(10)
 ACCEL_BRUTE, ACCEL_BVH, ACCEL_BVH2 = 0, 1, 2
-OPT_COUNTERS, OPT_TILE_RANK, OPT_TILE_COUNT = 0, 1, 2
+OPT_COUNTERS, OPT_TILE_RANK, OPT_TILE_COUNT, OPT_SKIP_PARITY_STORES, OPT_PRIMARY_PACKETS = 0, 1, 2, 3, 4
 NO_RAY_HIT = 0xFFFFFFFF
 NO_HIT = np.float32(3.4028235e38)
 
 EXPORTS = [
     "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_option", "rtb_set_stream", "rtb_resize", "rtb_upload",
-    "rtb_upload_skybox", "rtb_build_accel", "rtb_accel_info_get", "rtb_dispatch", "rtb_readback", "rtb_device_ptr", "rtb_sync",
+    "rtb_upload_skybox", "rtb_build_accel", "rtb_refit_accel", "rtb_accel_info_get", "rtb_dispatch", "rtb_readback", "rtb_device_ptr", "rtb_sync",
     "rtb_counters_get", "rtb_last_frame_ms", "rtb_trace_rays", "rtb_occlusion_rays", "rtb_untile", "rtb_pack_triangle",
-    "rtb_pack_light_directional", "rtb_pack_light_point", "rtb_pack_material", "rtb_pack_camera", "rtb_load_hdr",
+    "rtb_pack_light_directional", "rtb_pack_light_point", "rtb_pack_material", "rtb_pack_camera", "rtb_load_hdr", "rtb_write_png",
     "rtb_gen_soup", "rtb_gen_heightfield",
 ]
 
@@ -38,7 +38,8 @@ class Limits(C.Structure):
 
 class AccelInfo(C.Structure):
     _fields_ = [("mode", C.c_uint32), ("node_count", C.c_uint32), ("node_bytes", C.c_uint32), ("leaf_count", C.c_uint32),
-                ("max_depth", C.c_uint32), ("tri_record_bytes", C.c_uint32), ("sah_cost", C.c_float), ("build_ms", C.c_float)]
+                ("max_depth", C.c_uint32), ("tri_record_bytes", C.c_uint32), ("sah_cost", C.c_float), ("build_ms", C.c_float),
+                ("leaf_node_extent", C.c_float), ("refits", C.c_uint32), ("primary_packets", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -70,6 +71,7 @@ def lib() -> C.CDLL:
         L.rtb_upload.argtypes = [vp, C.c_int, sz, sz, vp]
         L.rtb_upload_skybox.argtypes = [vp, u32, u32, vp]
         L.rtb_build_accel.argtypes = [vp, C.c_int]
+        L.rtb_refit_accel.argtypes = [vp]
         L.rtb_accel_info_get.argtypes = [vp, C.POINTER(AccelInfo)]
         L.rtb_dispatch.argtypes = [vp, C.c_int]
         L.rtb_readback.argtypes = [vp, C.c_int, vp, sz]
@@ -259,6 +261,17 @@ class Context:
         self.upload_skybox(skybox)
 
     def build_accel(self, mode=ACCEL_BVH): self._ck(self.L.rtb_build_accel(self.h, mode))
+
+    def refit_accel(self): self._ck(self.L.rtb_refit_accel(self.h))
+
+    def accel_bytes(self, target=None):
+        """Raw node (or traversal-triangle) records of the acceleration structure."""
+        target = TGT_ACCEL_NODES if target is None else target
+        _, n = self.device_ptr(target)
+        out = np.zeros(n, np.uint8)
+        if n:
+            self._ck(self.L.rtb_readback(self.h, target, _p(out), n))
+        return out
 
     def accel_info(self) -> AccelInfo:
         a = AccelInfo()

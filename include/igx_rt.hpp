@@ -251,7 +251,8 @@ private:
     SceneGraphInfo info{}, limits{};
     List<u32> materialByObject;
     u32 geometryId = 0;
-    bool geometryDirty = true;      // triangles changed since the last acceleration-structure build
+    bool geometryDirty = true;      // triangles changed since the last acceleration-structure build or refit
+    bool topologyDirty = true;      // ... and their number or order changed too: a refit is not enough
     String sceneName;
     List<u16> skyboxPixels; u32 skyW = 0, skyH = 0; bool skyboxDirty = false;
     int lastError = 0;
@@ -287,7 +288,7 @@ public:
             const u8 t = u8(it->second.type);
             objects[t].toIndex[it->second.index] = 0;
             objects[t].markedForUpdate[it->second.index] = false;
-            if (it->second.type == SceneObjectType::TRIANGLE) geometryDirty = true;
+            if (it->second.type == SceneObjectType::TRIANGLE) geometryDirty = topologyDirty = true;
             entries.erase(it);
         }
     }
@@ -351,11 +352,16 @@ public:
     }
 
     // the copy commands of the frame (scene_graph.cpp:253-265); the skybox is flushed when it changed, and the
-    // acceleration structure — which the reference does not have — is rebuilt when triangles changed
+    // acceleration structure — which the reference does not have — follows the triangles: update<Triangle>() (the
+    // reference's per-frame mutation path, niels_scene.cpp:61-70) costs a device refit, add / del / compaction a rebuild
     void fillCommandList(CommandList* cl) {
         cl->add([this](rtb_ctx* c) {
             if (skyboxDirty) { skyboxDirty = false; const int rc = rtb_upload_skybox(c, skyW, skyH, skyboxPixels.empty() ? nullptr : skyboxPixels.data()); if (rc) return rc; }
-            if (geometryDirty) { geometryDirty = false; return rtb_build_accel(c, accelMode); }
+            if (geometryDirty) {
+                const bool rebuild = topologyDirty;
+                geometryDirty = topologyDirty = false;
+                return rebuild ? rtb_build_accel(c, accelMode) : rtb_refit_accel(c);
+            }
             return 0;
         });
     }
@@ -387,7 +393,7 @@ private:
         obj.markedForUpdate[i] = true;
         obj.toIndex[i] = counter;
         std::memcpy(obj.cpuData.data() + siz * i, v, siz);
-        if (t == SceneObjectType::TRIANGLE) geometryDirty = true;
+        if (t == SceneObjectType::TRIANGLE) geometryDirty = topologyDirty = true;
         return counter;
     }
 
@@ -453,7 +459,7 @@ private:
                 ++j;
             }
             for (u32 i = j; i < count; ++i) { obj.toIndex[i] = 0; obj.markedForUpdate[i] = false; }
-            if (type == SceneObjectType::TRIANGLE) geometryDirty = true;
+            if (type == SceneObjectType::TRIANGLE) geometryDirty = topologyDirty = true;
         }
         count = j;
         std::memcpy(cpuPtr, gpuPtr, usz(j) * stride);

@@ -77,14 +77,16 @@ typedef enum rtb_target {
     RTB_TGT_RGBA8 = 5,        /* rgba8    w*h*4 B    (what presentToCpu copies out) */
     RTB_TGT_SEED = 6,         /* 24 B: the Seed buffer after K0 */
     RTB_TGT_RGBA8_TILED = 7,  /* multi-GPU only: this rank's pixels in wavefront-slot order; ceil(blocks/n)*4096 B on every rank (see rtb_untile) */
-    RTB_TGT_COUNT = 8
+    RTB_TGT_ACCEL_NODES = 8,  /* the acceleration structure's node records (rtb_accel_info.node_count * node_bytes): inspection / tests */
+    RTB_TGT_ACCEL_TRIANGLES = 9, /* its traversal triangles (48 B each, leaf order) */
+    RTB_TGT_COUNT = 10
 } rtb_target;
 
 /* How the nearest-hit search runs.  The reference has exactly one way: a linear loop over every
  * primitive (ref: res/shaders/trace.glsl:25-45,78-94).  BVH is new and returns the same hits. */
 typedef enum rtb_accel_mode {
     RTB_ACCEL_BRUTE = 0,   /* the reference algorithm, verbatim, on the GPU */
-    RTB_ACCEL_BVH = 1,     /* triangles through the 8-wide compressed BVH (80-byte nodes); spheres, cubes, planes stay linear */
+    RTB_ACCEL_BVH = 1,     /* triangles through the 8-wide compressed BVH (128-byte nodes); spheres, cubes, planes stay linear */
     RTB_ACCEL_BVH2 = 2     /* triangles through the binary BVH (64-byte two-box nodes): the first-generation kernel, kept for comparison */
 } rtb_accel_mode;
 
@@ -97,6 +99,9 @@ typedef struct rtb_accel_info {
     uint32_t tri_record_bytes;/* bytes per traversal triangle record */
     float    sah_cost;
     float    build_ms;        /* host wall clock of the last build */
+    float    leaf_node_extent;/* 8-wide tree: mean edge length of the nodes that hold only triangles (world units) */
+    uint32_t refits;          /* rtb_refit_accel calls served by a device refit since the last host build */
+    uint32_t primary_packets; /* 1 when the last RAYGEN / FRAME dispatch walked the camera rays as 8x4-pixel packets */
 } rtb_accel_info;
 
 /* Counters of the last instrumented dispatch (rtb_set_option(RTB_OPT_COUNTERS, 1)); the timed build
@@ -109,11 +114,17 @@ typedef struct rtb_counters {
 } rtb_counters;
 
 typedef enum rtb_option {
-    RTB_OPT_COUNTERS = 0,     /* 0/1: run the instrumented traversal kernels */
+    RTB_OPT_COUNTERS = 0,     /* 0: off.  1: instrumented per-ray traversal (the ALGORITHMIC node / triangle records each ray
+                                 needs).  2: instrumented build of the kernels in use (records actually fetched: a packet
+                                 fetch serves 32 rays and counts once) */
     RTB_OPT_TILE_RANK = 1,    /* multi-GPU screen partition: this context renders tiles t with t % count == rank */
     RTB_OPT_TILE_COUNT = 2,
-    RTB_OPT_SKIP_PARITY_STORES = 3 /* 0/1: RELEASE-shader behaviour (no uvObjectNormal/lighting store on misses) is NOT
+    RTB_OPT_SKIP_PARITY_STORES = 3,/* 0/1: RELEASE-shader behaviour (no uvObjectNormal/lighting store on misses) is NOT
                                       modelled; reserved, must be 0 */
+    RTB_OPT_PRIMARY_PACKETS = 4    /* nearest-hit search of the camera rays with RTB_ACCEL_BVH: 0 = one traversal per ray,
+                                      1 = one warp-cooperative traversal per 8x4 pixel patch, 2 = choose from the patch
+                                      size against the tree's leaf nodes (default).  Same hits either way.  With 1 the
+                                      rays-in call rtb_trace_rays also walks its rays in packets of 32 consecutive rays. */
 } rtb_option;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
@@ -139,6 +150,13 @@ int  rtb_upload_skybox(rtb_ctx* ctx, uint32_t width, uint32_t height, const uint
 /* NEW (no reference counterpart): (re)build the acceleration structure over the uploaded triangles.
  * Must be called after triangle uploads and before a dispatch when mode == RTB_ACCEL_BVH. */
 int  rtb_build_accel(rtb_ctx* ctx, rtb_accel_mode mode);
+/* NEW: after triangles MOVED (same count; uploads into RTB_BUF_TRIANGLES), recompute every box of the existing tree on
+ * the device instead of rebuilding it on the host — what a per-frame SceneGraph::update of dirty triangle ranges needs
+ * (ref: igx/src/helpers/scene_graph.cpp:267-323, test/scene/niels_scene.cpp:61-70).  Stream-ordered, no host work
+ * beyond the launches.  Topology is kept, so hits stay exact but traversal cost grows with the deformation; rebuild
+ * when rtb_accel_info.sah_cost matters.  Falls back to rtb_build_accel when there is no 8-wide tree of the current
+ * triangle count (first call, other mode, count changed). */
+int  rtb_refit_accel(rtb_ctx* ctx);
 int  rtb_accel_info_get(const rtb_ctx* ctx, rtb_accel_info* out);
 
 /* ---- execution ----------------------------------------------------------------------------------- */
@@ -188,6 +206,12 @@ void rtb_pack_camera(const float eye[3], float pitch, float yaw, float roll, flo
 /* Radiance .hdr -> rgba16f the way igxi-convert does (ref: igx/igxi-tool/src/igxi/convert.cpp:59-78,148-153,209-231).
  * out == NULL only queries the size. */
 int  rtb_load_hdr(const char* path, uint16_t* out, uint32_t* width, uint32_t* height);
+
+/* Frame export: an rgba8 frame as read back from RTB_TGT_RGBA8 -> 8-bit RGBA PNG at `path`.  flip_vertically != 0 writes the
+ * last row first, which is what the reference does (row 0 of the frame is the bottom of the view)
+ * (ref: src/rt/raytracing_interface.cpp:124-142 onRenderFinish -> igxi::Helper::toDiskExternal,
+ *  igx/igxi-tool/src/igxi/convert.cpp:747-781,904-928).  Host-only; returns 0 on success. */
+int  rtb_write_png(const char* path, uint32_t width, uint32_t height, const void* rgba8, int flip_vertically);
 
 /* ---- synthetic scenes of BASELINE.json (no reference counterpart; deterministic) ------------------- */
 /* n flat-shaded triangles: centre uniform in [-10,10]^3, three offsets uniform in [-0.05,0.05]^3 */

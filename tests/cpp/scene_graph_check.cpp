@@ -110,5 +110,23 @@ int main(int argc, char** argv) {
     CHECK(rti.error() == 0);
     std::FILE* f = argc > 2 ? std::fopen(argv[2], "wb") : nullptr;
     if (f) { std::fwrite(px.data(), 4, px.size(), f); std::fclose(f); }
+    // third frame after moving a TRIANGLE with update<T>(): dirty-range upload + device refit (no host rebuild)
+    u64 tri1 = 0;
+    for (u64 hnd = 1; hnd < 64 && !tri1; ++hnd) {
+        auto it = sg2.find(hnd);
+        if (sg2.exists(hnd) && it->second.type == SceneObjectType::TRIANGLE && it->second.index == 1) tri1 = hnd;
+    }
+    CHECK(tri1 != 0);
+    rtb_accel_info ai{};
+    CHECK(rtb_accel_info_get(dev2.get(), &ai) == 0 && ai.refits == 0);
+    CHECK(sg2.update(tri1, Triangle(Vec3f32(-3, 6, 1), Vec3f32(2, 5, 0.5f), Vec3f32(1, 2, 3))));
+    rti.update(0.2);
+    rti.render();
+    CHECK(rti.readPixels(px));
+    CHECK(rti.error() == 0);
+    CHECK(rtb_accel_info_get(dev2.get(), &ai) == 0 && ai.refits == 1);
+    f = argc > 3 ? std::fopen(argv[3], "wb") : nullptr;
+    if (f) { std::fwrite(px.data(), 4, px.size(), f); std::fclose(f); }
+    std::printf("OK refit frame\n");
     return 0;
 }

@@ -218,3 +218,13 @@ def test_scene_graph_facade_host_logic(rtb, tmp_path):
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     assert "OK" in r.stdout, r.stdout
+
+
+def test_crmath_matches_binary64_libm(tmp_path):
+    """rtb_crmath.h (sin / cos / pow5 of binary32 arguments without the slow general path) returns the binary32 value the
+    oracle's `(float)std::sin((double)x)` returns: ~1.6e8 arguments incl. the RNG's own, at most 1e-7 may differ."""
+    exe = str(tmp_path / "crmath_check")
+    subprocess.check_call(["g++", "-O2", "-march=native", "-fopenmp", "-ffp-contract=off", "-I", os.path.join(ROOT, "igx_raytracing_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "cpp", "crmath_check.cpp"), "-o", exe])
+    r = subprocess.run([exe, "37"], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout

@@ -248,16 +248,67 @@ def test_soup_full_size_bvh_equals_brute(rtb):
     for mode in (rtb.ACCEL_BVH, rtb.ACCEL_BVH2, rtb.ACCEL_BRUTE):
         ctx = make_ctx(rtb, scene, None, w, h, 1, mode, max_triangles=n_tri)
         ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 13.9)))
-        ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
-        ctx.dispatch(rtb.PASS_FRAME)
-        out[mode] = (ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8))
-        if mode != rtb.ACCEL_BRUTE:
-            info = ctx.accel_info()
-            assert info.node_count > n_tri // 16 and info.max_depth <= 60
+        for packets in ((0, 1) if mode == rtb.ACCEL_BVH else (2,)):   # camera rays one by one / as 8x4-pixel packets
+            ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
+            ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+            ctx.dispatch(rtb.PASS_FRAME)
+            out[mode, packets] = (ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8))
+            if mode != rtb.ACCEL_BRUTE:
+                info = ctx.accel_info()
+                assert info.node_count > n_tri // 16 and info.max_depth <= 60
+                assert mode != rtb.ACCEL_BVH or info.primary_packets == packets
         ctx.close()
     n = w * h
-    for accel in (rtb.ACCEL_BVH, rtb.ACCEL_BVH2):
-        compare_frames(out[accel], out[rtb.ACCEL_BRUTE], n)
+    for key in ((rtb.ACCEL_BVH, 0), (rtb.ACCEL_BVH, 1), (rtb.ACCEL_BVH2, 2)):
+        compare_frames(out[key], out[rtb.ACCEL_BRUTE, 2], n)
+    # the two 8-wide kernels run the same triangle arithmetic with the same tie rule: identical, not just close
+    for a, b in zip(out[rtb.ACCEL_BVH, 0], out[rtb.ACCEL_BVH, 1]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("pose", ["all_objects", "inside_cube"])
+def test_niels_frame_packets(rtb, oracle, sky, pose):
+    """NielsScene through the packet kernel (forced on: the auto rule would pick it anyway for three large triangles)."""
+    w, h = 333, 127
+    scene = rtb.niels_scene(0.0)
+    ctx = make_ctx(rtb, scene, sky, w, h, 1, rtb.ACCEL_BVH)
+    ctx.set_option(rtb.OPT_PRIMARY_PACKETS, 1)
+    cam = rtb.pack_camera(w, h, **POSES[pose])
+    ctx.upload(rtb.BUF_CAMERA, cam)
+    ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+    ctx.dispatch(rtb.PASS_FRAME)
+    assert ctx.accel_info().primary_packets == 1
+    got = dict(dirT=ctx.readback(rtb.TGT_DIR_T), uvN=ctx.readback(rtb.TGT_UV_NORMAL), bits=ctx.readback(rtb.TGT_SHADOW_BITS),
+               lighting=ctx.readback(rtb.TGT_LIGHTING), rgba8=ctx.readback(rtb.TGT_RGBA8), accum=ctx.readback(rtb.TGT_ACCUM),
+               seed=ctx.readback(rtb.TGT_SEED))
+    ctx.close()
+    oseed = oracle.seed((0.0, 0.0))
+    ref = oracle.frame(to_oracle_scene(scene, sky), oracle.camera(w, h, **POSES[pose]), oseed, 1)
+    ref["seed"] = oseed
+    check_frame(got, ref, w, h)
+
+
+def test_soup_rays_in_packets(rtb, oracle):
+    """Rays-in mode with packets forced on, on INCOHERENT rays (32 unrelated rays per packet): the union walk must
+    still return exactly the per-ray result — coherence is a performance assumption, never a correctness one."""
+    n_tri, n_rays = 20000, 4096
+    scene = soup_scene(rtb, n_tri)
+    rng = np.random.default_rng(5)
+    o = rng.uniform(-12, 12, (n_rays, 3)).astype(np.float32)
+    d = rng.normal(size=(n_rays, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], axis=1).astype(np.float32)
+    ctx = make_ctx(rtb, scene, None, 64, 64, 1, rtb.ACCEL_BVH, max_triangles=n_tri)
+    res = {}
+    for packets in (0, 1):
+        ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
+        res[packets] = ctx.trace_rays(rays)
+    ctx.close()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    obj, t, uv, nrm, flags = oracle.trace_rays(to_oracle_scene(scene), rays, want_flags=True)
+    ok = flags == 0
+    assert np.array_equal(res[1][0][ok], obj[ok])
 
 
 def compare_frames(a, b, n):
@@ -326,9 +377,9 @@ def test_cpp_facade_renders_like_the_oracle(rtb, oracle, tmp_path):
     libdir = os.path.dirname(rtb.LIB_PATH)
     subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-ffp-contract=off", "-I", os.path.join(root, "include"),
                     os.path.join(root, "tests", "cpp", "scene_graph_check.cpp"), "-L", libdir, "-lrtb200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
-    out = str(tmp_path / "frame.bin")
-    r = subprocess.run([exe, "render", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert r.returncode == 0 and "OK render" in r.stdout, r.stdout
+    out, out3 = str(tmp_path / "frame.bin"), str(tmp_path / "frame3.bin")
+    r = subprocess.run([exe, "render", out, out3], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "OK render" in r.stdout and "OK refit frame" in r.stdout, r.stdout
     got = np.fromfile(out, np.uint32).reshape(360, 640)
     scene = rtb.niels_scene(0.0)
     sph = scene["spheres"].view(np.float32).reshape(7, 4).copy()
@@ -337,3 +388,70 @@ def test_cpp_facade_renders_like_the_oracle(rtb, oracle, tmp_path):
     ref = oracle.frame(to_oracle_scene(scene), oracle.camera(640, 360, eye=(6, 5, 12)), oracle.seed((0.0, 0.0)), 1)
     d = np.abs(got.view(np.uint8).astype(np.int32) - ref["rgba8"].view(np.uint8).reshape(-1).astype(np.int32).reshape(got.view(np.uint8).shape))
     assert int((d > 1).sum()) <= 4 and int((d > 0).sum()) <= 64, f"{int((d > 0).sum())} channel values differ"
+    # third frame: triangle 1 moved through update<Triangle>() -> device refit; the oracle sees the moved triangle
+    got3 = np.fromfile(out3, np.uint32).reshape(360, 640)
+    tri = scene["triangles"].copy()
+    tri[48:96] = oracle.triangle_flat([[-3, 6, 1], [2, 5, 0.5], [1, 2, 3]])
+    scene["triangles"] = tri
+    ref3 = oracle.frame(to_oracle_scene(scene), oracle.camera(640, 360, eye=(6, 5, 12)), oracle.seed((0.0, 0.0)), 1)
+    d3 = np.abs(got3.view(np.uint8).astype(np.int32) - ref3["rgba8"].view(np.uint8).reshape(-1).astype(np.int32).reshape(got3.view(np.uint8).shape))
+    assert int((d3 > 1).sum()) <= 4 and int((d3 > 0).sum()) <= 64, f"{int((d3 > 0).sum())} channel values differ after the refit"
+    assert int((got3 != got).sum()) > 500, "the moved triangle must change the picture"
+
+
+def test_refit_unmoved_reproduces_the_build(rtb):
+    """rtb_refit_accel on unmoved triangles rewrites every node and traversal triangle bit for bit: the device refit
+    and the host builder share one encoder (csrc/rtb_node8_encode.h) and one padding rule."""
+    n_tri = 50000
+    scene = soup_scene(rtb, n_tri)
+    ctx = make_ctx(rtb, scene, None, 64, 64, 1, rtb.ACCEL_BVH, max_triangles=n_tri)
+    nodes0, tris0 = ctx.accel_bytes(rtb.TGT_ACCEL_NODES), ctx.accel_bytes(rtb.TGT_ACCEL_TRIANGLES)
+    assert nodes0.size == ctx.accel_info().node_count * 128 and tris0.size == n_tri * 48
+    ctx.refit_accel()
+    assert ctx.accel_info().refits == 1
+    assert np.array_equal(ctx.accel_bytes(rtb.TGT_ACCEL_NODES), nodes0)
+    assert np.array_equal(ctx.accel_bytes(rtb.TGT_ACCEL_TRIANGLES), tris0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("packets", [0, 1])
+def test_refit_after_motion_equals_brute(rtb, packets):
+    """Triangles move (a dirty-range upload, as SceneGraph::update does), the tree is refitted on the device, and the
+    nearest hits / shadow bits / pixels equal the reference's linear loop over the moved triangles."""
+    n_tri, w, h = 100000, 320, 180
+    scene = soup_scene(rtb, n_tri)
+    ctx = make_ctx(rtb, scene, None, w, h, 1, rtb.ACCEL_BVH, max_triangles=n_tri)
+    ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
+    tris = scene["triangles"].copy().view(np.float32).reshape(n_tri, 12)
+    rng = np.random.default_rng(3)
+    lo, hi = 20000, 60000                                    # the dirty range
+    shift = rng.uniform(-0.3, 0.3, (hi - lo, 1, 3)).astype(np.float32)
+    shift[:100] *= 40.0                                      # a few fly far outside the old bounds
+    pts = tris[lo:hi].reshape(-1, 3, 4)
+    pts[:, :, :3] += shift
+    moved = tris.reshape(-1).view(np.uint8)
+    ctx.upload(rtb.BUF_TRIANGLES, moved[lo * 48:hi * 48], offset=lo * 48)
+    with pytest.raises(rtb.RtbError):                        # stale tree: the dispatch refuses
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 13.9)))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+        ctx.dispatch(rtb.PASS_FRAME)
+    ctx.refit_accel()
+    ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+    ctx.dispatch(rtb.PASS_FRAME)
+    got = (ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8))
+    assert ctx.accel_info().refits == 1
+    ctx.close()
+    scene2 = dict(scene, triangles=moved.copy())
+    ref_ctx = make_ctx(rtb, scene2, None, w, h, 1, rtb.ACCEL_BRUTE, max_triangles=n_tri)
+    ref_ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 13.9)))
+    ref_ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+    ref_ctx.dispatch(rtb.PASS_FRAME)
+    ref = (ref_ctx.readback(rtb.TGT_DIR_T), ref_ctx.readback(rtb.TGT_SHADOW_BITS), ref_ctx.readback(rtb.TGT_RGBA8))
+    ref_ctx.close()
+    ids_a, ids_b = got[0][..., 3].view(np.uint32), ref[0][..., 3].view(np.uint32)
+    assert (ids_a != NO_RAY_HIT).mean() > 0.03
+    assert int((ids_a != ids_b).sum()) <= 1e-4 * w * h
+    same = ids_a == ids_b
+    assert np.array_equal(got[0].view(np.uint32)[same], ref[0].view(np.uint32)[same])
+    assert int((got[1] != ref[1]).sum()) <= 1e-4 * w * h
+    assert int((got[2] != ref[2]).sum()) <= 2e-4 * w * h
