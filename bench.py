@@ -42,6 +42,12 @@ WORKLOADS = {
                       desc="configs[1]: NielsScene (13 primitives) at 1920x1080, 1 spp primary + 1 shadow ray"),
     "heightfield10m": dict(kind="heightfield", grid=2236, width=1920, height=1080, eye=(0.0, 6.0, 13.0), pitch=0.45, samples=1,
                            desc="configs[3] geometry: 10M-triangle displaced height field at 1080p, first hit + 1 shadow ray (no bounces: the reference has none)"),
+    # BASELINE.json configs[4]: 8K, 16 spp progressive accumulation (the reference's export path: the command list replayed
+    # per sample with USE_SUPERSAMPLING, raytracing_interface.cpp:196-242), screen tiles across the ranks, one gather per frame
+    "niels8k16": dict(kind="niels", width=7680, height=4320, eye=(6.0, 5.0, 12.0), samples=1, spp=16,
+                      desc="configs[4]: NielsScene at 7680x4320, 16 spp progressive accumulation (16 replays of init..composite per frame), 1 shadow ray per sample"),
+    "soup8k16": dict(kind="soup", triangles=1_000_000, width=7680, height=4320, eye=(0.0, 0.0, 13.9), samples=1, spp=16,
+                     desc="configs[4] on the configs[2] scene: 1M-triangle soup at 7680x4320, 16 spp progressive accumulation, 1 shadow ray per sample"),
 }
 
 
@@ -62,7 +68,7 @@ def build_scene(rtb, wl):
 
 
 def camera_kwargs(wl):
-    return dict(eye=wl["eye"], pitch=wl.get("pitch", 0.0), yaw=wl.get("yaw", 0.0))
+    return dict(eye=wl["eye"], pitch=wl.get("pitch", 0.0), yaw=wl.get("yaw", 0.0), flags=2 if wl.get("spp", 1) > 1 else 0)
 
 
 class ClockSampler:
@@ -243,11 +249,16 @@ def main():
         if rank == 0:
             gathered = torch.empty(world * slots, dtype=torch.int32, device=f"cuda:{local_rank}")
 
+    spp = wl.get("spp", 1)
+
     def frame(e2e: bool):
         if e2e:   # what the host does per frame in the reference: camera + seed upload (raytracing_interface.cpp:327, composite_task.cpp:243)
             ctx.upload_raw(rtb.BUF_CAMERA, cam_pin.data_ptr(), 144)
             ctx.upload_raw(rtb.BUF_SEED, seed_pin.data_ptr(), 24)
-        ctx.dispatch(rtb.PASS_FRAME)
+        elif spp > 1:   # a new accumulation starts at sampleCount 0
+            ctx.upload_raw(rtb.BUF_SEED, seed_pin.data_ptr(), 24)
+        for _ in range(spp):   # the recorded command list replayed once per sample
+            ctx.dispatch(rtb.PASS_FRAME)
         if world > 1:
             dist.gather(tiled, list(gathered.split(slots)) if rank == 0 else None, dst=0)
             if rank == 0:
@@ -268,6 +279,12 @@ def main():
     ctx.dispatch(rtb.PASS_FRAME)
     ctx.sync()
     c = ctx.counters()
+    hits_all = c.primary_hits
+    for _ in range(spp - 1):   # every sample has its own jitter: count the hit pixels (= shadow rays) of each
+        ctx.dispatch(rtb.PASS_FRAME)
+        ctx.sync()
+        hits_all += ctx.counters().primary_hits
+    hits_local = torch.tensor([hits_all], dtype=torch.int64, device="cuda")
     ctx.set_option(rtb.OPT_COUNTERS, 2)   # what the kernels in use fetch (a packet fetch serves 32 rays and counts once)
     ctx.dispatch(rtb.PASS_FRAME)
     ctx.sync()
@@ -280,9 +297,10 @@ def main():
                           c.shadow_occluded], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(local)
+        dist.all_reduce(hits_local)
     tot = local.tolist()
-    # rays per frame: every pixel's primary ray + one shadow ray per hit pixel and sample
-    rays_per_frame = w * h + tot[6] * samples
+    # rays per frame: every pixel's primary ray + one shadow ray per hit pixel and shadow sample, for each of the spp replays
+    rays_per_frame = w * h * spp + int(hits_local.item()) * samples
 
     def timed(e2e: bool, steps: int, warmup: int, sample_clocks: bool):
         ctx.upload(rtb.BUF_SEED, seed0)
@@ -341,10 +359,19 @@ def main():
     except Exception:
         pass
 
+    # second denominator: L2 read bandwidth measured on this GPU by the library's streaming probe (48 MiB, L2-only loads)
+    try:
+        l2_peak = ctx.probe_l2_read_gbs(48 << 20)
+    except Exception:
+        l2_peak = None
+
     def roof(kernel, nbytes, secs, key):
         ach = nbytes / secs / 1e9 if secs > 0 else 0.0
-        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic.get(key),
-                "kernel": kernel, "algorithmic_bytes_per_launch_rank0": nbytes, "ms_per_launch": secs * 1e3}
+        r = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic.get(key),
+             "kernel": kernel, "algorithmic_bytes_per_launch_rank0": nbytes, "ms_per_launch": secs * 1e3}
+        if l2_peak:
+            r["l2"] = {"peak": l2_peak, "unit": "GB/s", "frac": ach / l2_peak, "peak_source": "rtb_probe_l2_read_gbs, 48 MiB buffer, ld.global.cg, best of 5"}
+        return r
 
     if info.primary_packets:
         roofline = roof("k_trace_cwbvh_packet (nearest-hit launch: one warp-cooperative traversal per 8x4-pixel patch)", bytes_primary, t_primary, "k_trace_cwbvh_packet")
@@ -367,11 +394,11 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{n_px} random pixels of the same {w}x{h} frame ({rays} rays, {secs:.1f} s), brute force over {n_tri} triangles as the reference shaders do"}
 
-    kernels_per_frame = 7
+    kernels_per_frame = 7 * spp
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "rays_per_frame": rays_per_frame, "hit_fraction": tot[6] / (w * h),
+        "config": {"workload": wl["desc"], "spp": spp, "rays_per_frame": rays_per_frame, "hit_fraction": tot[6] / (w * h),
                    "l2": "no explicit flush: each frame streams ~0.9 GB of ray / G-buffer data through the 126 MB L2 between traversal launches; the BVH (nodes + triangles) stays resident as it would in steady-state rendering",
                    "partition": f"{world} ranks x interleaved 32x32-pixel blocks, scene+BVH replicated, NCCL gather of rgba8 tiles to rank 0" if world > 1 else "single GPU",
                    "bvh": {"nodes": info.node_count, "node_bytes": info.node_bytes, "leaves": info.leaf_count, "depth": info.max_depth,

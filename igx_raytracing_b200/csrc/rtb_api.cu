@@ -175,6 +175,7 @@ int passRaygen(rtb_ctx* c, bool mark) {
     launch_trace_closest(sv, c->rays.p, c->fm.localSlots, c->hits.p, c->workCounter.p, c->countersOn ? c->counters.p : nullptr, c->lastPrimaryPackets, c->stream);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     launch_finish_primary(c->fm, sv, c->rays.p, c->hits.p, c->dirT.p, c->uvN.p, c->stream);
+    if (c->countersOn) launch_count_hits(c->fm, c->dirT.p, c->counters.p, c->stream);
     return RTB_OK;
 }
 int passShadow(rtb_ctx* c, bool mark) {
@@ -482,6 +483,16 @@ int rtb_untile(rtb_ctx* c, const void* tiledAll, uint32_t nranks, uint32_t slots
     if ((uint64_t)((total + nranks - 1) / nranks) * 1024ull > slotsPerRank) return fail(c, RTB_ERR_ARG, "rtb_untile: slots_per_rank too small for this frame");
     launch_untile(fm, static_cast<const uint32_t*>(tiledAll), slotsPerRank, out ? static_cast<uint32_t*>(out) : c->rgba8.p, c->stream);
     RTB_CUDA(c, cudaGetLastError());
+    return RTB_OK;
+}
+
+int rtb_probe_l2_read_gbs(rtb_ctx* c, size_t bytes, double* outGbs) {
+    if (!c || !outGbs || bytes < (1u << 20)) return c ? fail(c, RTB_ERR_ARG, "rtb_probe_l2_read_gbs: bad argument") : RTB_ERR_ARG;
+    RTB_BIND(c);
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const double v = measure_l2_read_gbs(bytes, 64, c->stream);
+    if (v < 0.0) return cudaFail(c, (cudaError_t)(int)(-v), "measure_l2_read_gbs");
+    *outGbs = v;
     return RTB_OK;
 }
 

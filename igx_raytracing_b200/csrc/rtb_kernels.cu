@@ -455,6 +455,20 @@ void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec
     k_finish_primary<<<(fm.localSlots + 255) / 256, 256, 0, st>>>(fm, sv, rays, hits, dirT, uvN);
 }
 
+// instrumented frames only: pixels whose nearest hit is ANY primitive (= the shadow rays the reference traces per sample)
+__global__ void __launch_bounds__(256) k_count_hits(const FrameMap fm, const float4* __restrict__ dirT, TraceCounters* __restrict__ counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t x, y;
+    const bool hit = i < fm.localSlots && slotToPixel(fm, i, x, y) && fbits(dirT[(size_t)y * fm.w + x].w) != NO_RAY_HIT;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    if ((threadIdx.x & 31u) == 0 && m) atomicAdd(&counters->hits, (unsigned long long)__popc(m));
+}
+void launch_count_hits(const FrameMap& fm, const float4* dirT, TraceCounters* counters, cudaStream_t st) {
+    if (!fm.localSlots) return;
+    cudaMemsetAsync(&counters->hits, 0, sizeof(unsigned long long), st);
+    k_count_hits<<<(fm.localSlots + 255) / 256, 256, 0, st>>>(fm, dirT, counters);
+}
+
 __global__ void __launch_bounds__(256) k_finish_rays(const SceneView sv, const RayRec* __restrict__ rays, const TriHit* __restrict__ hits,
                                                      uint32_t n, uint32_t* __restrict__ object, float* __restrict__ t, float2* __restrict__ uv) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -36,6 +36,8 @@ void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, T
 // spheres, cubes, planes after the triangles, normal interpolation, G-buffer stores (raygen.comp:39-51)
 void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits,
                            float4* dirT, float4* uvN, cudaStream_t s);
+// instrumented frames: counters->hits = pixels of this rank whose nearest hit is any primitive
+void launch_count_hits(const FrameMap& fm, const float4* dirT, TraceCounters* counters, cudaStream_t s);
 // shadow.comp ray set-up + occlusion by the non-triangle primitives; leaves triangle work in `rays`
 void launch_shadowgen(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
                       const float4* dirT, RayRec* rays, uint32_t* bits, cudaStream_t s);
@@ -60,6 +62,9 @@ void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsP
 // refit of the 8-wide tree from the current triangle buffer (rtb_refit.cu); levelFirst is a HOST array of levels + 1 entries
 void launch_refit(const TriangleRec* tris, uint32_t triCount, TravTri* tt, uint32_t ttCount, Node8* nodes, const uint32_t* levelFirst,
                   uint32_t levels, float* nodeBox, uint32_t* maxBits, cudaStream_t s);
+
+// rtb_probe.cu: L2 read bandwidth (GB/s) over a buffer of `bytes` read `passes` times; negative = -cudaError_t
+double measure_l2_read_gbs(size_t bytes, uint32_t passes, cudaStream_t s);
 
 int trace_grid_blocks();   // persistent grid size used by the traversal kernels (for reporting)
 

@@ -26,7 +26,7 @@ NO_HIT = np.float32(3.4028235e38)
 EXPORTS = [
     "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_option", "rtb_set_stream", "rtb_resize", "rtb_upload",
     "rtb_upload_skybox", "rtb_build_accel", "rtb_refit_accel", "rtb_accel_info_get", "rtb_dispatch", "rtb_readback", "rtb_device_ptr", "rtb_sync",
-    "rtb_counters_get", "rtb_last_frame_ms", "rtb_trace_rays", "rtb_occlusion_rays", "rtb_untile", "rtb_pack_triangle",
+    "rtb_counters_get", "rtb_probe_l2_read_gbs", "rtb_last_frame_ms", "rtb_trace_rays", "rtb_occlusion_rays", "rtb_untile", "rtb_pack_triangle",
     "rtb_pack_light_directional", "rtb_pack_light_point", "rtb_pack_material", "rtb_pack_camera", "rtb_load_hdr", "rtb_write_png",
     "rtb_gen_soup", "rtb_gen_heightfield",
 ]
@@ -143,6 +143,16 @@ def make_seed(cpu_offset=(0.0, 0.0), sample_count=0, sample_offset=0, random=(0.
     s[:16].view(np.float32)[:] = [random[0], random[1], cpu_offset[0], cpu_offset[1]]
     s[16:].view(np.uint32)[:] = [sample_count, sample_offset]
     return s
+
+
+def write_png(path, rgba8, flip_vertically=True):
+    """rgba8: (h, w) uint32 or (h, w, 4) uint8 frame as read back from TGT_RGBA8 (row 0 = bottom of the view)."""
+    a = np.ascontiguousarray(rgba8)
+    h, w = a.shape[0], a.shape[1]
+    lib().rtb_write_png.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
+    rc = lib().rtb_write_png(str(path).encode(), w, h, _p(a), 1 if flip_vertically else 0)
+    if rc:
+        raise IOError(f"rtb_write_png({path}): error {rc}")
 
 
 def load_hdr(path: str) -> np.ndarray:
@@ -296,6 +306,12 @@ class Context:
         p, n = C.c_void_p(), C.c_size_t()
         self._ck(self.L.rtb_device_ptr(self.h, target, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def probe_l2_read_gbs(self, nbytes=64 << 20) -> float:
+        v = C.c_double()
+        self.L.rtb_probe_l2_read_gbs.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]
+        self._ck(self.L.rtb_probe_l2_read_gbs(self.h, nbytes, C.byref(v)))
+        return v.value
 
     def counters(self) -> Counters:
         c = Counters()

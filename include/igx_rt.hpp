@@ -615,6 +615,22 @@ public:
 
 // Headless RaytracingInterface: camera buffer + CompositeTask + pre/post passes, one command list replayed per frame
 // (ref: src/rt/raytracing_interface.cpp:19-54,96-120,144-179,194-255,258-339).  Window, swapchain, input and GUI are out of scope.
+// Output presets and export settings (include/rt/raytracing_interface.hpp:20-91).  UI-only members (fps readout, the
+// Nuklear button) are not modelled; exportToPNG() arms the next render() exactly like the reference's button does.
+enum class Resolution : u8 { CUSTOM, SD, HD, FHD, QHD, UHD_4K, UHD_8K };
+static constexpr u16 pixelsByResolution[7][2] = {{0, 0}, {720, 480}, {1280, 720}, {1920, 1080}, {2560, 1440}, {3840, 2160}, {7680, 4320}};
+
+struct RaytracingProperties {
+    String targetOutput = "./output/0";       // ".png" is appended (igxi::Helper::toDiskExternal, convert.cpp:877-886,925)
+    u16 targetSizeX = 7680, targetSizeY = 4320;
+    u16 targetSamples = 128;                  // ui::Slider<u16, 1, 4096>
+    Resolution res = Resolution::UHD_8K;
+    bool shouldOutputNextFrame = false, isPortrait = false;
+    void exportToPNG() { shouldOutputNextFrame = true; }
+    void setResolution(Resolution r) { res = r; if (r != Resolution::CUSTOM) { targetSizeX = pixelsByResolution[u8(r)][0]; targetSizeY = pixelsByResolution[u8(r)][1]; } }
+    Vec2u32 getRes() const { return isPortrait ? Vec2u32(targetSizeY, targetSizeX) : Vec2u32(targetSizeX, targetSizeY); }
+};
+
 class RaytracingInterface {
     Device& device;
     SceneGraph* sceneGraph;
@@ -625,7 +641,9 @@ class RaytracingInterface {
     int lastError = 0;
 public:
     CPUCamera camera;
-    u32 targetSamples = 1;          // RaytracingProperties::targetSamples (include/rt/raytracing_interface.hpp:51)
+    u32 targetSamples = 1;          // replays of the command list per interactive render() (1 in the reference)
+    RaytracingProperties properties;
+    String lastExport;              // path written by the last export ("" when it failed)
 
     RaytracingInterface(Device& d, SceneGraph* sg) : device(d), sceneGraph(sg), compositeTask(d) {
         camera.flags = CameraFlags::NONE;   // headless: no UI blend (the export path clears USE_UI the same way, raytracing_interface.cpp:203-204)
@@ -658,8 +676,38 @@ public:
         for (auto* p : postPasses) p->update(dt);
     }
 
-    // re-record when a task is dirty, then replay `targetSamples` times (progressive accumulation when > 1)
+    // re-record when a task is dirty, then replay `targetSamples` times (progressive accumulation when > 1).
+    // With properties.shouldOutputNextFrame set, first renders the export frame the way the reference does
+    // (raytracing_interface.cpp:196-242): resize to the target size, no UI, USE_SUPERSAMPLING when more than one sample,
+    // update(0), the command list replayed targetSamples times (each replay K0 advances the sample counter and the
+    // composite pass accumulates), read the rgba8 frame back, write <targetOutput>.png, restore size and flags.
     void render() {
+        if (properties.shouldOutputNextFrame) exportFrame();
+        renderOnce(targetSamples ? targetSamples : 1);
+    }
+
+    bool exportFrame() {
+        const Vec2u32 oldRes = res;
+        const CameraFlags oldFlags = camera.flags;
+        resize(properties.getRes());
+        u32 flags = u32(camera.flags) & ~u32(CameraFlags::USE_UI);
+        if (properties.targetSamples > 1) flags |= u32(CameraFlags::USE_SUPERSAMPLING);
+        camera.flags = CameraFlags(flags);
+        update(0);
+        renderOnce(properties.targetSamples ? properties.targetSamples : 1);
+        List<u32> px;
+        bool ok = readPixels(px);
+        lastExport = properties.targetOutput + ".png";
+        if (ok) ok = rtb_write_png(lastExport.c_str(), res.x, res.y, px.data(), 1) == 0;
+        if (!ok) { lastExport.clear(); note(RTB_ERR_ARG); }
+        camera.flags = oldFlags;
+        properties.shouldOutputNextFrame = false;
+        if (oldRes.x && oldRes.y) { resize(oldRes); update(0); }
+        return ok;
+    }
+
+private:
+    void renderOnce(u32 replays) {
         bool record = cl.empty() || compositeTask.needsCommandUpdate();
         for (auto* p : prePasses) record |= p->needsCommandUpdate();
         for (auto* p : postPasses) record |= p->needsCommandUpdate();
@@ -672,8 +720,9 @@ public:
             compositeTask.prepareCommandList(&cl);
             for (auto* p : postPasses) p->prepareCommandList(&cl);
         }
-        for (u32 i = 0; i < (targetSamples ? targetSamples : 1); ++i) note(cl.execute(device.get()));
+        for (u32 i = 0; i < replays; ++i) note(cl.execute(device.get()));
     }
+public:
 
     // presentToCpu: the rgba8 frame, row 0 first (which is the bottom of the view)
     bool readPixels(List<u32>& out) {

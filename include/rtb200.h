@@ -110,7 +110,7 @@ typedef struct rtb_counters {
     uint64_t primary_rays, shadow_rays;          /* rays handed to the nearest-hit / occlusion search */
     uint64_t primary_nodes, primary_tris;        /* node records fetched, triangle records tested */
     uint64_t shadow_nodes, shadow_tris;
-    uint64_t primary_hits, shadow_occluded;
+    uint64_t primary_hits, shadow_occluded;      /* pixels whose nearest hit is any primitive; shadow rays found occluded by a triangle */
 } rtb_counters;
 
 typedef enum rtb_option {
@@ -179,6 +179,10 @@ int  rtb_counters_get(rtb_ctx* ctx, rtb_counters* out);
 /* milliseconds spent in each phase of the last RTB_PASS_FRAME (CUDA events on the context's stream): init, ray generation,
  * nearest-hit traversal, G-buffer finish, shadow-ray set-up, occlusion traversal, lighting+composite, total.  Synchronises. */
 int  rtb_last_frame_ms(rtb_ctx* ctx, float out_ms[8]);
+
+/* Measurement aid, not on the hot path: read-only streaming bandwidth (1e9 B/s) over a buffer of `bytes` (choose <= 64 MiB so
+ * that it stays L2-resident) with L2-only cached loads — the denominator of the L2 roofline. */
+int  rtb_probe_l2_read_gbs(rtb_ctx* ctx, size_t bytes, double* out_gbs);
 
 /* ---- rays-in mode (parity harness: same traversal, explicit rays) --------------------------------- */
 /* rays: n * 6 floats (origin, dir) in HOST memory; prev: n object ids to exclude or NULL (= none).

@@ -78,6 +78,23 @@ int main(int argc, char** argv) {
     CHECK(std::fabs(cam.p1.x - 5.7777777f) < 1e-6f && cam.p2.y == 1.0f);
     CHECK(cam.tiles.x == 40 && cam.tiles.y == 22);
 
+    // export settings: presets and portrait mode (include/rt/raytracing_interface.hpp:20-91)
+    RaytracingProperties props;
+    CHECK(props.getRes().x == 7680 && props.getRes().y == 4320 && props.targetSamples == 128 && !props.shouldOutputNextFrame);
+    props.setResolution(Resolution::QHD); props.isPortrait = true;
+    CHECK(props.getRes().x == 1440 && props.getRes().y == 2560);
+    props.setResolution(Resolution::CUSTOM);
+    CHECK(props.targetSizeX == 2560);   // CUSTOM keeps the size as it is
+    props.exportToPNG();
+    CHECK(props.shouldOutputNextFrame);
+    // PNG writer, host-only: 3x2 frame, flipped on write like the reference's stb call
+    {
+        const u32 img[6] = {0xFF0000FFu, 0xFF00FF00u, 0xFFFF0000u, 0x80FFFFFFu, 0x00000000u, 0x7F102030u};
+        const char* pngPath = argc > 5 ? argv[5] : "/tmp/rtb_scene_graph_check.png";
+        CHECK(rtb_write_png(pngPath, 3, 2, img, 1) == 0);
+        CHECK(rtb_write_png("/nonexistent-dir/x.png", 3, 2, img, 1) != 0);
+    }
+
     if (!render) {
         CHECK(!dev.valid());                       // no GPU here: creation fails loudly, nothing falls back
         CHECK(sg.error() != 0);
@@ -128,5 +145,18 @@ int main(int argc, char** argv) {
     f = argc > 3 ? std::fopen(argv[3], "wb") : nullptr;
     if (f) { std::fwrite(px.data(), 4, px.size(), f); std::fclose(f); }
     std::printf("OK refit frame\n");
+    // export path: RaytracingProperties::exportToPNG() arms the next render(): SD preset, 4 accumulated samples
+    if (argc > 4) {
+        rti.properties.targetOutput = argv[4];
+        rti.properties.setResolution(Resolution::SD);
+        rti.properties.targetSamples = 4;
+        rti.properties.exportToPNG();
+        rti.render();
+        CHECK(rti.error() == 0);
+        CHECK(!rti.properties.shouldOutputNextFrame);
+        CHECK(rti.lastExport == String(argv[4]) + ".png");
+        CHECK(rti.readPixels(px) && px.size() == 640u * 360u);   // the interactive size is back
+        std::printf("OK export %s\n", rti.lastExport.c_str());
+    }
     return 0;
 }

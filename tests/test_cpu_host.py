@@ -228,3 +228,27 @@ def test_crmath_matches_binary64_libm(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "crmath_check.cpp"), "-o", exe])
     r = subprocess.run([exe, "37"], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stdout
+
+
+@pytest.mark.parametrize("stored", [False, True])
+def test_png_export_roundtrip(rtb, tmp_path, monkeypatch, stored):
+    """rtb_write_png (the export step after the hot path, ref: igxi convert.cpp:747-781): 8-bit RGBA, rows flipped on write.
+    Both encodings (libz looked up at run time / stored deflate blocks) decode to the same pixels."""
+    from PIL import Image
+    if stored:
+        monkeypatch.setenv("RTB_PNG_STORED", "1")
+    rng = np.random.default_rng(1)
+    frame = rng.integers(0, 2**32, (37, 53), dtype=np.uint32)
+    frame[:8] = 0xFF336699          # compressible rows too
+    path = tmp_path / "f.png"
+    rtb.write_png(path, frame)
+    im = np.array(Image.open(path))
+    assert im.shape == (37, 53, 4)
+    assert np.array_equal(im, frame.view(np.uint8).reshape(37, 53, 4)[::-1])
+    rtb.write_png(path, frame, flip_vertically=False)
+    assert np.array_equal(np.array(Image.open(path)), frame.view(np.uint8).reshape(37, 53, 4))
+    big = np.full((300, 400), 0xFF102030, np.uint32)   # > 65535 bytes: several stored blocks
+    rtb.write_png(path, big)
+    assert np.array_equal(np.array(Image.open(path)).view(np.uint32)[..., 0], big)
+    size = os.path.getsize(path)
+    assert (size > big.nbytes) == stored

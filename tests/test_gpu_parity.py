@@ -377,9 +377,9 @@ def test_cpp_facade_renders_like_the_oracle(rtb, oracle, tmp_path):
     libdir = os.path.dirname(rtb.LIB_PATH)
     subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-ffp-contract=off", "-I", os.path.join(root, "include"),
                     os.path.join(root, "tests", "cpp", "scene_graph_check.cpp"), "-L", libdir, "-lrtb200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
-    out, out3 = str(tmp_path / "frame.bin"), str(tmp_path / "frame3.bin")
-    r = subprocess.run([exe, "render", out, out3], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert r.returncode == 0 and "OK render" in r.stdout and "OK refit frame" in r.stdout, r.stdout
+    out, out3, exp = str(tmp_path / "frame.bin"), str(tmp_path / "frame3.bin"), str(tmp_path / "export0")
+    r = subprocess.run([exe, "render", out, out3, exp, str(tmp_path / "tiny.png")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "OK render" in r.stdout and "OK refit frame" in r.stdout and "OK export" in r.stdout, r.stdout
     got = np.fromfile(out, np.uint32).reshape(360, 640)
     scene = rtb.niels_scene(0.0)
     sph = scene["spheres"].view(np.float32).reshape(7, 4).copy()
@@ -397,6 +397,19 @@ def test_cpp_facade_renders_like_the_oracle(rtb, oracle, tmp_path):
     d3 = np.abs(got3.view(np.uint8).astype(np.int32) - ref3["rgba8"].view(np.uint8).reshape(-1).astype(np.int32).reshape(got3.view(np.uint8).shape))
     assert int((d3 > 1).sum()) <= 4 and int((d3 > 0).sum()) <= 64, f"{int((d3 > 0).sum())} channel values differ after the refit"
     assert int((got3 != got).sum()) > 500, "the moved triangle must change the picture"
+    # export: SD preset (720x480), 4 accumulated samples, written as <targetOutput>.png with the rows flipped
+    from PIL import Image
+    png = np.array(Image.open(exp + ".png"))
+    assert png.shape == (480, 720, 4)
+    ocam = oracle.camera(720, 480, eye=(6, 5, 12), flags=2)
+    oseed = oracle.seed((0.0, 0.0))
+    accum = np.zeros((480, 720, 4), np.float32)
+    osc = to_oracle_scene(scene)
+    for _ in range(4):
+        ref4 = oracle.frame(osc, ocam, oseed, 1, accum=accum)
+    want = ref4["rgba8"].view(np.uint8).reshape(480, 720, 4)[::-1]
+    dp = np.abs(png.astype(np.int32) - want.astype(np.int32))
+    assert int((dp > 1).sum()) <= 16 and int((dp > 0).sum()) <= 400, f"{int((dp > 0).sum())} channel values of the exported PNG differ"
 
 
 def test_refit_unmoved_reproduces_the_build(rtb):
