@@ -22,6 +22,9 @@ constexpr int PACKET_STACK = 64;   // node groups only (no postponed triangle gr
 #ifndef RTB_PK_MINBLOCKS
 #define RTB_PK_MINBLOCKS 3
 #endif
+#ifndef RTB_PK_PERM_LUT
+#define RTB_PK_PERM_LUT 1
+#endif
 
 // Measured on B200 (1M-triangle soup, 3840x2160, profiles/r1g_*): 3 blocks/SM at 77 registers 3.88 ms; forcing 4 blocks
 // (64 registers) 4.16 ms; requesting the hit children and triangles early (LDGSTS prefetch into L1) 4.11 ms.  The kernel
@@ -30,6 +33,18 @@ constexpr int PACKET_STACK = 64;   // node groups only (no postponed triangle gr
 template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS, RTB_PK_MINBLOCKS) k_trace_cwbvh_packet(const TraceArgs a) {
     __shared__ uint2 sStack[TRACE_THREADS / 32][PACKET_STACK];
+#if RTB_PK_PERM_LUT
+    // hit-mask bits from slot order to traversal order (bit s -> bit s ^ octant) as one shared-memory byte load instead of
+    // three conditional swap stages: 8 octants x 256 masks
+    __shared__ uint8_t sPerm[8][256];
+    for (uint32_t i = threadIdx.x; i < 2048u; i += TRACE_THREADS) {
+        const uint32_t o = i >> 8, m = i & 255u;
+        uint32_t r = 0;
+        for (uint32_t b = 0; b < 8u; ++b) r |= ((m >> b) & 1u) << (b ^ o);
+        sPerm[o][m] = (uint8_t)r;
+    }
+    __syncthreads();
+#endif
     const unsigned lane = threadIdx.x & 31u;
     uint2* stack = sStack[threadIdx.x >> 5];
     unsigned long long cRays = 0, cNodes = 0, cTris = 0, cHits = 0;
@@ -61,6 +76,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_PK_MINBLOCKS) k_trace_cwbvh
             const uint32_t negX = ~octinv & 1u, negY = ~octinv & 2u, negZ = ~octinv & 4u;   // per lane: near / far of its own ray
             const uint32_t woct = __shfl_sync(0xFFFFFFFFu, octinv, __ffs(liveMask) - 1);    // per warp: child order
             if (COUNT && live) cRays++;
+#if RTB_PK_PERM_LUT
+            const uint8_t* permRow = sPerm[woct];
+#endif
 
             int sp = 0;
             uint2 G = make_uint2(0u, 0x80000000u);   // the root as a one-node group
@@ -92,10 +110,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_PK_MINBLOCKS) k_trace_cwbvh
                 testPair<4>(wnx.z, wny.z, wnz.z, wfx.z, wfy.z, wfz.z, kx, ky, kz, cx, cy, cz, best, hitmask);
                 testPair<6>(wnx.w, wny.w, wnz.w, wfx.w, wfy.w, wfz.w, kx, ky, kz, cx, cy, cz, best, hitmask);
                 const uint32_t any = __reduce_or_sync(0xFFFFFFFFu, hitmask) & n1.z;   // valid: imask << 24 | triangle presence
+#if RTB_PK_PERM_LUT
+                const uint32_t top = permRow[any >> 24];
+#else
                 uint32_t top = any >> 24;
                 if (woct & 1u) top = ((top & 0x55u) << 1) | ((top >> 1) & 0x55u);
                 if (woct & 2u) top = ((top & 0x33u) << 2) | ((top >> 2) & 0x33u);
                 if (woct & 4u) top = ((top & 0x0Fu) << 4) | (top >> 4);
+#endif
                 const uint32_t P = n1.z & 0x00FFFFFFu;
                 uint32_t T = any & 0x00FFFFFFu;
 
