@@ -190,7 +190,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="soup1m", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--packets", default="auto", choices=["off", "on", "auto"],
+    ap.add_argument("--packets", default="auto", choices=["off", "union", "frustum", "auto"],
                     help="camera rays as 8x4-pixel packets (RTB_OPT_PRIMARY_PACKETS); auto = the library's patch-size rule")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -230,7 +230,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     ctx.set_option(rtb.OPT_TILE_COUNT, world)
     ctx.set_option(rtb.OPT_TILE_RANK, rank)
-    ctx.set_option(rtb.OPT_PRIMARY_PACKETS, {"off": 0, "on": 1, "auto": 2}[args.packets])
+    ctx.set_option(rtb.OPT_PRIMARY_PACKETS, {"off": 0, "union": 1, "auto": 2, "frustum": 3}[args.packets])
     ctx.resize(w, h, samples)
     ctx.upload_scene(scene, None)
     ctx.build_accel(rtb.ACCEL_BVH)
@@ -376,7 +376,8 @@ def main():
         return r
 
     if info.primary_packets:
-        roofline = roof("k_trace_cwbvh_packet (nearest-hit launch: one warp-cooperative traversal per 8x4-pixel patch)", bytes_primary, t_primary, "k_trace_cwbvh_packet")
+        kname = "k_trace_cwbvh_frustum" if info.primary_packets == 3 else "k_trace_cwbvh_packet"
+        roofline = roof(kname + " (nearest-hit launch: one warp-cooperative traversal per 8x4-pixel patch)", bytes_primary, t_primary, kname)
         roofline["fetched_bytes_per_launch_rank0"] = cf.primary_nodes * info.node_bytes + cf.primary_tris * info.tri_record_bytes
     else:
         roofline = roof("k_trace_cwbvh<MODE_CLOSEST> (nearest-hit launch, the dominant kernel)", bytes_primary, t_primary, "k_trace_cwbvh<0,0>")
@@ -405,7 +406,7 @@ def main():
                    "partition": f"{world} ranks x interleaved 32x32-pixel blocks, scene+BVH replicated, NCCL gather of rgba8 tiles to rank 0" if world > 1 else "single GPU",
                    "bvh": {"nodes": info.node_count, "node_bytes": info.node_bytes, "leaves": info.leaf_count, "depth": info.max_depth,
                            "sah_cost": info.sah_cost, "build_ms": info.build_ms, "leaf_node_extent": info.leaf_node_extent},
-                   "primary_packets": bool(info.primary_packets), "packets_option": args.packets,
+                   "primary_packets": {0: "per ray", 1: "union packets", 3: "frustum packets"}.get(info.primary_packets, str(info.primary_packets)), "packets_option": args.packets,
                    "phase_ms_rank0": {k: float(v) for k, v in zip(["init", "raygen", "trace_primary", "finish", "shadowgen", "trace_shadow", "shade", "total"], phases)}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 168 * world, "d2h_bytes_per_step": w * h * 4,

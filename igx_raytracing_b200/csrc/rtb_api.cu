@@ -68,8 +68,8 @@ struct rtb_ctx {
     DevBuf<TraceCounters> counters;   // [0] primary, [1] shadow
     bool countersOn = false;
     uint32_t countersMode = 0;        // 1: per-ray algorithmic counts (per-lane kernel); 2: what the kernels in use fetch
-    uint32_t packetsOpt = 2;          // RTB_OPT_PRIMARY_PACKETS: 0 off, 1 on, 2 auto
-    bool lastPrimaryPackets = false;
+    uint32_t packetsOpt = 2;          // RTB_OPT_PRIMARY_PACKETS: 0 off, 1 union packets, 2 auto, 3 frustum packets
+    int lastPrimaryPackets = 0;       // PACKETS_* of the last camera-ray launch
 
     // rays-in scratch
     DevBuf<RayRec> rinRays; DevBuf<TriHit> rinHits; DevBuf<uint32_t> rinObj; DevBuf<float> rinT; DevBuf<float2> rinUv; DevBuf<uint8_t> rinOcc, rinOcc2;
@@ -146,12 +146,12 @@ int checkReady(rtb_ctx* c) {
 // below PACKET_RATIO leaf-node edges.  Above that the union of the nodes the 32 rays need grows faster than the
 // shared fetches save (measured on the 1M-triangle soup from two distances and on the 10M-triangle height field).
 constexpr float PACKET_RATIO = 1.0f;
-bool primaryPackets(const rtb_ctx* c) {
-    if (c->accelMode != RTB_ACCEL_BVH || !c->accelValid || !c->info.triangleCount) return false;
-    if (c->countersOn && c->countersMode == 1) return false;
-    if (c->packetsOpt != 2) return c->packetsOpt == 1;
+int primaryPackets(const rtb_ctx* c) {
+    if (c->accelMode != RTB_ACCEL_BVH || !c->accelValid || !c->info.triangleCount) return PACKETS_OFF;
+    if (c->countersOn && c->countersMode == 1) return PACKETS_OFF;
+    if (c->packetsOpt != 2) return (int)c->packetsOpt;
     const CameraRec& cam = c->camera;
-    if (cam.projectionType != 0 || !cam.width) return false;
+    if (cam.projectionType != 0 || !cam.width) return PACKETS_OFF;   // the frustum kernel wants one origin per packet
     float ctr[3], e2c = 0.0f, rad = 0.0f, pw = 0.0f, pd = 0.0f;
     for (int a = 0; a < 3; ++a) {
         ctr[a] = 0.5f * (c->stats.lo[a] + c->stats.hi[a]);
@@ -163,7 +163,7 @@ bool primaryPackets(const rtb_ctx* c) {
     }
     const float dist = std::max(std::sqrt(e2c), 0.5f * std::sqrt(rad));
     const float patch = 8.0f * std::sqrt(pw) / (float)cam.width / std::max(std::sqrt(pd), 1e-20f) * dist;
-    return patch < PACKET_RATIO * c->stats.leafNodeExtent;
+    return patch < PACKET_RATIO * c->stats.leafNodeExtent ? PACKETS_FRUSTUM : PACKETS_OFF;
 }
 
 // `mark` (frame dispatch only) records an event after each phase so the traversal launches can be timed alone
@@ -256,7 +256,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
     switch (opt) {
         case RTB_OPT_COUNTERS: c->countersOn = value != 0; c->countersMode = value; return RTB_OK;
         case RTB_OPT_PRIMARY_PACKETS:
-            if (value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_PRIMARY_PACKETS: 0 off, 1 on, 2 auto");
+            if (value > 3) return fail(c, RTB_ERR_ARG, "RTB_OPT_PRIMARY_PACKETS: 0 off, 1 union packets, 2 auto, 3 frustum packets");
             c->packetsOpt = value; return RTB_OK;
         case RTB_OPT_TILE_RANK:
             c->tileRank = value;
@@ -402,7 +402,7 @@ int rtb_accel_info_get(const rtb_ctx* c, rtb_accel_info* out) {
     if (!c || !out) return RTB_ERR_ARG;
     out->mode = c->accelMode; out->node_count = c->nodeCount; out->node_bytes = c->accelMode == RTB_ACCEL_BVH ? sizeof(Node8) : sizeof(BvhNode); out->leaf_count = c->stats.leafCount;
     out->max_depth = c->stats.maxDepth; out->tri_record_bytes = sizeof(TravTri); out->sah_cost = c->stats.sahCost; out->build_ms = c->stats.buildMs;
-    out->leaf_node_extent = c->stats.leafNodeExtent; out->refits = c->refits; out->primary_packets = c->lastPrimaryPackets ? 1u : 0u;
+    out->leaf_node_extent = c->stats.leafNodeExtent; out->refits = c->refits; out->primary_packets = (uint32_t)c->lastPrimaryPackets;
     return RTB_OK;
 }
 
@@ -548,7 +548,7 @@ int rtb_trace_rays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* pr
     if (rc) return rc;
     RTB_CUDA(c, c->rinHits.alloc((size_t)n)); RTB_CUDA(c, c->rinObj.alloc((size_t)n)); RTB_CUDA(c, c->rinT.alloc((size_t)n)); RTB_CUDA(c, c->rinUv.alloc((size_t)n));
     const SceneView sv = sceneView(c);
-    launch_trace_closest(sv, c->rinRays.p, (uint32_t)n, c->rinHits.p, c->workCounter.p, nullptr, c->packetsOpt == 1, c->stream);
+    launch_trace_closest(sv, c->rinRays.p, (uint32_t)n, c->rinHits.p, c->workCounter.p, nullptr, c->packetsOpt == 2 ? PACKETS_OFF : (int)c->packetsOpt, c->stream);
     launch_finish_rays(sv, c->rinRays.p, c->rinHits.p, (uint32_t)n, c->rinObj.p, c->rinT.p, c->rinUv.p, c->stream);
     RTB_CUDA(c, cudaGetLastError());
     if (object) RTB_CUDA(c, cudaMemcpyAsync(object, c->rinObj.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));

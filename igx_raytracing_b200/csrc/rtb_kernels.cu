@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) 
 }  // namespace rtb
 #include "rtb_trace8.cuh"
 #include "rtb_trace8p.cuh"
+#include "rtb_trace8f.cuh"
 namespace rtb {
 
 // persistent grid: one resident wave (SM count x blocks that fit per SM), fewer when the wavefront is small
@@ -272,10 +273,10 @@ static void launchTrace(const SceneView& sv, const TraceArgs& a, bool count, cud
 }
 int trace_grid_blocks() { return g_traceBlocks; }
 
-template <bool COUNT>
+template <bool COUNT, bool FRUSTUM>
 static void launchPacket(const TraceArgs& a, cudaStream_t st) {
     static int blocks = 0;
-    auto kernel = k_trace_cwbvh_packet<COUNT>;
+    auto kernel = FRUSTUM ? k_trace_cwbvh_frustum<COUNT> : k_trace_cwbvh_packet<COUNT>;
     if (!blocks) {
         int dev = 0, sms = 0, perSm = 0;
         cudaGetDevice(&dev);
@@ -357,13 +358,14 @@ static TraceArgs makeArgs(const SceneView& sv, const RayRec* rays, uint32_t n, u
 }
 
 void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
-                          TraceCounters* counters, bool packets, cudaStream_t st) {
+                          TraceCounters* counters, int packets, cudaStream_t st) {
     if (!n) return;
     if (sv.info.triangleCount == 0) { k_fill_miss<<<(n + 255) / 256, 256, 0, st>>>(hits, n); return; }
     if (sv.useBvh == ACCEL_KIND_CWBVH && packets) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
         a.hits = hits;
-        if (counters) launchPacket<true>(a, st); else launchPacket<false>(a, st);
+        if (packets == PACKETS_FRUSTUM) { if (counters) launchPacket<true, true>(a, st); else launchPacket<false, true>(a, st); }
+        else { if (counters) launchPacket<true, false>(a, st); else launchPacket<false, false>(a, st); }
     } else if (sv.useBvh) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
         a.hits = hits;

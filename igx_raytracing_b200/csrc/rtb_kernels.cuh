@@ -29,10 +29,13 @@ struct TraceCounters { unsigned long long rays, nodes, tris, hits; };
 
 void launch_init(SeedRec* seed, cudaStream_t s);
 void launch_raygen(const FrameMap& fm, const CameraRec* cam, const SeedRec* seed, RayRec* rays, cudaStream_t s);
-// nearest triangle for every ray slot (BVH or brute force according to sv.useBvh).  packets: 32 consecutive slots are a
-// coherent patch and the 8-wide tree is walked once per warp (rtb_trace8p.cuh); otherwise one traversal per lane.
+// nearest triangle for every ray slot (BVH or brute force according to sv.useBvh).  packets != PACKETS_OFF: 32 consecutive
+// slots are a coherent patch and the 8-wide tree is walked once per warp — every lane testing every child box
+// (PACKETS_UNION, rtb_trace8p.cuh) or one lane testing one child box against one quadrant's interval ray
+// (PACKETS_FRUSTUM, rtb_trace8f.cuh); otherwise one traversal per lane.
+enum { PACKETS_OFF = 0, PACKETS_UNION = 1, PACKETS_FRUSTUM = 3 };
 void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
-                          TraceCounters* counters, bool packets, cudaStream_t s);
+                          TraceCounters* counters, int packets, cudaStream_t s);
 // spheres, cubes, planes after the triangles, normal interpolation, G-buffer stores (raygen.comp:39-51)
 void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits,
                            float4* dirT, float4* uvN, cudaStream_t s);

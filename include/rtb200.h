@@ -101,7 +101,7 @@ typedef struct rtb_accel_info {
     float    build_ms;        /* host wall clock of the last build */
     float    leaf_node_extent;/* 8-wide tree: mean edge length of the nodes that hold only triangles (world units) */
     uint32_t refits;          /* rtb_refit_accel calls served by a device refit since the last host build */
-    uint32_t primary_packets; /* 1 when the last RAYGEN / FRAME dispatch walked the camera rays as 8x4-pixel packets */
+    uint32_t primary_packets; /* how the last RAYGEN / FRAME dispatch walked the camera rays: 0 per ray, 1 union packets, 3 frustum packets */
 } rtb_accel_info;
 
 /* Counters of the last instrumented dispatch (rtb_set_option(RTB_OPT_COUNTERS, 1)); the timed build
@@ -121,10 +121,15 @@ typedef enum rtb_option {
     RTB_OPT_TILE_COUNT = 2,
     RTB_OPT_SKIP_PARITY_STORES = 3,/* 0/1: RELEASE-shader behaviour (no uvObjectNormal/lighting store on misses) is NOT
                                       modelled; reserved, must be 0 */
-    RTB_OPT_PRIMARY_PACKETS = 4    /* nearest-hit search of the camera rays with RTB_ACCEL_BVH: 0 = one traversal per ray,
-                                      1 = one warp-cooperative traversal per 8x4 pixel patch, 2 = choose from the patch
-                                      size against the tree's leaf nodes (default).  Same hits either way.  With 1 the
-                                      rays-in call rtb_trace_rays also walks its rays in packets of 32 consecutive rays. */
+    RTB_OPT_PRIMARY_PACKETS = 4    /* nearest-hit search of the camera rays with RTB_ACCEL_BVH.  0 = one traversal per ray.
+                                      1 = one warp-cooperative traversal per 8x4-pixel patch, every ray testing every
+                                      child box of the union ("union packets").  3 = the same walk with the box tests
+                                      done once per packet against the interval rays of the patch's four quadrants
+                                      ("frustum packets"; meant for rays sharing one origin — other packets are still
+                                      answered exactly, only slowly).  2 = default: frustum packets when the projection
+                                      is Default and the patch is small against the tree's leaf nodes, else per ray.
+                                      The hits are identical in every mode.  With 1 or 3 the rays-in call rtb_trace_rays
+                                      also walks its rays in packets of 32 consecutive rays. */
 } rtb_option;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

@@ -248,7 +248,7 @@ def test_soup_full_size_bvh_equals_brute(rtb):
     for mode in (rtb.ACCEL_BVH, rtb.ACCEL_BVH2, rtb.ACCEL_BRUTE):
         ctx = make_ctx(rtb, scene, None, w, h, 1, mode, max_triangles=n_tri)
         ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 13.9)))
-        for packets in ((0, 1) if mode == rtb.ACCEL_BVH else (2,)):   # camera rays one by one / as 8x4-pixel packets
+        for packets in ((0, 1, 3) if mode == rtb.ACCEL_BVH else (2,)):   # camera rays one by one / union packets / frustum packets
             ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
             ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
             ctx.dispatch(rtb.PASS_FRAME)
@@ -259,25 +259,27 @@ def test_soup_full_size_bvh_equals_brute(rtb):
                 assert mode != rtb.ACCEL_BVH or info.primary_packets == packets
         ctx.close()
     n = w * h
-    for key in ((rtb.ACCEL_BVH, 0), (rtb.ACCEL_BVH, 1), (rtb.ACCEL_BVH2, 2)):
+    for key in ((rtb.ACCEL_BVH, 0), (rtb.ACCEL_BVH, 1), (rtb.ACCEL_BVH, 3), (rtb.ACCEL_BVH2, 2)):
         compare_frames(out[key], out[rtb.ACCEL_BRUTE, 2], n)
-    # the two 8-wide kernels run the same triangle arithmetic with the same tie rule: identical, not just close
-    for a, b in zip(out[rtb.ACCEL_BVH, 0], out[rtb.ACCEL_BVH, 1]):
-        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # the three 8-wide kernels run the same triangle arithmetic with the same tie rule: identical, not just close
+    for pk in (1, 3):
+        for a, b in zip(out[rtb.ACCEL_BVH, 0], out[rtb.ACCEL_BVH, pk]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+@pytest.mark.parametrize("packets", [1, 3])
 @pytest.mark.parametrize("pose", ["all_objects", "inside_cube"])
-def test_niels_frame_packets(rtb, oracle, sky, pose):
+def test_niels_frame_packets(rtb, oracle, sky, pose, packets):
     """NielsScene through the packet kernel (forced on: the auto rule would pick it anyway for three large triangles)."""
     w, h = 333, 127
     scene = rtb.niels_scene(0.0)
     ctx = make_ctx(rtb, scene, sky, w, h, 1, rtb.ACCEL_BVH)
-    ctx.set_option(rtb.OPT_PRIMARY_PACKETS, 1)
+    ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
     cam = rtb.pack_camera(w, h, **POSES[pose])
     ctx.upload(rtb.BUF_CAMERA, cam)
     ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
     ctx.dispatch(rtb.PASS_FRAME)
-    assert ctx.accel_info().primary_packets == 1
+    assert ctx.accel_info().primary_packets == packets
     got = dict(dirT=ctx.readback(rtb.TGT_DIR_T), uvN=ctx.readback(rtb.TGT_UV_NORMAL), bits=ctx.readback(rtb.TGT_SHADOW_BITS),
                lighting=ctx.readback(rtb.TGT_LIGHTING), rgba8=ctx.readback(rtb.TGT_RGBA8), accum=ctx.readback(rtb.TGT_ACCUM),
                seed=ctx.readback(rtb.TGT_SEED))
@@ -300,12 +302,13 @@ def test_soup_rays_in_packets(rtb, oracle):
     rays = np.concatenate([o, d], axis=1).astype(np.float32)
     ctx = make_ctx(rtb, scene, None, 64, 64, 1, rtb.ACCEL_BVH, max_triangles=n_tri)
     res = {}
-    for packets in (0, 1):
+    for packets in (0, 1, 3):   # 3: the packets share no origin, every axis is left unconstrained — slow, still exact
         ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
         res[packets] = ctx.trace_rays(rays)
     ctx.close()
-    for a, b in zip(res[0], res[1]):
-        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for pk in (1, 3):
+        for a, b in zip(res[0], res[pk]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     obj, t, uv, nrm, flags = oracle.trace_rays(to_oracle_scene(scene), rays, want_flags=True)
     ok = flags == 0
     assert np.array_equal(res[1][0][ok], obj[ok])
@@ -427,7 +430,7 @@ def test_refit_unmoved_reproduces_the_build(rtb):
     ctx.close()
 
 
-@pytest.mark.parametrize("packets", [0, 1])
+@pytest.mark.parametrize("packets", [0, 1, 3])
 def test_refit_after_motion_equals_brute(rtb, packets):
     """Triangles move (a dirty-range upload, as SceneGraph::update does), the tree is refitted on the device, and the
     nearest hits / shadow bits / pixels equal the reference's linear loop over the moved triangles."""
@@ -479,7 +482,7 @@ def mesh_scene(rtb, grid, seed=0xB200):
                 info=np.array([1, 1, n, 0, 0, 0, 1, 0, 0], np.uint32)), n
 
 
-@pytest.mark.parametrize("packets", [0, 1])
+@pytest.mark.parametrize("packets", [0, 1, 3])
 def test_heightfield_frame_vs_oracle(rtb, oracle, sky, packets):
     """BASELINE config 4 geometry at oracle size: a connected mesh with smooth vertex normals (the 6-argument Triangle
     constructor, interpolated un-normalised as SH/trace.glsl:52-60 does).  Shared edges are where tie-breaking shows: a ray
@@ -526,13 +529,36 @@ def test_heightfield_full_size_bvh_equals_brute(rtb):
     for mode in (rtb.ACCEL_BVH, rtb.ACCEL_BRUTE):
         ctx = make_ctx(rtb, scene, None, w, h, 1, mode, max_triangles=n_tri)
         ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0.0, 4.0, 9.0), pitch=0.3))
-        for packets in ((0, 1) if mode == rtb.ACCEL_BVH else (2,)):
+        for packets in ((0, 1, 3) if mode == rtb.ACCEL_BVH else (2,)):
             ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
             ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
             ctx.dispatch(rtb.PASS_FRAME)
             out[mode, packets] = (ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8))
         ctx.close()
-    for a, b in zip(out[rtb.ACCEL_BVH, 0], out[rtb.ACCEL_BVH, 1]):
-        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for pk in (1, 3):
+        for a, b in zip(out[rtb.ACCEL_BVH, 0], out[rtb.ACCEL_BVH, pk]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     # a connected mesh: rays through shared edges / vertices are exact ties, resolved by index in both searches
     compare_frames(out[rtb.ACCEL_BVH, 1], out[rtb.ACCEL_BRUTE, 2], w * h)
+
+
+def test_packets_identical_at_full_4k(rtb):
+    """The headline frame itself (1M-triangle soup, 3840x2160): per-ray, union-packet and frustum-packet searches return
+    the same 8.3 M hit records and the same pixels, bit for bit."""
+    n_tri, w, h = 1_000_000, 3840, 2160
+    scene = soup_scene(rtb, n_tri)
+    ctx = make_ctx(rtb, scene, None, w, h, 1, rtb.ACCEL_BVH, max_triangles=n_tri)
+    ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 13.9)))
+    out = {}
+    for packets in (0, 1, 3, 2):
+        ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+        ctx.dispatch(rtb.PASS_FRAME)
+        out[packets] = (ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_UV_NORMAL), ctx.readback(rtb.TGT_RGBA8))
+        if packets == 2:
+            assert ctx.accel_info().primary_packets == 3, "the auto rule takes frustum packets on this frame"
+    ctx.close()
+    assert (out[0][0][..., 3].view(np.uint32) != NO_RAY_HIT).mean() > 0.4
+    for pk in (1, 3, 2):
+        for a, b in zip(out[0], out[pk]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
