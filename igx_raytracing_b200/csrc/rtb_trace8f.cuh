@@ -30,6 +30,125 @@ namespace rtb {
 #define RTB_FR_MINBLOCKS 4
 #endif
 
+// Per-lane description of the quadrant's interval ray, in the form each of the two walks wants it.
+struct QuadPlain {      // every axis has a sign: mirrored so that the quadrant travels towards +
+    float sgx, sgy, sgz;          // +-1
+    uint32_t smx, smy, smz;       // the same sign as a bit mask for the grid step 2^e
+    float mox, moy, moz;          // -origin * sgn
+    float alx, ahx, aly, ahy, alz, ahz;   // reciprocal interval of |d|, widened: 0 < al <= ah
+};
+struct QuadGeneric {    // some axis straddles zero, or the packet has several origins
+    float lox, hix, loy, hiy, loz, hiz;   // direction interval of the quadrant
+    float fox, foy, foz;
+    bool oneOrigin;
+};
+
+// One packet through the tree.  PLAIN selects the box test; everything else is shared.
+template <bool COUNT, bool PLAIN>
+RTB_DI void walkFrustumPacket(const TraceArgs& a, uint2* stack, const uint8_t* permRow, const uint32_t* sSpread, uint32_t woct, uint32_t bitC,
+                              uint32_t planeOff, uint32_t halfSel, bool live, float ox, float oy, float oz, float dx, float dy, float dz, uint32_t prev,
+                              const QuadPlain& qp, const QuadGeneric& qg, float& best, uint32_t& bestId, float& bu, float& bv,
+                              unsigned long long& cNodes, unsigned long long& cTris, unsigned lane) {
+    const float INF = __int_as_float(0x7F800000);
+    uint32_t limitBits = __reduce_max_sync(0xFFFFFFFFu, live ? fbits(best) : 0u);   // largest nearest-hit distance in the packet
+    int sp = 0;
+    uint2 G = make_uint2(0u, 0x80000000u);   // the root as a one-node group
+    for (;;) {
+        // ---- one node for the warp --------------------------------------------------------------------------------
+        const uint32_t hits = G.y;
+        const uint32_t bit = 31u - (uint32_t)__clz(hits);
+        const uint32_t childSlot = (bit - 24u) ^ woct;
+        const uint32_t nodeIdx = G.x + (uint32_t)__popc(hits & 0xFFu & ~(0xFFFFFFFFu << childSlot));
+        G.y &= ~(1u << bit);
+        if (G.y & 0xFF000000u) { stack[sp] = G; ++sp; }
+        const char* p = reinterpret_cast<const char*>(a.nodes8) + (size_t)nodeIdx * 128u;
+        uint4 n0, n1;
+        ldg256(p, n0, n1);
+        const char* q = p + planeOff;
+        const uint32_t wlx = __ldg(reinterpret_cast<const uint32_t*>(q)), whx = __ldg(reinterpret_cast<const uint32_t*>(q + 16));
+        const uint32_t wly = __ldg(reinterpret_cast<const uint32_t*>(q + 32)), why = __ldg(reinterpret_cast<const uint32_t*>(q + 48));
+        const uint32_t wlz = __ldg(reinterpret_cast<const uint32_t*>(q + 64)), whz = __ldg(reinterpret_cast<const uint32_t*>(q + 80));
+        if (COUNT && lane == 0) cNodes++;
+        // this lane's child box: grid coordinates g (its slot's bf16, exact) -> world, relative to the origin
+        const float glx = __uint_as_float(__byte_perm(wlx, 0u, halfSel)), ghx = __uint_as_float(__byte_perm(whx, 0u, halfSel));
+        const float gly = __uint_as_float(__byte_perm(wly, 0u, halfSel)), ghy = __uint_as_float(__byte_perm(why, 0u, halfSel));
+        const float glz = __uint_as_float(__byte_perm(wlz, 0u, halfSel)), ghz = __uint_as_float(__byte_perm(whz, 0u, halfSel));
+        bool hit;
+        if (PLAIN) {
+            // mirrored: sgn * ((p + g * 2^e) - o); the near plane is the smaller of the two, whatever the sign was
+            const float sx = __uint_as_float(((n0.w & 0xFFu) << 23) ^ qp.smx), sy = __uint_as_float(((n0.w << 15) & 0x7F800000u) ^ qp.smy), sz = __uint_as_float(((n0.w << 7) & 0x7F800000u) ^ qp.smz);
+            const float px = fmaf(__uint_as_float(n0.x), qp.sgx, qp.mox), py = fmaf(__uint_as_float(n0.y), qp.sgy, qp.moy), pz = fmaf(__uint_as_float(n0.z), qp.sgz, qp.moz);
+            const float ax = fmaf(glx, sx, px), bx = fmaf(ghx, sx, px), ay = fmaf(gly, sy, py), by = fmaf(ghy, sy, py), az = fmaf(glz, sz, pz), bz = fmaf(ghz, sz, pz);
+            const float nx = fminf(ax, bx), fx = fmaxf(ax, bx), ny = fminf(ay, by), fy = fmaxf(ay, by), nz = fminf(az, bz), fz = fmaxf(az, bz);
+            const float ex = fminf(nx * qp.alx, nx * qp.ahx), xx = fmaxf(fx * qp.alx, fx * qp.ahx);
+            const float ey = fminf(ny * qp.aly, ny * qp.ahy), xy = fmaxf(fy * qp.aly, fy * qp.ahy);
+            const float ez = fminf(nz * qp.alz, nz * qp.ahz), xz = fmaxf(fz * qp.alz, fz * qp.ahz);
+            const float entry = fmaxf(fmaxf(ex, ey), fmaxf(ez, 0.0f));
+            const float exit = fminf(fminf(xx, xy), fminf(xz, __uint_as_float(limitBits)));
+            hit = entry <= fmaf(exit, 1.00001f, 1e-30f);
+        } else {
+            // rare packets (a quadrant crosses an axis plane of direction space; rays-in packets with several origins):
+            // nothing is kept in registers across nodes, the interval set-up is redone here
+            const float tiny = 8.271806e-25f, widen = 9.5367431640625e-7f;   // 2^-80, 2^-20
+            const bool zeroX = !(qg.lox > tiny || qg.hix < -tiny), zeroY = !(qg.loy > tiny || qg.hiy < -tiny), zeroZ = !(qg.loz > tiny || qg.hiz < -tiny);
+            const bool freeX = !qg.oneOrigin || zeroX, freeY = !qg.oneOrigin || zeroY, freeZ = !qg.oneOrigin || zeroZ;
+            float ilx = freeX ? 0.0f : 1.0f / qg.hix, ihx = freeX ? 0.0f : 1.0f / qg.lox;
+            float ily = freeY ? 0.0f : 1.0f / qg.hiy, ihy = freeY ? 0.0f : 1.0f / qg.loy;
+            float ilz = freeZ ? 0.0f : 1.0f / qg.hiz, ihz = freeZ ? 0.0f : 1.0f / qg.loz;
+            ilx -= fabsf(ilx) * widen; ihx += fabsf(ihx) * widen;
+            ily -= fabsf(ily) * widen; ihy += fabsf(ihy) * widen;
+            ilz -= fabsf(ilz) * widen; ihz += fabsf(ihz) * widen;
+            const bool negX = qg.hix < 0.0f, negY = qg.hiy < 0.0f, negZ = qg.hiz < 0.0f;
+            const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float((n0.w << 15) & 0x7F800000u), sz = __uint_as_float((n0.w << 7) & 0x7F800000u);
+            const float px = __uint_as_float(n0.x) - qg.fox, py = __uint_as_float(n0.y) - qg.foy, pz = __uint_as_float(n0.z) - qg.foz;
+            const float Wlx = fmaf(glx, sx, px), Whx = fmaf(ghx, sx, px), Wly = fmaf(gly, sy, py), Why = fmaf(ghy, sy, py), Wlz = fmaf(glz, sz, pz), Whz = fmaf(ghz, sz, pz);
+            const float nx = negX ? Whx : Wlx, fx = negX ? Wlx : Whx, ny = negY ? Why : Wly, fy = negY ? Wly : Why, nz = negZ ? Whz : Wlz, fz = negZ ? Wlz : Whz;
+            const float ex = freeX ? -INF : fminf(nx * ilx, nx * ihx), xx = freeX ? INF : fmaxf(fx * ilx, fx * ihx);
+            const float ey = freeY ? -INF : fminf(ny * ily, ny * ihy), xy = freeY ? INF : fmaxf(fy * ily, fy * ihy);
+            const float ez = freeZ ? -INF : fminf(nz * ilz, nz * ihz), xz = freeZ ? INF : fmaxf(fz * ilz, fz * ihz);
+            const float entry = fmaxf(fmaxf(ex, ey), fmaxf(ez, 0.0f));
+            const float exit = fminf(fminf(xx, xy), fminf(xz, __uint_as_float(limitBits)));
+            hit = entry <= exit * 1.00001f + 1e-30f;
+            if (qg.oneOrigin) {
+                // an axis whose direction interval contains zero has no reciprocal interval; it is tested as a wedge: up to the
+                // exit distance t1 the other axes give, the quadrant's rays stay within [t1 * min(lo, 0), t1 * max(hi, 0)]
+                const float t1 = fminf(exit, 1e30f) * 1.00001f;
+                if (zeroX) hit = hit && Wlx <= t1 * fmaxf(qg.hix, 0.0f) + 1e-30f && Whx >= t1 * fminf(qg.lox, 0.0f) - 1e-30f;
+                if (zeroY) hit = hit && Wly <= t1 * fmaxf(qg.hiy, 0.0f) + 1e-30f && Why >= t1 * fminf(qg.loy, 0.0f) - 1e-30f;
+                if (zeroZ) hit = hit && Wlz <= t1 * fmaxf(qg.hiz, 0.0f) + 1e-30f && Whz >= t1 * fminf(qg.loz, 0.0f) - 1e-30f;
+            }
+        }
+        const uint32_t any8 = __reduce_or_sync(0xFFFFFFFFu, hit ? bitC : 0u);
+        const uint32_t imask = n0.w >> 24;
+        const uint32_t top = permRow[any8 & imask];
+        const uint32_t P = n1.z & 0x00FFFFFFu;
+        uint32_t T = sSpread[any8 & ~imask & 0xFFu] & P;
+
+        // ---- the triangles of the hit leaf slots, every lane against its own ray --------------------------------------
+        if (T) {
+            do {
+                const uint32_t tb = 31u - (uint32_t)__clz(T);
+                T &= ~(1u << tb);
+                const float4* tp = a.tris + (size_t)(n1.y + (uint32_t)__popc(P & ~(0xFFFFFFFFu << tb))) * 3;
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                if (COUNT && lane == 0) cTris++;
+                float u, v, t, aa;
+                if (triCandidate(mk3(ox, oy, oz), mk3(dx, dy, dz), mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), u, v, t, aa)) {
+                    const uint32_t id = fbits(t0.w);
+                    // reference: strict t < hitT in index order => on equal t the lower index wins
+                    if (t > 0.0f && id != prev && (t < best || (t == best && id < bestId))) { best = t; bestId = id; bu = u; bv = v; }
+                }
+            } while (T);
+            limitBits = __reduce_max_sync(0xFFFFFFFFu, live ? fbits(best) : 0u);
+        }
+
+        // ---- descend, or pop ------------------------------------------------------------------------------------------
+        if (top) G = make_uint2(n1.x, (top << 24) | imask);
+        else if (sp > 0) { --sp; G = stack[sp]; }
+        else break;
+    }
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh_frustum(const TraceArgs a) {
     __shared__ uint2 sStack[TRACE_THREADS / 32][PACKET_STACK];
@@ -52,8 +171,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh
     uint2* stack = sStack[threadIdx.x >> 5];
     // test role of this lane: child slot c of its own quadrant (the 8 lanes of a quadrant differ in lane bits 0, 1, 3)
     const uint32_t c = (lane & 3u) | ((lane >> 1) & 4u);
-    const uint32_t planeOff = 32u + (c >> 1) * 4u;     // byte offset of the word holding slot c's lo plane on x
-    const bool lowerHalf = (c & 1u) != 0u;             // odd slots live in the lower 16 bits of their word
+    const uint32_t planeOff = 32u + (c >> 1) * 4u;            // byte offset of the word holding slot c's lo plane on x
+    const uint32_t halfSel = (c & 1u) ? 0x1044u : 0x3244u;    // PRMT selector: this slot's bf16 (odd slots: lower half of the word) into the upper half, zeros below
     unsigned long long cRays = 0, cNodes = 0, cTris = 0, cHits = 0;
 
     for (;;) {
@@ -71,113 +190,50 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh
         const unsigned liveMask = __ballot_sync(0xFFFFFFFFu, live);
         const float ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
         const uint32_t prev = fbits(o.w);
-        float best = live ? d.w : -1.0f;
+        float best = live ? d.w : -1.0f;   // a negative limit fails every triangle test
         float bu = 0.0f, bv = 0.0f;
         uint32_t bestId = NO_RAY_HIT;
         if (liveMask) {
             if (COUNT && live) cRays++;
             // ---- the quadrant's interval ray ------------------------------------------------------------------------
             const float INF = __int_as_float(0x7F800000);
-            float lox = live ? dx : INF, hix = live ? dx : -INF, loy = live ? dy : INF, hiy = live ? dy : -INF, loz = live ? dz : INF, hiz = live ? dz : -INF;
+            QuadGeneric qg;
+            qg.lox = live ? dx : INF; qg.hix = live ? dx : -INF; qg.loy = live ? dy : INF; qg.hiy = live ? dy : -INF; qg.loz = live ? dz : INF; qg.hiz = live ? dz : -INF;
             #pragma unroll
             for (int s = 0; s < 3; ++s) {
                 const int m = s == 0 ? 1 : (s == 1 ? 2 : 8);
-                lox = fminf(lox, __shfl_xor_sync(0xFFFFFFFFu, lox, m)); hix = fmaxf(hix, __shfl_xor_sync(0xFFFFFFFFu, hix, m));
-                loy = fminf(loy, __shfl_xor_sync(0xFFFFFFFFu, loy, m)); hiy = fmaxf(hiy, __shfl_xor_sync(0xFFFFFFFFu, hiy, m));
-                loz = fminf(loz, __shfl_xor_sync(0xFFFFFFFFu, loz, m)); hiz = fmaxf(hiz, __shfl_xor_sync(0xFFFFFFFFu, hiz, m));
+                qg.lox = fminf(qg.lox, __shfl_xor_sync(0xFFFFFFFFu, qg.lox, m)); qg.hix = fmaxf(qg.hix, __shfl_xor_sync(0xFFFFFFFFu, qg.hix, m));
+                qg.loy = fminf(qg.loy, __shfl_xor_sync(0xFFFFFFFFu, qg.loy, m)); qg.hiy = fmaxf(qg.hiy, __shfl_xor_sync(0xFFFFFFFFu, qg.hiy, m));
+                qg.loz = fminf(qg.loz, __shfl_xor_sync(0xFFFFFFFFu, qg.loz, m)); qg.hiz = fmaxf(qg.hiz, __shfl_xor_sync(0xFFFFFFFFu, qg.hiz, m));
             }
             const int first = __ffs(liveMask) - 1;
-            const float fox = __shfl_sync(0xFFFFFFFFu, ox, first), foy = __shfl_sync(0xFFFFFFFFu, oy, first), foz = __shfl_sync(0xFFFFFFFFu, oz, first);
-            const bool oneOrigin = __all_sync(0xFFFFFFFFu, !live || (ox == fox && oy == foy && oz == foz));
-            const bool quadLive = lox <= hix;                      // some live ray in this lane's quadrant
-            const float tiny = 8.271806e-25f;                      // 2^-80
-            const float widen = 9.5367431640625e-7f;               // 2^-20
-            // reciprocal interval per axis; an axis is "free" (unconstrained) when the interval touches zero
-            const bool zeroX = !(lox > tiny || hix < -tiny), zeroY = !(loy > tiny || hiy < -tiny), zeroZ = !(loz > tiny || hiz < -tiny);
-            const bool freeX = !oneOrigin || zeroX, freeY = !oneOrigin || zeroY, freeZ = !oneOrigin || zeroZ;
-            // an axis whose direction interval contains zero has no reciprocal interval; it is tested as a wedge instead:
-            // up to the exit distance t1 given by the other axes, the quadrant's rays stay within [t1 * min(lo, 0), t1 * max(hi, 0)]
-            const bool wedge = oneOrigin && (zeroX || zeroY || zeroZ);
-            const float wlo_x = fminf(lox, 0.0f), whi_x = fmaxf(hix, 0.0f), wlo_y = fminf(loy, 0.0f), whi_y = fmaxf(hiy, 0.0f), wlo_z = fminf(loz, 0.0f), whi_z = fmaxf(hiz, 0.0f);
-            float ilx = freeX ? 0.0f : 1.0f / hix, ihx = freeX ? 0.0f : 1.0f / lox;
-            float ily = freeY ? 0.0f : 1.0f / hiy, ihy = freeY ? 0.0f : 1.0f / loy;
-            float ilz = freeZ ? 0.0f : 1.0f / hiz, ihz = freeZ ? 0.0f : 1.0f / loz;
-            ilx -= fabsf(ilx) * widen; ihx += fabsf(ihx) * widen;
-            ily -= fabsf(ily) * widen; ihy += fabsf(ihy) * widen;
-            ilz -= fabsf(ilz) * widen; ihz += fabsf(ihz) * widen;
-            const bool negX = hix < 0.0f, negY = hiy < 0.0f, negZ = hiz < 0.0f;   // the quadrant travels towards - on that axis
+            qg.fox = __shfl_sync(0xFFFFFFFFu, ox, first); qg.foy = __shfl_sync(0xFFFFFFFFu, oy, first); qg.foz = __shfl_sync(0xFFFFFFFFu, oz, first);
+            qg.oneOrigin = __all_sync(0xFFFFFFFFu, !live || (ox == qg.fox && oy == qg.foy && oz == qg.foz));
+            const bool quadLive = qg.lox <= qg.hix;                // some live ray in this lane's quadrant
+            const float tiny = 8.271806e-25f, widen = 9.5367431640625e-7f;   // 2^-80, 2^-20
+            const bool zeroX = !(qg.lox > tiny || qg.hix < -tiny), zeroY = !(qg.loy > tiny || qg.hiy < -tiny), zeroZ = !(qg.loz > tiny || qg.hiz < -tiny);
+            const bool plain = __all_sync(0xFFFFFFFFu, qg.oneOrigin && !(quadLive && (zeroX || zeroY || zeroZ)));
+            const uint32_t bitC = quadLive ? (1u << c) : 0u;
             // child order for the warp: octant of the first live ray
             const uint32_t octLane = (dx < 0.0f ? 0u : 1u) | (dy < 0.0f ? 0u : 2u) | (dz < 0.0f ? 0u : 4u);
             const uint32_t woct = __shfl_sync(0xFFFFFFFFu, octLane, first);
             const uint8_t* permRow = sPerm[woct];
-            uint32_t limitBits = __reduce_max_sync(0xFFFFFFFFu, live ? fbits(best) : 0u);   // largest nearest-hit distance in the packet
-
-            int sp = 0;
-            uint2 G = make_uint2(0u, 0x80000000u);   // the root as a one-node group
-            for (;;) {
-                // ---- one node for the warp ------------------------------------------------------------------------
-                const uint32_t hits = G.y;
-                const uint32_t bit = 31u - (uint32_t)__clz(hits);
-                const uint32_t childSlot = (bit - 24u) ^ woct;
-                const uint32_t nodeIdx = G.x + (uint32_t)__popc(hits & 0xFFu & ~(0xFFFFFFFFu << childSlot));
-                G.y &= ~(1u << bit);
-                if (G.y & 0xFF000000u) { stack[sp] = G; ++sp; }
-                const char* p = reinterpret_cast<const char*>(a.nodes8) + (size_t)nodeIdx * 128u;
-                uint4 n0, n1;
-                ldg256(p, n0, n1);
-                const char* q = p + planeOff;
-                const uint32_t wlx = __ldg(reinterpret_cast<const uint32_t*>(q)), whx = __ldg(reinterpret_cast<const uint32_t*>(q + 16));
-                const uint32_t wly = __ldg(reinterpret_cast<const uint32_t*>(q + 32)), why = __ldg(reinterpret_cast<const uint32_t*>(q + 48));
-                const uint32_t wlz = __ldg(reinterpret_cast<const uint32_t*>(q + 64)), whz = __ldg(reinterpret_cast<const uint32_t*>(q + 80));
-                if (COUNT && lane == 0) cNodes++;
-                // this lane's child box in world space, relative to the origin: (p + g * 2^e) - o
-                const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float((n0.w << 15) & 0x7F800000u), sz = __uint_as_float((n0.w << 7) & 0x7F800000u);
-                const float px = __uint_as_float(n0.x) - fox, py = __uint_as_float(n0.y) - foy, pz = __uint_as_float(n0.z) - foz;
-                const float glx = __uint_as_float(lowerHalf ? wlx << 16 : wlx & 0xFFFF0000u), ghx = __uint_as_float(lowerHalf ? whx << 16 : whx | 0xFFFFu);
-                const float gly = __uint_as_float(lowerHalf ? wly << 16 : wly & 0xFFFF0000u), ghy = __uint_as_float(lowerHalf ? why << 16 : why | 0xFFFFu);
-                const float glz = __uint_as_float(lowerHalf ? wlz << 16 : wlz & 0xFFFF0000u), ghz = __uint_as_float(lowerHalf ? whz << 16 : whz | 0xFFFFu);
-                const float Wlx = fmaf(glx, sx, px), Whx = fmaf(ghx, sx, px), Wly = fmaf(gly, sy, py), Why = fmaf(ghy, sy, py), Wlz = fmaf(glz, sz, pz), Whz = fmaf(ghz, sz, pz);
-                const float nx = negX ? Whx : Wlx, fx = negX ? Wlx : Whx, ny = negY ? Why : Wly, fy = negY ? Wly : Why, nz = negZ ? Whz : Wlz, fz = negZ ? Wlz : Whz;
-                const float ex = freeX ? -INF : fminf(nx * ilx, nx * ihx), xx = freeX ? INF : fmaxf(fx * ilx, fx * ihx);
-                const float ey = freeY ? -INF : fminf(ny * ily, ny * ihy), xy = freeY ? INF : fmaxf(fy * ily, fy * ihy);
-                const float ez = freeZ ? -INF : fminf(nz * ilz, nz * ihz), xz = freeZ ? INF : fmaxf(fz * ilz, fz * ihz);
-                const float entry = fmaxf(fmaxf(ex, ey), fmaxf(ez, 0.0f));
-                const float exit = fminf(fminf(xx, xy), fminf(xz, __uint_as_float(limitBits)));
-                bool hit = quadLive && entry <= exit * 1.00001f + 1e-30f;
-                if (wedge) {
-                    const float t1 = fminf(exit, 1e30f) * 1.00001f;
-                    if (zeroX) hit = hit && Wlx <= t1 * whi_x + 1e-30f && Whx >= t1 * wlo_x - 1e-30f;
-                    if (zeroY) hit = hit && Wly <= t1 * whi_y + 1e-30f && Why >= t1 * wlo_y - 1e-30f;
-                    if (zeroZ) hit = hit && Wlz <= t1 * whi_z + 1e-30f && Whz >= t1 * wlo_z - 1e-30f;
-                }
-                const uint32_t any8 = __reduce_or_sync(0xFFFFFFFFu, hit ? (1u << c) : 0u);
-                const uint32_t imask = n0.w >> 24;
-                const uint32_t top = permRow[any8 & imask];
-                const uint32_t P = n1.z & 0x00FFFFFFu;
-                uint32_t T = sSpread[any8 & ~imask & 0xFFu] & P;
-
-                // ---- the triangles of the hit leaf slots, every lane against its own ray ------------------------------
-                if (T) {
-                    do {
-                        const uint32_t tb = 31u - (uint32_t)__clz(T);
-                        T &= ~(1u << tb);
-                        const float4* tp = a.tris + (size_t)(n1.y + (uint32_t)__popc(P & ~(0xFFFFFFFFu << tb))) * 3;
-                        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                        if (COUNT && lane == 0) cTris++;
-                        float u, v, t, aa;
-                        if (triCandidate(mk3(ox, oy, oz), mk3(dx, dy, dz), mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), u, v, t, aa)) {
-                            const uint32_t id = fbits(t0.w);
-                            // reference: strict t < hitT in index order => on equal t the lower index wins
-                            if (t > 0.0f && id != prev && (t < best || (t == best && id < bestId))) { best = t; bestId = id; bu = u; bv = v; }
-                        }
-                    } while (T);
-                    limitBits = __reduce_max_sync(0xFFFFFFFFu, live ? fbits(best) : 0u);
-                }
-
-                // ---- descend, or pop ----------------------------------------------------------------------------------
-                if (top) G = make_uint2(n1.x, (top << 24) | imask);
-                else if (sp > 0) { --sp; G = stack[sp]; }
-                else break;
+            QuadPlain qp;
+            if (plain) {
+                const bool negX = qg.hix < 0.0f, negY = qg.hiy < 0.0f, negZ = qg.hiz < 0.0f;   // the quadrant travels towards - on that axis
+                qp.sgx = negX ? -1.0f : 1.0f; qp.sgy = negY ? -1.0f : 1.0f; qp.sgz = negZ ? -1.0f : 1.0f;
+                qp.smx = negX ? 0x80000000u : 0u; qp.smy = negY ? 0x80000000u : 0u; qp.smz = negZ ? 0x80000000u : 0u;
+                qp.mox = -qg.fox * qp.sgx; qp.moy = -qg.foy * qp.sgy; qp.moz = -qg.foz * qp.sgz;
+                // |d| in [min, max] -> 1 / |d| in [1 / max, 1 / min]; a dead quadrant (lo = +inf, hi = -inf) gets a harmless interval
+                const float mnx = quadLive ? fminf(fabsf(qg.lox), fabsf(qg.hix)) : 1.0f, mxx = quadLive ? fmaxf(fabsf(qg.lox), fabsf(qg.hix)) : 1.0f;
+                const float mny = quadLive ? fminf(fabsf(qg.loy), fabsf(qg.hiy)) : 1.0f, mxy = quadLive ? fmaxf(fabsf(qg.loy), fabsf(qg.hiy)) : 1.0f;
+                const float mnz = quadLive ? fminf(fabsf(qg.loz), fabsf(qg.hiz)) : 1.0f, mxz = quadLive ? fmaxf(fabsf(qg.loz), fabsf(qg.hiz)) : 1.0f;
+                qp.alx = (1.0f / mxx) * (1.0f - widen); qp.ahx = (1.0f / mnx) * (1.0f + widen);
+                qp.aly = (1.0f / mxy) * (1.0f - widen); qp.ahy = (1.0f / mny) * (1.0f + widen);
+                qp.alz = (1.0f / mxz) * (1.0f - widen); qp.ahz = (1.0f / mnz) * (1.0f + widen);
+                walkFrustumPacket<COUNT, true>(a, stack, permRow, sSpread, woct, bitC, planeOff, halfSel, live, ox, oy, oz, dx, dy, dz, prev, qp, qg, best, bestId, bu, bv, cNodes, cTris, lane);
+            } else {
+                walkFrustumPacket<COUNT, false>(a, stack, permRow, sSpread, woct, bitC, planeOff, halfSel, live, ox, oy, oz, dx, dy, dz, prev, qp, qg, best, bestId, bu, bv, cNodes, cTris, lane);
             }
         }
         if (slot < a.n) {
