@@ -149,9 +149,103 @@ RTB_DI void walkFrustumPacket(const TraceArgs& a, uint2* stack, const uint8_t* p
     }
 }
 
+
+// ---- four nodes per step ---------------------------------------------------------------------------------------------
+// When all 32 rays of the packet share the sign of every direction component (all but the patches that cross an axis
+// plane of direction space), ONE interval ray bounds the whole patch, and since the warp descends into a child as soon as
+// any quadrant hits it, nothing is lost by testing the patch instead of its quadrants.  That frees three quarters of the
+// lanes: 8 lanes test the 8 children of one node, and the warp works on FOUR nodes per step.  The traversal state is a
+// per-warp stack of (node, entry distance) in shared memory; a step pops up to four entries (nearest on top), tests
+// 4 x 8 child boxes, pushes the hit inner children with one parallel store (positions from a ballot) and tests the
+// triangles of the hit leaf slots on every lane.  Entries whose entry distance has fallen behind the packet's largest
+// nearest-hit distance are dropped when popped.
+constexpr int PACKET4_STACK = 256;     // entries per warp; near the top a step pops one node only (<= +7 entries per level)
+
+template <bool COUNT>
+RTB_DI void walkFrustumPacket4(const TraceArgs& a, uint2* stack, uint32_t woct, bool live, float ox, float oy, float oz, float dx, float dy, float dz,
+                               uint32_t prev, const QuadPlain& qp, float& best, uint32_t& bestId, float& bu, float& bv,
+                               unsigned long long& cNodes, unsigned long long& cTris, unsigned lane) {
+    const uint32_t lanesBelow = (1u << lane) - 1u;
+    const uint32_t g = 3u - (lane >> 3);                 // which popped entry this lane works on: lanes 24..31 take the top of the stack
+    const uint32_t cs = (lane & 7u) ^ woct;              // its child slot: within a group, a higher lane is a nearer child
+    const uint32_t planeOff = 32u + (cs >> 1) * 4u;
+    const uint32_t halfSel = (cs & 1u) ? 0x1044u : 0x3244u;
+    const uint32_t csBelow = (1u << cs) - 1u, triShift = 3u * cs;
+    uint32_t limitBits = __reduce_max_sync(0xFFFFFFFFu, live ? fbits(best) : 0u);
+    if (lane == 0) stack[0] = make_uint2(0u, 0u);        // the root, entry distance 0
+    int sp = 1;
+    __syncwarp();
+    while (sp > 0) {
+        const int nPop = sp > PACKET4_STACK - 40 ? 1 : min(sp, 4);
+        uint2 e = make_uint2(0u, 0xFFFFFFFFu);
+        if ((int)g < nPop) e = stack[sp - 1 - (int)g];
+        sp -= nPop;
+        const bool activeNode = e.y <= limitBits;        // non-negative floats order like their bit patterns
+        __syncwarp();                                    // every pop has been read before this step's pushes land
+        bool inner = false, leaf = false;
+        uint32_t childIdx = 0, triFirst = 0, triCnt = 0, entryBits = 0;
+        if (activeNode) {
+            const char* p = reinterpret_cast<const char*>(a.nodes8) + (size_t)e.x * 128u;
+            uint4 n0, n1;
+            ldg256(p, n0, n1);
+            const char* q = p + planeOff;
+            const uint32_t wlx = __ldg(reinterpret_cast<const uint32_t*>(q)), whx = __ldg(reinterpret_cast<const uint32_t*>(q + 16));
+            const uint32_t wly = __ldg(reinterpret_cast<const uint32_t*>(q + 32)), why = __ldg(reinterpret_cast<const uint32_t*>(q + 48));
+            const uint32_t wlz = __ldg(reinterpret_cast<const uint32_t*>(q + 64)), whz = __ldg(reinterpret_cast<const uint32_t*>(q + 80));
+            if (COUNT && (lane & 7u) == 0u) cNodes++;
+            const float glx = __uint_as_float(__byte_perm(wlx, 0u, halfSel)), ghx = __uint_as_float(__byte_perm(whx, 0u, halfSel));
+            const float gly = __uint_as_float(__byte_perm(wly, 0u, halfSel)), ghy = __uint_as_float(__byte_perm(why, 0u, halfSel));
+            const float glz = __uint_as_float(__byte_perm(wlz, 0u, halfSel)), ghz = __uint_as_float(__byte_perm(whz, 0u, halfSel));
+            const float sx = __uint_as_float(((n0.w & 0xFFu) << 23) ^ qp.smx), sy = __uint_as_float(((n0.w << 15) & 0x7F800000u) ^ qp.smy), sz = __uint_as_float(((n0.w << 7) & 0x7F800000u) ^ qp.smz);
+            const float px = fmaf(__uint_as_float(n0.x), qp.sgx, qp.mox), py = fmaf(__uint_as_float(n0.y), qp.sgy, qp.moy), pz = fmaf(__uint_as_float(n0.z), qp.sgz, qp.moz);
+            const float ax = fmaf(glx, sx, px), bx = fmaf(ghx, sx, px), ay = fmaf(gly, sy, py), by = fmaf(ghy, sy, py), az = fmaf(glz, sz, pz), bz = fmaf(ghz, sz, pz);
+            const float nx = fminf(ax, bx), fx = fmaxf(ax, bx), ny = fminf(ay, by), fy = fmaxf(ay, by), nz = fminf(az, bz), fz = fmaxf(az, bz);
+            const float ex = fminf(nx * qp.alx, nx * qp.ahx), xx = fmaxf(fx * qp.alx, fx * qp.ahx);
+            const float ey = fminf(ny * qp.aly, ny * qp.ahy), xy = fmaxf(fy * qp.aly, fy * qp.ahy);
+            const float ez = fminf(nz * qp.alz, nz * qp.ahz), xz = fmaxf(fz * qp.alz, fz * qp.ahz);
+            const float entry = fmaxf(fmaxf(ex, ey), fmaxf(ez, 0.0f));
+            const float exit = fminf(fminf(xx, xy), fminf(xz, __uint_as_float(limitBits)));
+            const bool hit = entry <= fmaf(exit, 1.00001f, 1e-30f);
+            const uint32_t imask = n0.w >> 24, P = n1.z & 0x00FFFFFFu;
+            triCnt = (uint32_t)__popc((P >> triShift) & 7u);
+            inner = hit && ((imask >> cs) & 1u);
+            leaf = hit && triCnt != 0u;                  // a slot is an inner node or holds triangles, never both
+            childIdx = n1.x + (uint32_t)__popc(imask & csBelow);
+            triFirst = n1.y + (uint32_t)__popc(P & ((1u << triShift) - 1u));
+            entryBits = fbits(entry);
+        }
+        const uint32_t mInner = __ballot_sync(0xFFFFFFFFu, inner);
+        uint32_t mLeaf = __ballot_sync(0xFFFFFFFFu, leaf);
+        if (inner) stack[sp + __popc(mInner & lanesBelow)] = make_uint2(childIdx, entryBits);
+        sp += __popc(mInner);
+
+        // ---- the triangles of the hit leaf slots, every lane against its own ray --------------------------------------
+        if (mLeaf) {
+            do {
+                const int L = 31 - __clz(mLeaf);
+                mLeaf &= ~(1u << L);
+                const uint32_t tf = __shfl_sync(0xFFFFFFFFu, triFirst, L), tc = __shfl_sync(0xFFFFFFFFu, triCnt, L);
+                for (uint32_t k = 0; k < tc; ++k) {
+                    const float4* tp = a.tris + (size_t)(tf + k) * 3;
+                    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                    if (COUNT && lane == 0) cTris++;
+                    float u, v, t, aa;
+                    if (triCandidate(mk3(ox, oy, oz), mk3(dx, dy, dz), mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), u, v, t, aa)) {
+                        const uint32_t id = fbits(t0.w);
+                        // reference: strict t < hitT in index order => on equal t the lower index wins
+                        if (t > 0.0f && id != prev && (t < best || (t == best && id < bestId))) { best = t; bestId = id; bu = u; bv = v; }
+                    }
+                }
+            } while (mLeaf);
+            limitBits = __reduce_max_sync(0xFFFFFFFFu, live ? fbits(best) : 0u);
+        }
+        __syncwarp();                                    // pushes are visible to the next step's pops
+    }
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh_frustum(const TraceArgs a) {
-    __shared__ uint2 sStack[TRACE_THREADS / 32][PACKET_STACK];
+    __shared__ uint2 sStack[TRACE_THREADS / 32][PACKET4_STACK];
     __shared__ uint8_t sPerm[8][256];     // hit-mask bits from slot order to traversal order: bit s -> bit s ^ octant
     __shared__ uint32_t sSpread[256];     // child bit c -> the three triangle bits 3c .. 3c+2
     for (uint32_t i = threadIdx.x; i < 2048u; i += TRACE_THREADS) {
@@ -219,7 +313,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh
             const uint32_t woct = __shfl_sync(0xFFFFFFFFu, octLane, first);
             const uint8_t* permRow = sPerm[woct];
             QuadPlain qp;
-            if (plain) {
+            // the whole patch on one side of every axis plane of direction space: one interval ray for all 32 rays
+            const unsigned ngx = __ballot_sync(0xFFFFFFFFu, live && dx < 0.0f), ngy = __ballot_sync(0xFFFFFFFFu, live && dy < 0.0f), ngz = __ballot_sync(0xFFFFFFFFu, live && dz < 0.0f);
+            const bool plain4 = plain && (ngx == 0u || ngx == liveMask) && (ngy == 0u || ngy == liveMask) && (ngz == 0u || ngz == liveMask);
+            if (plain4) {
+                const bool negX = ngx != 0u, negY = ngy != 0u, negZ = ngz != 0u;
+                qp.sgx = negX ? -1.0f : 1.0f; qp.sgy = negY ? -1.0f : 1.0f; qp.sgz = negZ ? -1.0f : 1.0f;
+                qp.smx = negX ? 0x80000000u : 0u; qp.smy = negY ? 0x80000000u : 0u; qp.smz = negZ ? 0x80000000u : 0u;
+                qp.mox = -qg.fox * qp.sgx; qp.moy = -qg.foy * qp.sgy; qp.moz = -qg.foz * qp.sgz;
+                // |d| over the live rays of the patch (positive floats order like their bit patterns)
+                const float mnx = __uint_as_float(__reduce_min_sync(0xFFFFFFFFu, live ? fbits(fabsf(dx)) : 0x7F800000u)), mxx = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, live ? fbits(fabsf(dx)) : 0u));
+                const float mny = __uint_as_float(__reduce_min_sync(0xFFFFFFFFu, live ? fbits(fabsf(dy)) : 0x7F800000u)), mxy = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, live ? fbits(fabsf(dy)) : 0u));
+                const float mnz = __uint_as_float(__reduce_min_sync(0xFFFFFFFFu, live ? fbits(fabsf(dz)) : 0x7F800000u)), mxz = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, live ? fbits(fabsf(dz)) : 0u));
+                qp.alx = (1.0f / mxx) * (1.0f - widen); qp.ahx = (1.0f / mnx) * (1.0f + widen);
+                qp.aly = (1.0f / mxy) * (1.0f - widen); qp.ahy = (1.0f / mny) * (1.0f + widen);
+                qp.alz = (1.0f / mxz) * (1.0f - widen); qp.ahz = (1.0f / mnz) * (1.0f + widen);
+                walkFrustumPacket4<COUNT>(a, stack, woct, live, ox, oy, oz, dx, dy, dz, prev, qp, best, bestId, bu, bv, cNodes, cTris, lane);
+            } else if (plain) {
                 const bool negX = qg.hix < 0.0f, negY = qg.hiy < 0.0f, negZ = qg.hiz < 0.0f;   // the quadrant travels towards - on that axis
                 qp.sgx = negX ? -1.0f : 1.0f; qp.sgy = negY ? -1.0f : 1.0f; qp.sgz = negZ ? -1.0f : 1.0f;
                 qp.smx = negX ? 0x80000000u : 0u; qp.smy = negY ? 0x80000000u : 0u; qp.smz = negZ ? 0x80000000u : 0u;
