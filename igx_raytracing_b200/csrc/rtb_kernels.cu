@@ -516,10 +516,43 @@ RTB_DI bool occludedByOthers(const SceneView& sv, const Ray& ray, float maxDist,
     return hit.hitT < maxDist;
 }
 
-__global__ void __launch_bounds__(256) k_shadowgen(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
+// Hit and miss pixels do very different amounts of work (a shadow ray and Cook-Torrance against one sky lookup), and in
+// a scene like the triangle soup they alternate inside every 8x4 patch: half the lanes of every warp idle through the
+// other half's branch (ncu r1r: 16.8 of 32 lanes active in k_shade and k_shadowgen).  The 256 slots of a block are
+// therefore dealt to its threads hits first: all-hit warps, one mixed warp, all-miss warps.  Every slot is still
+// processed exactly once by the same code, so nothing changes but which thread does it.  All 256 threads must call.
+RTB_DI uint32_t hitsFirst(bool isHit) {
+    __shared__ uint16_t sOrder[256];
+    __shared__ uint32_t sWarpHits[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, isHit);
+    if (lane == 0) sWarpHits[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    #pragma unroll
+    for (uint32_t w = 0; w < 8u; ++w) { const uint32_t c = sWarpHits[w]; total += c; if (w < warp) before += c; }
+    const uint32_t hitsBeforeMe = before + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    sOrder[isHit ? hitsBeforeMe : total + (tid - hitsBeforeMe)] = (uint16_t)tid;
+    __syncthreads();
+    return sOrder[tid];
+}
+
+// Both shading kernels are chains of dependent binary64 operations: latency-bound, so occupancy pays even at the price
+// of spills (B200, 4K soup frame: k_shadowgen 0.231 ms at 4 blocks/SM -> 0.202 at 8; k_shade 0.535 ms at 3 -> 0.411 at 6).
+#ifndef RTB_SHADOWGEN_MINBLOCKS
+#define RTB_SHADOWGEN_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(256, RTB_SHADOWGEN_MINBLOCKS) k_shadowgen(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
                                                    uint32_t samples, const float4* __restrict__ dirT, RayRec* __restrict__ rays,
                                                    uint32_t* __restrict__ bits) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    // localSlots is a multiple of 1024: a block of 256 slots lies in one sample and is never ragged
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        const uint32_t sample0 = j / fm.localSlots, i0 = j - sample0 * fm.localSlots;
+        uint32_t x0, y0;
+        const bool hit0 = j < fm.localSlots * samples && slotToPixel(fm, i0, x0, y0) && fbits(__ldg(dirT + (size_t)y0 * fm.w + x0).w) != NO_RAY_HIT;
+        j = blockIdx.x * blockDim.x + hitsFirst(hit0);
+    }
     if (j >= fm.localSlots * samples) return;
     const uint32_t sample = j / fm.localSlots, i = j - sample * fm.localSlots;
     float4 ro = make_float4(0.f, 0.f, 0.f, ubits(NO_RAY_HIT)), rd = make_float4(0.f, 0.f, 1.f, -1.0f);
@@ -584,12 +617,20 @@ void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint
 // --------------------------------------------------------------------------------------------------------
 // DO_LIGHT: evaluate lighting.comp; DO_COMP: evaluate composite.comp.  Both: the fused frame path (the rgba16f
 // rounding of the lighting texture is reproduced in registers); one only: the reference's separate dispatches.
+#ifndef RTB_SHADE_MINBLOCKS
+#define RTB_SHADE_MINBLOCKS 6
+#endif
 template <bool DO_LIGHT, bool DO_COMP>
-__global__ void __launch_bounds__(256) k_shade(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
+__global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
                                                uint32_t samples, const float4* __restrict__ dirT, const float4* __restrict__ uvN,
                                                const uint32_t* __restrict__ bits, uint2* __restrict__ lighting, float4* __restrict__ accum,
                                                uint32_t* __restrict__ rgba8, uint32_t* __restrict__ rgba8Tiled) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        uint32_t x0, y0;
+        const bool hit0 = i < fm.localSlots && slotToPixel(fm, i, x0, y0) && fbits(__ldg(dirT + (size_t)y0 * fm.w + x0).w) != NO_RAY_HIT;
+        i = blockIdx.x * blockDim.x + hitsFirst(hit0);
+    }
     if (i >= fm.localSlots) return;
     uint32_t x, y;
     if (!slotToPixel(fm, i, x, y)) { if (DO_COMP && rgba8Tiled) rgba8Tiled[i] = 0u; return; }
