@@ -70,6 +70,7 @@ struct rtb_ctx {
     uint32_t countersMode = 0;        // 1: per-ray algorithmic counts (per-lane kernel); 2: what the kernels in use fetch
     uint32_t packetsOpt = 2;          // RTB_OPT_PRIMARY_PACKETS: 0 off, 1 union packets, 2 auto, 3 frustum packets
     int lastPrimaryPackets = 0;       // PACKETS_* of the last camera-ray launch
+    uint32_t fuseOpt = 1;             // RTB_OPT_FUSE_PRIMARY
 
     // rays-in scratch
     DevBuf<RayRec> rinRays; DevBuf<TriHit> rinHits; DevBuf<uint32_t> rinObj; DevBuf<float> rinT; DevBuf<float2> rinUv; DevBuf<uint8_t> rinOcc, rinOcc2;
@@ -169,9 +170,16 @@ int primaryPackets(const rtb_ctx* c) {
 // `mark` (frame dispatch only) records an event after each phase so the traversal launches can be timed alone
 int passRaygen(rtb_ctx* c, bool mark) {
     const SceneView sv = sceneView(c);
+    c->lastPrimaryPackets = primaryPackets(c);
+    if (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt) {
+        // one launch: rays generated in registers, traced, G-buffer written (the phase events collapse onto the trace phase)
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+        launch_primary_fused(c->fm, sv, &c->camera, c->seed.p, c->dirT.p, c->uvN.p, c->workCounter.p, c->stream);
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+        return RTB_OK;
+    }
     launch_raygen(c->fm, &c->camera, c->seed.p, c->rays.p, c->stream);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    c->lastPrimaryPackets = primaryPackets(c);
     launch_trace_closest(sv, c->rays.p, c->fm.localSlots, c->hits.p, c->workCounter.p, c->countersOn ? c->counters.p : nullptr, c->lastPrimaryPackets, c->stream);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     launch_finish_primary(c->fm, sv, c->rays.p, c->hits.p, c->dirT.p, c->uvN.p, c->stream);
@@ -255,6 +263,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
     if (!c) return RTB_ERR_ARG;
     switch (opt) {
         case RTB_OPT_COUNTERS: c->countersOn = value != 0; c->countersMode = value; return RTB_OK;
+        case RTB_OPT_FUSE_PRIMARY: c->fuseOpt = value ? 1u : 0u; return RTB_OK;
         case RTB_OPT_PRIMARY_PACKETS:
             if (value > 3) return fail(c, RTB_ERR_ARG, "RTB_OPT_PRIMARY_PACKETS: 0 off, 1 union packets, 2 auto, 3 frustum packets");
             c->packetsOpt = value; return RTB_OK;

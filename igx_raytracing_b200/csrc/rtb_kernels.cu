@@ -273,20 +273,29 @@ static void launchTrace(const SceneView& sv, const TraceArgs& a, bool count, cud
 }
 int trace_grid_blocks() { return g_traceBlocks; }
 
-template <bool COUNT, bool FRUSTUM>
-static void launchPacket(const TraceArgs& a, cudaStream_t st) {
-    static int blocks = 0;
-    auto kernel = FRUSTUM ? k_trace_cwbvh_frustum<COUNT> : k_trace_cwbvh_packet<COUNT>;
-    if (!blocks) {
+template <class K>
+static uint32_t persistentBlocks(K kernel, int& cache, uint32_t n) {
+    if (!cache) {
         int dev = 0, sms = 0, perSm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TRACE_THREADS, 0);
-        blocks = sms * (perSm > 0 ? perSm : 1);
+        cache = sms * (perSm > 0 ? perSm : 1);
     }
+    const uint32_t warpsNeeded = (n + 31u) / 32u, blocksNeeded = (warpsNeeded + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32);
+    return min((uint32_t)cache, blocksNeeded ? blocksNeeded : 1u);
+}
+template <bool COUNT, bool FRUSTUM>
+static void launchPacket(const TraceArgs& a, cudaStream_t st) {
+    static int blocks = 0;
     cudaMemsetAsync(a.workCounter, 0, sizeof(uint32_t), st);
-    const uint32_t warpsNeeded = (a.n + 31u) / 32u, blocksNeeded = (warpsNeeded + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32);
-    kernel<<<min((uint32_t)blocks, blocksNeeded ? blocksNeeded : 1u), TRACE_THREADS, 0, st>>>(a);
+    if (FRUSTUM) {
+        auto kernel = k_trace_cwbvh_frustum<COUNT, false>;
+        kernel<<<persistentBlocks(kernel, blocks, a.n), TRACE_THREADS, 0, st>>>(a, FusedArgs{});
+    } else {
+        auto kernel = k_trace_cwbvh_packet<COUNT>;
+        kernel<<<persistentBlocks(kernel, blocks, a.n), TRACE_THREADS, 0, st>>>(a);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -355,6 +364,18 @@ static TraceArgs makeArgs(const SceneView& sv, const RayRec* rays, uint32_t n, u
     a.tris = reinterpret_cast<const float4*>(sv.travTris); a.nodeCount = sv.nodeCount;
     a.workCounter = workCounter; a.counters = counters;
     return a;
+}
+
+// camera rays generated, traced and finished into the G-buffer by one launch (frustum packets; see rtb_trace8f.cuh, FusedArgs)
+void launch_primary_fused(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, float4* dirT, float4* uvN,
+                          uint32_t* workCounter, cudaStream_t st) {
+    if (!fm.localSlots) return;
+    static int blocks = 0;
+    TraceArgs a = makeArgs(sv, nullptr, fm.localSlots, workCounter, nullptr);
+    FusedArgs f{fm, *cam, seed, sv, dirT, uvN};
+    cudaMemsetAsync(workCounter, 0, sizeof(uint32_t), st);
+    auto kernel = k_trace_cwbvh_frustum<false, true>;
+    kernel<<<persistentBlocks(kernel, blocks, a.n), TRACE_THREADS, 0, st>>>(a, f);
 }
 
 void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,

@@ -36,6 +36,9 @@ void launch_raygen(const FrameMap& fm, const CameraRec* cam, const SeedRec* seed
 enum { PACKETS_OFF = 0, PACKETS_UNION = 1, PACKETS_FRUSTUM = 3 };
 void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
                           TraceCounters* counters, int packets, cudaStream_t s);
+// raygen + nearest hit (frustum packets) + G-buffer finish as ONE launch: no ray / hit records in between
+void launch_primary_fused(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, float4* dirT, float4* uvN,
+                          uint32_t* workCounter, cudaStream_t s);
 // spheres, cubes, planes after the triangles, normal interpolation, G-buffer stores (raygen.comp:39-51)
 void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits,
                            float4* dirT, float4* uvN, cudaStream_t s);

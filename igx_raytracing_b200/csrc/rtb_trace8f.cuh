@@ -30,6 +30,14 @@ namespace rtb {
 #define RTB_FR_MINBLOCKS 4
 #endif
 
+// FUSED: the kernel generates the camera rays itself (raygen.comp:16-37) and finishes the G-buffer in its epilogue
+// (trace.glsl:31-63, raygen.comp:39-51) instead of reading 32-byte ray records and writing 16-byte hit records for two
+// more kernels to pick up: the same device functions k_raygen and k_finish_primary call, so the same bits.
+struct FusedArgs {
+    FrameMap fm; CameraRec cam; const SeedRec* seed; SceneView sv; float4* dirT; float4* uvN;
+};
+RTB_DI void finishGeometry(const SceneView& sv, const Ray& ray, uint32_t prev, const TriHit& th, Hit& hit, vec3& objectNormal);   // rtb_kernels.cu
+
 // Per-lane description of the quadrant's interval ray, in the form each of the two walks wants it.
 struct QuadPlain {      // every axis has a sign: mirrored so that the quadrant travels towards +
     float sgx, sgy, sgz;          // +-1
@@ -243,8 +251,8 @@ RTB_DI void walkFrustumPacket4(const TraceArgs& a, uint2* stack, uint32_t woct, 
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh_frustum(const TraceArgs a) {
+template <bool COUNT, bool FUSED>
+__global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh_frustum(const TraceArgs a, const FusedArgs f) {
     __shared__ uint2 sStack[TRACE_THREADS / 32][PACKET4_STACK];
     __shared__ uint8_t sPerm[8][256];     // hit-mask bits from slot order to traversal order: bit s -> bit s ^ octant
     __shared__ uint32_t sSpread[256];     // child bit c -> the three triangle bits 3c .. 3c+2
@@ -275,8 +283,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= a.n) break;
         const uint32_t slot = base + lane;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 1.f, -1.0f);
-        if (slot < a.n) {
+        float4 o = make_float4(0.f, 0.f, 0.f, ubits(NO_RAY_HIT)), d = make_float4(0.f, 0.f, 1.f, -1.0f);
+        uint32_t pxX = 0, pxY = 0;
+        if (FUSED) {
+            if (slot < a.n && slotToPixel(f.fm, slot, pxX, pxY)) {
+                const Ray r = calculatePrimary(f.cam, pxX, pxY, mk2(__ldg(&f.seed->randomX), __ldg(&f.seed->randomY)));
+                o = make_float4(r.pos.x, r.pos.y, r.pos.z, ubits(NO_RAY_HIT));
+                d = make_float4(r.dir.x, r.dir.y, r.dir.z, NO_HIT);
+            }
+        } else if (slot < a.n) {
             o = __ldg(reinterpret_cast<const float4*>(a.rays + slot));
             d = __ldg(reinterpret_cast<const float4*>(a.rays + slot) + 1);
         }
@@ -346,11 +361,25 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh
                 walkFrustumPacket<COUNT, false>(a, stack, permRow, sSpread, woct, bitC, planeOff, halfSel, live, ox, oy, oz, dx, dy, dz, prev, qp, qg, best, bestId, bu, bv, cNodes, cTris, lane);
             }
         }
-        if (slot < a.n) {
-            TriHit h; h.t = bestId == NO_RAY_HIT ? NO_HIT : best; h.id = bestId; h.u = bu; h.v = bv;
+        TriHit h; h.t = bestId == NO_RAY_HIT ? NO_HIT : best; h.id = bestId; h.u = bu; h.v = bv;
+        if (FUSED) {
+            if (live) {   // k_finish_primary, on registers
+                Ray ray; ray.pos = mk3(ox, oy, oz); ray.dir = mk3(dx, dy, dz);
+                Hit hit; vec3 objectNormal;
+                finishGeometry(f.sv, ray, NO_RAY_HIT, h, hit, objectNormal);
+                float4 out0;
+                if (hit.hitT == NO_HIT) out0 = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ubits(NO_RAY_HIT));
+                else { const vec3 v = ray.dir * hit.hitT; out0 = make_float4(v.x, v.y, v.z, ubits(hit.object)); }
+                uint32_t ex, ey;
+                encodeNormalGpu(objectNormal, ex, ey);
+                const size_t px = (size_t)pxY * f.fm.w + pxX;
+                f.dirT[px] = out0;
+                f.uvN[px] = make_float4(hit.uv.x, hit.uv.y, ubits(ex), ubits(ey));
+            }
+        } else if (slot < a.n) {
             *reinterpret_cast<float4*>(a.hits + slot) = *reinterpret_cast<float4*>(&h);
-            if (COUNT && bestId != NO_RAY_HIT) cHits++;
         }
+        if (COUNT && slot < a.n && bestId != NO_RAY_HIT) cHits++;
     }
 
     if (COUNT) {

@@ -121,7 +121,7 @@ typedef enum rtb_option {
     RTB_OPT_TILE_COUNT = 2,
     RTB_OPT_SKIP_PARITY_STORES = 3,/* 0/1: RELEASE-shader behaviour (no uvObjectNormal/lighting store on misses) is NOT
                                       modelled; reserved, must be 0 */
-    RTB_OPT_PRIMARY_PACKETS = 4    /* nearest-hit search of the camera rays with RTB_ACCEL_BVH.  0 = one traversal per ray.
+    RTB_OPT_PRIMARY_PACKETS = 4,   /* nearest-hit search of the camera rays with RTB_ACCEL_BVH.  0 = one traversal per ray.
                                       1 = one warp-cooperative traversal per 8x4-pixel patch, every ray testing every
                                       child box of the union ("union packets").  3 = the same walk with the box tests
                                       done once per packet against the interval rays of the patch's four quadrants
@@ -130,6 +130,9 @@ typedef enum rtb_option {
                                       is Default and the patch is small against the tree's leaf nodes, else per ray.
                                       The hits are identical in every mode.  With 1 or 3 the rays-in call rtb_trace_rays
                                       also walks its rays in packets of 32 consecutive rays. */
+    RTB_OPT_FUSE_PRIMARY = 5       /* 0/1 (default 1): with frustum packets, generate the camera rays inside the traversal launch and
+                                      write the G-buffer from its epilogue (one launch instead of three; same bits).  0 keeps
+                                      the three launches, e.g. to time them apart. */
 } rtb_option;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
