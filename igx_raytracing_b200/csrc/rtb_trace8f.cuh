@@ -167,10 +167,15 @@ RTB_DI void walkFrustumPacket(const TraceArgs& a, uint2* stack, const uint8_t* p
 // 4 x 8 child boxes, pushes the hit inner children with one parallel store (positions from a ballot) and tests the
 // triangles of the hit leaf slots on every lane.  Entries whose entry distance has fallen behind the packet's largest
 // nearest-hit distance are dropped when popped.
-constexpr int PACKET4_STACK = 256;     // entries per warp; near the top a step pops one node only (<= +7 entries per level)
+#ifndef RTB_PK4_STACK
+#define RTB_PK4_STACK 256
+#endif
+constexpr int PACKET4_STACK = RTB_PK4_STACK;     // entries per warp; near the top a step pops one node only, and a packet that would
+                                       // still overflow (no real tree does) is handed to the one-node walk, whose stack is
+                                       // bounded by the tree depth
 
 template <bool COUNT>
-RTB_DI void walkFrustumPacket4(const TraceArgs& a, uint2* stack, uint32_t woct, bool live, float ox, float oy, float oz, float dx, float dy, float dz,
+RTB_DI bool walkFrustumPacket4(const TraceArgs& a, uint2* stack, uint32_t woct, bool live, float ox, float oy, float oz, float dx, float dy, float dz,
                                uint32_t prev, const QuadPlain& qp, float& best, uint32_t& bestId, float& bu, float& bv,
                                unsigned long long& cNodes, unsigned long long& cTris, unsigned lane) {
     const uint32_t lanesBelow = (1u << lane) - 1u;
@@ -224,6 +229,7 @@ RTB_DI void walkFrustumPacket4(const TraceArgs& a, uint2* stack, uint32_t woct, 
         }
         const uint32_t mInner = __ballot_sync(0xFFFFFFFFu, inner);
         uint32_t mLeaf = __ballot_sync(0xFFFFFFFFu, leaf);
+        if (sp + __popc(mInner) > PACKET4_STACK) return true;   // uniform: hits found so far stay valid, the caller restarts from the root
         if (inner) stack[sp + __popc(mInner & lanesBelow)] = make_uint2(childIdx, entryBits);
         sp += __popc(mInner);
 
@@ -249,6 +255,7 @@ RTB_DI void walkFrustumPacket4(const TraceArgs& a, uint2* stack, uint32_t woct, 
         }
         __syncwarp();                                    // pushes are visible to the next step's pops
     }
+    return false;
 }
 
 template <bool COUNT, bool FUSED>
@@ -343,7 +350,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh
                 qp.alx = (1.0f / mxx) * (1.0f - widen); qp.ahx = (1.0f / mnx) * (1.0f + widen);
                 qp.aly = (1.0f / mxy) * (1.0f - widen); qp.ahy = (1.0f / mny) * (1.0f + widen);
                 qp.alz = (1.0f / mxz) * (1.0f - widen); qp.ahz = (1.0f / mnz) * (1.0f + widen);
-                walkFrustumPacket4<COUNT>(a, stack, woct, live, ox, oy, oz, dx, dy, dz, prev, qp, best, bestId, bu, bv, cNodes, cTris, lane);
+                if (walkFrustumPacket4<COUNT>(a, stack, woct, live, ox, oy, oz, dx, dy, dz, prev, qp, best, bestId, bu, bv, cNodes, cTris, lane)) {
+                    __syncwarp();
+                    walkFrustumPacket<COUNT, true>(a, stack, permRow, sSpread, woct, bitC, planeOff, halfSel, live, ox, oy, oz, dx, dy, dz, prev, qp, qg, best, bestId, bu, bv, cNodes, cTris, lane);
+                }
             } else if (plain) {
                 const bool negX = qg.hix < 0.0f, negY = qg.hiy < 0.0f, negZ = qg.hiz < 0.0f;   // the quadrant travels towards - on that axis
                 qp.sgx = negX ? -1.0f : 1.0f; qp.sgy = negY ? -1.0f : 1.0f; qp.sgz = negZ ? -1.0f : 1.0f;
