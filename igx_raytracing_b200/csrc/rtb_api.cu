@@ -142,11 +142,13 @@ int checkReady(rtb_ctx* c) {
     return RTB_OK;
 }
 
-// Primary rays of an 8x4 pixel patch are walked through the 8-wide tree as one packet (rtb_trace8p.cuh) when the patch
-// is small against the tree's leaf nodes: its width at the distance of the scene centre, 8 pixels wide, must stay
-// below PACKET_RATIO leaf-node edges.  Above that the union of the nodes the 32 rays need grows faster than the
-// shared fetches save (measured on the 1M-triangle soup from two distances and on the 10M-triangle height field).
-constexpr float PACKET_RATIO = 1.0f;
+// Camera rays of an 8x4-pixel patch are walked through the 8-wide tree as one packet (rtb_trace8f.cuh) when the patch is
+// small against the tree's leaf nodes: its width at the distance of the scene centre, 8 pixels wide, must stay below
+// PACKET_RATIO mean leaf-node edges.  Beyond that the triangles of the union, which every lane tests, grow with the square
+// of the ratio.  Measured on B200 with the four-node walk (nearest-hit phase incl. ray generation and G-buffer finish):
+// ratio 0.76 (1M-triangle soup, 4K) 1.38 ms against 5.25 per ray; ratio 1.64 (same soup from z = 30) 0.58 against 0.87;
+// ratio 16.8 (10M-triangle height field, 1080p) 14.5 against 0.51.
+constexpr float PACKET_RATIO = 2.0f;
 int primaryPackets(const rtb_ctx* c) {
     if (c->accelMode != RTB_ACCEL_BVH || !c->accelValid || !c->info.triangleCount) return PACKETS_OFF;
     if (c->countersOn && c->countersMode == 1) return PACKETS_OFF;
