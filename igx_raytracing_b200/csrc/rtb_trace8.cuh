@@ -18,6 +18,9 @@
 // peak with 8 x LDG.128 per node), so a node is fetched with four LDG.256: header, and one granule per axis holding
 // (lo, hi); the near / far assignment is a pair of complementary predicated loads with swapped destinations.
 //
+// Also measured and rejected for the node fetch (occlusion launch, 2.14 ms with the four LDG.256): eight 16-byte texture
+// fetches of the same record through a linear uint4 texture object, near / far by texel index: 2.42 ms.
+//
 // The per-lane stack holds 8-byte (base, mask) groups: the first SM_STACK entries in shared memory ([entry][thread],
 // conflict-free for any mix of depths), the rest in local memory.
 #pragma once
