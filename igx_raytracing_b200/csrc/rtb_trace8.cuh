@@ -33,8 +33,14 @@ namespace rtb {
 constexpr int TOP8_NODES = RTB_CW_TOP_NODES;   // 16 KB of shared memory: the breadth-first top of the tree (0 = not staged)
 constexpr int SM_STACK = 8;          // 16 KB of shared memory per 256-thread block
 constexpr int LOCAL_STACK = 56;      // rtb_build_accel refuses trees that could need more than SM_STACK + LOCAL_STACK entries
-constexpr int REFILL8 = 22;
-constexpr int POSTPONE8 = 8;
+#ifndef RTB_CW_REFILL
+#define RTB_CW_REFILL 22
+#endif
+#ifndef RTB_CW_POSTPONE
+#define RTB_CW_POSTPONE 8
+#endif
+constexpr int REFILL8 = RTB_CW_REFILL;
+constexpr int POSTPONE8 = RTB_CW_POSTPONE;
 
 // 32 bytes from global memory through the read-only path in one instruction (LDG.E.256, sm_100)
 RTB_DI void ldg256(const char* p, uint4& a, uint4& b) {
