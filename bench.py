@@ -250,7 +250,8 @@ def main():
     # pinned host staging for the end-to-end leg
     cam_pin = torch.from_numpy(cam.copy()).pin_memory()
     seed_pin = torch.from_numpy(seed0.copy()).pin_memory()
-    frame_pin = torch.empty(w * h, dtype=torch.int32).pin_memory()
+    frame_pins = [torch.empty(w * h, dtype=torch.int32).pin_memory() for _ in range(2)]   # the frame being copied out / the one the host may read
+    e2e_count = [0]
 
     tiled = gathered = None
     slots = 0
@@ -275,8 +276,10 @@ def main():
             dist.gather(tiled, list(gathered.split(slots)) if rank == 0 else None, dst=0)
             if rank == 0:
                 ctx.untile(gathered.data_ptr(), world, slots, 0)
-        if e2e and rank == 0:   # presentToCpu: the rgba8 frame lands in host memory
-            ctx.readback_into(rtb.TGT_RGBA8, frame_pin.data_ptr(), w * h * 4)
+        if e2e and rank == 0:   # presentToCpu: the rgba8 frame lands in host memory (a copy + fence, like the reference's PBO read-back:
+            # frame N is copied out while frame N+1 renders; the timed region ends with the last copy landed)
+            ctx.readback_async_into(rtb.TGT_RGBA8, frame_pins[e2e_count[0] & 1].data_ptr(), w * h * 4)
+            e2e_count[0] += 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -326,6 +329,8 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             frame(e2e)
+        if e2e and rank == 0:
+            ctx.readback_wait()   # every frame of the timed region is in host memory
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <initializer_list>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -76,6 +77,10 @@ struct rtb_ctx {
     DevBuf<RayRec> rinRays; DevBuf<TriHit> rinHits; DevBuf<uint32_t> rinObj; DevBuf<float> rinT; DevBuf<float2> rinUv; DevBuf<uint8_t> rinOcc, rinOcc2;
 
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // frame-phase boundaries
+    // asynchronous read-back (rtb_readback_async): a copy stream ordered after the frame by evReady; the next pass that
+    // overwrites the target waits for evCopied, everything before it overlaps the copy
+    cudaStream_t copyStream = nullptr; cudaEvent_t evReady = nullptr, evCopied = nullptr;
+    int copyTarget = -1;
     bool frameTimed = false;
 };
 
@@ -129,6 +134,18 @@ int allocFrame(rtb_ctx* c) {
     return RTB_OK;
 }
 
+// before a pass overwrites `target`: let a read-back of it that is still in flight finish first (device-side wait)
+int waitCopy(rtb_ctx* c, std::initializer_list<int> targets) {
+    if (c->copyTarget < 0) return RTB_OK;
+    for (int t : targets)
+        if (t == c->copyTarget) { RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evCopied, 0)); c->copyTarget = -1; break; }
+    return RTB_OK;
+}
+int drainCopy(rtb_ctx* c) {
+    if (c->copyTarget >= 0) { RTB_CUDA(c, cudaEventSynchronize(c->evCopied)); c->copyTarget = -1; }
+    return RTB_OK;
+}
+
 int checkReady(rtb_ctx* c) {
     if (!c->width || !c->height) return fail(c, RTB_ERR_STATE, "rtb_dispatch before rtb_resize");
     if (!c->cameraSet) return fail(c, RTB_ERR_STATE, "rtb_dispatch before the camera was uploaded");
@@ -171,6 +188,7 @@ int primaryPackets(const rtb_ctx* c) {
 
 // `mark` (frame dispatch only) records an event after each phase so the traversal launches can be timed alone
 int passRaygen(rtb_ctx* c, bool mark) {
+    { const int rc = waitCopy(c, {RTB_TGT_DIR_T, RTB_TGT_UV_NORMAL}); if (rc) return rc; }
     const SceneView sv = sceneView(c);
     c->lastPrimaryPackets = primaryPackets(c);
     if (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt) {
@@ -189,6 +207,7 @@ int passRaygen(rtb_ctx* c, bool mark) {
     return RTB_OK;
 }
 int passShadow(rtb_ctx* c, bool mark) {
+    { const int rc = waitCopy(c, {RTB_TGT_SHADOW_BITS}); if (rc) return rc; }
     const SceneView sv = sceneView(c);
     RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, c->samples) * 4, c->stream));
     launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, c->stream);
@@ -197,6 +216,7 @@ int passShadow(rtb_ctx* c, bool mark) {
     return RTB_OK;
 }
 int passShade(rtb_ctx* c, int what) {
+    { const int rc = waitCopy(c, {RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
     const SceneView sv = sceneView(c);
     launch_shade(what, c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->uvN.p, c->bits.p, c->lighting.p, c->accum.p,
                  c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, c->stream);
@@ -249,6 +269,9 @@ void rtb_destroy(rtb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
+    if (c->evReady) cudaEventDestroy(c->evReady);
+    if (c->evCopied) cudaEventDestroy(c->evCopied);
     c->triangles.release(); c->spheres.release(); c->cubes.release(); c->planes.release(); c->lights.release(); c->materials.release();
     c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
@@ -299,6 +322,7 @@ int rtb_resize(rtb_ctx* c, uint32_t w, uint32_t h, uint32_t shadowSamples) {
     if (w == c->width && h == c->height && shadowSamples == c->samples) return RTB_OK;
     if ((uint64_t)((w + 31) / 32) * ((h + 31) / 32) * 1024ull * shadowSamples > 0xFFFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_resize: too many shadow rays per frame");
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    { const int rc = drainCopy(c); if (rc) return rc; }
     c->width = w; c->height = h; c->samples = shadowSamples; c->shadowSamplesProp = shadowSamples;
     return allocFrame(c);
 }
@@ -423,7 +447,7 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
     if (pass != RTB_PASS_INIT) { const int rc = checkReady(c); if (rc) return rc; }
     int rc = RTB_OK;
     switch (pass) {
-        case RTB_PASS_INIT: launch_init(c->seed.p, c->stream); break;
+        case RTB_PASS_INIT: if ((rc = waitCopy(c, {RTB_TGT_SEED}))) return rc; launch_init(c->seed.p, c->stream); break;
         case RTB_PASS_RAYGEN: rc = passRaygen(c, false); break;
         case RTB_PASS_SHADOW: rc = passShadow(c, false); break;
         case RTB_PASS_LIGHTING: rc = passShade(c, SHADE_LIGHTING); break;
@@ -431,6 +455,7 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
         case RTB_PASS_FRAME:
             if (c->countersOn) RTB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(TraceCounters), c->stream));
             RTB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+            if ((rc = waitCopy(c, {RTB_TGT_SEED}))) return rc;
             launch_init(c->seed.p, c->stream);
             RTB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
             if ((rc = passRaygen(c, true))) return rc;
@@ -484,9 +509,38 @@ int rtb_readback(rtb_ctx* c, rtb_target t, void* dst, size_t bytes) {
     return RTB_OK;
 }
 
+int rtb_readback_async(rtb_ctx* c, rtb_target t, void* dst, size_t bytes) {
+    if (!c || !dst) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    void* p; size_t n;
+    int rc = rtb_device_ptr(c, t, &p, &n);
+    if (rc) return rc;
+    if (bytes > n) return fail(c, RTB_ERR_ARG, "rtb_readback_async: more bytes requested than the target holds");
+    if ((rc = drainCopy(c))) return rc;   // one read-back in flight at a time
+    if (!c->copyStream) {
+        RTB_CUDA(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+        RTB_CUDA(c, cudaEventCreateWithFlags(&c->evReady, cudaEventDisableTiming));
+        RTB_CUDA(c, cudaEventCreateWithFlags(&c->evCopied, cudaEventDisableTiming));
+    }
+    RTB_CUDA(c, cudaEventRecord(c->evReady, c->stream));
+    RTB_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->evReady, 0));
+    RTB_CUDA(c, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, c->copyStream));
+    RTB_CUDA(c, cudaEventRecord(c->evCopied, c->copyStream));
+    c->copyTarget = (int)t;
+    return RTB_OK;
+}
+
+int rtb_readback_wait(rtb_ctx* c) {
+    if (!c) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (c->copyStream) RTB_CUDA(c, cudaEventSynchronize(c->evCopied));   // the host may read dst; the device-side guard (copyTarget) stays armed until the next writer has waited
+    return RTB_OK;
+}
+
 int rtb_untile(rtb_ctx* c, const void* tiledAll, uint32_t nranks, uint32_t slotsPerRank, void* out) {
     if (!c || !tiledAll || !nranks) return c ? fail(c, RTB_ERR_ARG, "rtb_untile: bad argument") : RTB_ERR_ARG;
     RTB_BIND(c);
+    if (!out) { const int rc = waitCopy(c, {RTB_TGT_RGBA8}); if (rc) return rc; }
     if (!c->width) return fail(c, RTB_ERR_STATE, "rtb_untile before rtb_resize");
     FrameMap fm = c->fm;
     fm.nranks = nranks; fm.rank = 0;
@@ -511,6 +565,7 @@ int rtb_sync(rtb_ctx* c) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->copyStream) RTB_CUDA(c, cudaStreamSynchronize(c->copyStream));
     return RTB_OK;
 }
 

@@ -25,7 +25,7 @@ NO_HIT = np.float32(3.4028235e38)
 
 EXPORTS = [
     "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_option", "rtb_set_stream", "rtb_resize", "rtb_upload",
-    "rtb_upload_skybox", "rtb_build_accel", "rtb_refit_accel", "rtb_accel_info_get", "rtb_dispatch", "rtb_readback", "rtb_device_ptr", "rtb_sync",
+    "rtb_upload_skybox", "rtb_build_accel", "rtb_refit_accel", "rtb_accel_info_get", "rtb_dispatch", "rtb_readback", "rtb_readback_async", "rtb_readback_wait", "rtb_device_ptr", "rtb_sync",
     "rtb_counters_get", "rtb_probe_l2_read_gbs", "rtb_last_frame_ms", "rtb_trace_rays", "rtb_occlusion_rays", "rtb_untile", "rtb_pack_triangle",
     "rtb_pack_light_directional", "rtb_pack_light_point", "rtb_pack_material", "rtb_pack_camera", "rtb_load_hdr", "rtb_write_png",
     "rtb_gen_soup", "rtb_gen_heightfield",
@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         L.rtb_accel_info_get.argtypes = [vp, C.POINTER(AccelInfo)]
         L.rtb_dispatch.argtypes = [vp, C.c_int]
         L.rtb_readback.argtypes = [vp, C.c_int, vp, sz]
+        L.rtb_readback_async.argtypes = [vp, C.c_int, vp, sz]
+        L.rtb_readback_wait.argtypes = [vp]
         L.rtb_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
         L.rtb_sync.argtypes = [vp]
         L.rtb_counters_get.argtypes = [vp, C.POINTER(Counters)]
@@ -301,6 +303,8 @@ class Context:
         return out
 
     def readback_into(self, target, ptr, nbytes): self._ck(self.L.rtb_readback(self.h, target, C.c_void_p(ptr), nbytes))
+    def readback_async_into(self, target, ptr, nbytes): self._ck(self.L.rtb_readback_async(self.h, target, C.c_void_p(ptr), nbytes))
+    def readback_wait(self): self._ck(self.L.rtb_readback_wait(self.h))
 
     def device_ptr(self, target):
         p, n = C.c_void_p(), C.c_size_t()

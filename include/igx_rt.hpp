@@ -731,6 +731,9 @@ public:
         note(rc);
         return rc == 0;
     }
+    // the same without blocking (presentToCpu + fence): dst must stay valid until waitPixels(); rendering may go on meanwhile
+    bool readPixelsAsync(u32* dst) { const int rc = rtb_readback_async(device.get(), RTB_TGT_RGBA8, dst, usz(res.x) * res.y * 4); note(rc); return rc == 0; }
+    bool waitPixels() { const int rc = rtb_readback_wait(device.get()); note(rc); return rc == 0; }
 private:
     void note(int rc) { if (rc && !lastError) lastError = rc; }
 };

@@ -174,6 +174,13 @@ int  rtb_dispatch(rtb_ctx* ctx, rtb_pass pass);
 /* replaces Graphics::presentToCpu + wait (ref: src/rt/raytracing_interface.cpp:222-226,
  * IGNIS/api/opengl/src/graphics/gl_graphics.cpp:221-242); blocks until the copy has landed */
 int  rtb_readback(rtb_ctx* ctx, rtb_target target, void* dst, size_t bytes);
+/* The same copy without blocking the host, the way the reference's presentToCpu works (a PBO copy plus a fence, picked up later:
+ * ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:221-256,546-595).  The copy is ordered after everything dispatched so
+ * far and runs on its own stream; following dispatches overlap it, and only the pass that overwrites `target` waits for it on
+ * the device.  dst should be page-locked memory; it may be read after rtb_readback_wait (or rtb_sync).  One read-back is in
+ * flight at a time: a second call first waits for the previous one. */
+int  rtb_readback_async(rtb_ctx* ctx, rtb_target target, void* dst, size_t bytes);
+int  rtb_readback_wait(rtb_ctx* ctx);
 /* device address of a target (for zero-copy consumers such as an NCCL gather); valid until the next rtb_resize */
 int  rtb_device_ptr(rtb_ctx* ctx, rtb_target target, void** out_ptr, size_t* out_bytes);
 /* Multi-GPU presentation (no reference counterpart; the reference is single-GPU).  With RTB_OPT_TILE_COUNT = n > 1 each

@@ -562,3 +562,36 @@ def test_packets_identical_at_full_4k(rtb):
     for pk in (1, 3, 2):
         for a, b in zip(out[0], out[pk]):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_async_readback_pipelines_frames(rtb, sky):
+    """rtb_readback_async (the reference's presentToCpu + fence): frame N is copied out while frame N+1 renders; the pass
+    that overwrites the target waits for the copy, so each buffer holds exactly its own frame."""
+    w, h = 640, 360
+    scene = rtb.niels_scene(0.0)
+    ctx = make_ctx(rtb, scene, sky, w, h, 1, rtb.ACCEL_BVH)
+    poses = [dict(eye=(6, 5, 12)), dict(eye=(4, 2, -2)), dict(eye=(6, 5, 12), yaw=0.4)]
+    want = []
+    for pose in poses:   # reference frames, synchronous read-back
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, **pose))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+        ctx.dispatch(rtb.PASS_FRAME)
+        want.append(ctx.readback(rtb.TGT_RGBA8).copy())
+    assert not np.array_equal(want[0], want[1])
+    bufs = [np.zeros((h, w), np.uint32) for _ in poses]
+    for pose, buf in zip(poses, bufs):   # pipelined: no host wait between frames
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, **pose))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+        ctx.dispatch(rtb.PASS_FRAME)
+        ctx.readback_async_into(rtb.TGT_RGBA8, buf.ctypes.data, buf.nbytes)
+    ctx.readback_wait()
+    for got, ref in zip(bufs, want):
+        assert np.array_equal(got, ref)
+    # a synchronous read-back and a resize with a copy in flight
+    ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+    ctx.dispatch(rtb.PASS_FRAME)
+    ctx.readback_async_into(rtb.TGT_RGBA8, bufs[0].ctypes.data, bufs[0].nbytes)
+    assert np.array_equal(ctx.readback(rtb.TGT_RGBA8), want[2])
+    ctx.resize(320, 180, 1)
+    assert np.array_equal(bufs[0], want[2])
+    ctx.close()
