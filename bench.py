@@ -89,7 +89,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.monotonic()] + [x.strip() for x in line.split(",")])
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi was started before the warm-up so that its start-up (and the driver queries it
+        makes) does not fall into a timed region that may be only a few milliseconds long."""
+        self.t_begin = time.monotonic()
 
     def stop(self):
         if not self.proc:
@@ -100,13 +105,18 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows if len(r) >= 8]
+        inside = [r[1:] for r in self.rows if len(r) >= 8 and r[0] >= getattr(self, "t_begin", 0.0)]
+        window = "timed region"
+        if len(inside) < 2:   # a timed region shorter than the 200 ms sampling period: the warm-up ran the same load just before
+            inside, window = rows, "warm-up + timed region"
+        sm = [float(r[0]) for r in inside if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        reasons = sorted({names[i] for r in inside for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    power_w_max=max(pw) if pw else None, samples=len(sm))
+                    power_w_max=max(pw) if pw else None, samples=len(sm), window=window)
 
 
 def cpu_sample_pixels(w, h, n, seed=1234):
@@ -318,13 +328,16 @@ def main():
     rays_per_frame = w * h * spp + int(hits_local.item()) * samples
 
     def timed(e2e: bool, steps: int, warmup: int, sample_clocks: bool):
+        sampler = ClockSampler(local_rank) if sample_clocks and rank == 0 else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)   # nvidia-smi is up and sampling before any frame is issued
         ctx.upload(rtb.BUF_SEED, seed0)
         for _ in range(warmup):
             frame(e2e)
         barrier()
-        sampler = ClockSampler(local_rank) if sample_clocks and rank == 0 else None
         if sampler:
-            sampler.start()
+            sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
