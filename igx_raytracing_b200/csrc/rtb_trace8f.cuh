@@ -68,7 +68,7 @@ RTB_DI void walkFrustumPacket(const TraceArgs& a, uint2* stack, const uint8_t* p
         const uint32_t childSlot = (bit - 24u) ^ woct;
         const uint32_t nodeIdx = G.x + (uint32_t)__popc(hits & 0xFFu & ~(0xFFFFFFFFu << childSlot));
         G.y &= ~(1u << bit);
-        if (G.y & 0xFF000000u) { stack[sp] = G; ++sp; }
+        if (G.y & 0xFF000000u) { if (lane == 0) stack[sp] = G; ++sp; }   // one writer; __syncwarp below orders it before any pop
         const char* p = reinterpret_cast<const char*>(a.nodes8) + (size_t)nodeIdx * 128u;
         uint4 n0, n1;
         ldg256(p, n0, n1);
@@ -152,7 +152,7 @@ RTB_DI void walkFrustumPacket(const TraceArgs& a, uint2* stack, const uint8_t* p
 
         // ---- descend, or pop ------------------------------------------------------------------------------------------
         if (top) G = make_uint2(n1.x, (top << 24) | imask);
-        else if (sp > 0) { --sp; G = stack[sp]; }
+        else if (sp > 0) { __syncwarp(); --sp; G = stack[sp]; __syncwarp(); }   // (the second barrier: the slot is not rewritten before every lane has read it)
         else break;
     }
 }

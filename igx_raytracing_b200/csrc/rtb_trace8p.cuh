@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_PK_MINBLOCKS) k_trace_cwbvh
                 const uint32_t childSlot = (bit - 24u) ^ woct;
                 const uint32_t nodeIdx = G.x + (uint32_t)__popc(hits & 0xFFu & ~(0xFFFFFFFFu << childSlot));
                 G.y &= ~(1u << bit);
-                if (G.y & 0xFF000000u) { stack[sp] = G; ++sp; }
+                if (G.y & 0xFF000000u) { if (lane == 0) stack[sp] = G; ++sp; }   // one writer; __syncwarp below orders it before any pop
                 uint4 n0, n1, wnx, wny, wnz, wfx, wfy, wfz;
                 const char* p = reinterpret_cast<const char*>(a.nodes8) + (size_t)nodeIdx * 128u;
                 const char* p2 = reinterpret_cast<const char*>(a.nodes8Alias) + (size_t)nodeIdx * 128u;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_PK_MINBLOCKS) k_trace_cwbvh
 
                 // ---- descend, or pop ----------------------------------------------------------------------------------
                 if (top) G = make_uint2(n1.x, (top << 24) | (n0.w >> 24));
-                else if (sp > 0) { --sp; G = stack[sp]; }
+                else if (sp > 0) { __syncwarp(); --sp; G = stack[sp]; __syncwarp(); }   // (the second barrier: the slot is not rewritten before every lane has read it)
                 else break;
             }
         }
