@@ -18,6 +18,8 @@
 // peak with 8 x LDG.128 per node), so a node is fetched with four LDG.256: header, and one granule per axis holding
 // (lo, hi); the near / far assignment is a pair of complementary predicated loads with swapped destinations.
 //
+// Child order of the occlusion rays: nearest first like the nearest-hit search; farthest first visits 27.3 instead of
+// 28.0 nodes per ray on the soup frame and runs 2 % slower (2.17 vs 2.14 ms) — the order hardly matters there.
 // Also measured and rejected for the node fetch (occlusion launch, 2.14 ms with the four LDG.256): eight 16-byte texture
 // fetches of the same record through a linear uint4 texture object, near / far by texel index: 2.42 ms.
 //

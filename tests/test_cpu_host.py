@@ -184,6 +184,27 @@ def test_no_cpu_fallback(rtb):
     assert "CUDA" in str(e.value) or "device" in str(e.value)
 
 
+def test_null_context_is_an_argument_error(rtb):
+    """Every context-taking entry point rejects a NULL context with RTB_ERR_ARG instead of touching it (no GPU needed)."""
+    L = rtb.lib()
+    null = C.c_void_p(None)
+    buf = (C.c_uint8 * 16)()
+    d = C.c_double()
+    assert L.rtb_refit_accel(null) == 1
+    assert L.rtb_build_accel(null, 1) == 1
+    assert L.rtb_dispatch(null, 5) == 1
+    assert L.rtb_readback(null, 5, buf, 16) == 1
+    L.rtb_readback_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.rtb_readback_wait.argtypes = [C.c_void_p]
+    L.rtb_probe_l2_read_gbs.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]
+    assert L.rtb_readback_async(null, 5, buf, 16) == 1
+    assert L.rtb_readback_wait(null) == 1
+    assert L.rtb_probe_l2_read_gbs(null, 1 << 20, C.byref(d)) == 1
+    assert L.rtb_set_option(null, 4, 3) == 1
+    assert L.rtb_sync(null) == 1
+    L.rtb_destroy(null)   # a no-op
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "igx_raytracing_b200")):
         for fn in files:

@@ -595,3 +595,28 @@ def test_async_readback_pipelines_frames(rtb, sky):
     ctx.resize(320, 180, 1)
     assert np.array_equal(bufs[0], want[2])
     ctx.close()
+
+
+def test_api_state_and_argument_errors(rtb):
+    """Error behaviour of the entry points added for refit / packets / read-back: codes, not aborts."""
+    scene = soup_scene(rtb, 2000)
+    ctx = rtb.Context(max_triangles=2000)
+    ctx.resize(64, 64, 1)
+    ctx.upload_scene(scene, None)
+    ctx.refit_accel()                                   # no tree yet: falls back to a build of the current mode (brute = nothing to do)
+    assert ctx.accel_info().refits == 0
+    ctx.build_accel(rtb.ACCEL_BVH2)
+    ctx.refit_accel()                                   # binary tree: rebuilt, not refitted
+    assert ctx.accel_info().refits == 0 and ctx.accel_info().mode == rtb.ACCEL_BVH2
+    ctx.build_accel(rtb.ACCEL_BVH)
+    ctx.refit_accel()
+    assert ctx.accel_info().refits == 1
+    with pytest.raises(rtb.RtbError):
+        ctx.set_option(rtb.OPT_PRIMARY_PACKETS, 4)
+    buf = np.zeros(64 * 64 + 1, np.uint32)
+    with pytest.raises(rtb.RtbError):
+        ctx.readback_async_into(rtb.TGT_RGBA8, buf.ctypes.data, buf.nbytes)   # more bytes than the target holds
+    with pytest.raises(rtb.RtbError):
+        ctx.probe_l2_read_gbs(1024)
+    assert ctx.probe_l2_read_gbs(8 << 20) > 1000.0
+    ctx.close()
