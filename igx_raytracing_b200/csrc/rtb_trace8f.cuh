@@ -3,29 +3,36 @@
 //
 // rtb_trace8p.cuh walks the union of the nodes the 32 rays of an 8x4-pixel patch need, but every lane still tests all
 // eight child boxes of every node against its own ray: ~130 of the ~190 instructions per node, on a kernel bound by
-// instruction issue.  Camera rays of a patch share their origin and differ by a few pixel angles, so the patch can be
-// bounded by four thin frusta (its 4x2-pixel quadrants), each an interval ray: origin o, direction intervals
-// [dmin, dmax] per axis.  One lane tests ONE child box against ONE quadrant (8 children x 4 quadrants = 32 lanes):
+// instruction issue — although the warp only needs to know whether ANY ray enters a child.  Camera rays of a patch share
+// their origin and differ by a few pixel angles, so they are bounded by an interval ray: origin o, direction intervals
+// [dmin, dmax] per axis.  One lane tests ONE child box against the interval ray:
 //
 //     entry >= min over the interval of (near plane - o) / d,   exit <= max over the interval of (far plane - o) / d
 //
 // with interval end points widened by 2^-20 and the final comparison given 1e-5 of slack.  The test is conservative —
-// a child is visited whenever any ray of the quadrant could enter its (already padded, outward-rounded) box before the
+// a child is visited whenever any ray of the interval could enter its (already padded, outward-rounded) box before the
 // packet's largest nearest-hit distance — so the set of triangles tested is a superset of what each ray needs, and the
 // triangles themselves are tested by every lane with the reference's exact Möller–Trumbore arithmetic and tie rule.
 // The hits are therefore bit-identical to the per-ray kernel's (tests/test_gpu_parity.py: packets 0 / 1 / 3 compared
 // with array equality, and against the brute-force loop).
 //
-// An axis on which a quadrant's directions straddle zero (or are tiny), and every axis when the rays of a packet do not
-// share one origin, is left unconstrained: correct, only slower.  The host picks this kernel for the Default projection
-// (one eye) when the patch is small against the leaf nodes (rtb_api.cu, primaryPackets).
+// Three walks, chosen per packet:
+//   walkFrustumPacket4          all 32 rays share the sign of every direction component (99.6 % of a frame): one interval
+//                               ray for the patch, 8 lanes per node, FOUR nodes per step
+//   walkFrustumPacket<PLAIN>    the patch crosses an axis plane of direction space but each 4x2-pixel quadrant has its
+//                               signs: one interval ray per quadrant, 8 children x 4 quadrants = 32 lanes, one node per step
+//   walkFrustumPacket<generic>  a quadrant's directions straddle zero on an axis (tested as a wedge there), or the rays of
+//                               the packet do not share one origin (every axis unconstrained: correct, only slow)
+// The host picks this kernel for the Default projection (one eye) when the patch is small against the leaf nodes
+// (rtb_api.cu, primaryPackets).
 #pragma once
 
 namespace rtb {
 
-// Measured on B200 (1M-triangle soup, 3840x2160): 4 blocks/SM (64 registers) 2.93 ms; 3 blocks (72 registers) 3.10 ms;
-// 5 blocks (48 registers, spills) 3.26 ms.  ncu (profiles/r1o_frustum_trace_full.md): issue slots 85 % busy, 143 instructions
-// per node visit against ~190 in rtb_trace8p.cuh.
+// Measured on B200 (1M-triangle soup, 3840x2160), nearest-hit launch: union packets 3.81 ms -> one node per step, per-quadrant
+// interval rays 2.93 ms (143 instructions per node; 3 blocks/SM 3.10 ms, 5 blocks 3.26 ms) -> mirrored fast path 2.43 ms
+// -> four nodes per step 1.26 ms (4 blocks/SM; 3 blocks 1.38 ms) -> fused with ray generation and G-buffer finish 1.38 ms
+// for what took 0.09 + 1.26 + 0.13.  ncu (profiles/r1z_trace_full.md): issue slots 79 % busy, L1 wavefronts 63 %.
 #ifndef RTB_FR_MINBLOCKS
 #define RTB_FR_MINBLOCKS 4
 #endif
