@@ -28,8 +28,10 @@ def make_ctx(rtb, scene, sky, w, h, samples, accel, **limits):
     return ctx
 
 
-def frame_both(rtb, oracle, scene, sky, cam_kwargs, w, h, samples, accel, cpu_offset=(0.0, 0.0), frames=1, limits=None):
+def frame_both(rtb, oracle, scene, sky, cam_kwargs, w, h, samples, accel, cpu_offset=(0.0, 0.0), frames=1, limits=None, packets=None):
     ctx = make_ctx(rtb, scene, sky, w, h, samples, accel, **(limits or {}))
+    if packets is not None:
+        ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
     cam = rtb.pack_camera(w, h, **cam_kwargs)
     ocam = oracle.camera(w, h, **cam_kwargs)
     assert np.array_equal(cam, ocam), "camera packing differs from the oracle"
@@ -128,11 +130,12 @@ def test_progressive_accumulation(rtb, oracle, sky):
     assert bad <= 1e-3 * w * h, f"{bad} accumulation texels differ"
 
 
-@pytest.mark.parametrize("projection", [1, 2, 3, 4, 5])
-def test_projection_modes(rtb, oracle, sky, projection):
+@pytest.mark.parametrize("packets", [2, 3])   # 2: the auto rule keeps these projections per ray; 3: frustum packets forced (eyes differ per half /
+@pytest.mark.parametrize("projection", [1, 2, 3, 4, 5])   # per pixel in the stereo modes: packets with several origins take the generic walk)
+def test_projection_modes(rtb, oracle, sky, projection, packets):
     w, h = 256, 128
     cam = dict(eye=(6, 5, 12), projection=projection, yaw=0.3)
-    got, ref = frame_both(rtb, oracle, rtb.niels_scene(0.0), sky, cam, w, h, 1, rtb.ACCEL_BVH)
+    got, ref = frame_both(rtb, oracle, rtb.niels_scene(0.0), sky, cam, w, h, 1, rtb.ACCEL_BVH, packets=packets)
     check_frame(got, ref, w, h, budget=1e-4, rgb_budget=1e-4)
 
 
