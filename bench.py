@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — Mrays/s (primary + shadow) and ms/frame of the hot path on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload soup1m|niels1080|heightfield10m]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--packets off|union|frustum|auto]
+                    [--workload soup1m|soup1m_far|niels360|niels1080|heightfield10m|niels8k16|soup8k16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step is one frame: init -> primary rays -> nearest hit -> shadow rays -> occlusion -> lighting + composite -> rgba8
@@ -38,6 +39,8 @@ WORKLOADS = {
     # SURVEY.md §8(d) camera for the same scene: the soup covers ~3.7 % of the frame
     "soup1m_far": dict(kind="soup", triangles=1_000_000, width=3840, height=2160, eye=(0.0, 0.0, 30.0), samples=1,
                        desc="configs[2] geometry with the survey camera eye (0,0,30): soup covers ~4 % of the frame"),
+    "niels360": dict(kind="niels", width=640, height=360, eye=(4.0, 2.0, -2.0), samples=1,
+                     desc="configs[0]: NielsScene (13 primitives) at 640x360, 1 spp primary + 1 shadow ray (the reference's own CPU-runnable case; the CPU baseline runs the whole frame)"),
     "niels1080": dict(kind="niels", width=1920, height=1080, eye=(4.0, 2.0, -2.0), samples=1,
                       desc="configs[1]: NielsScene (13 primitives) at 1920x1080, 1 spp primary + 1 shadow ray"),
     "heightfield10m": dict(kind="heightfield", grid=2236, width=1920, height=1080, eye=(0.0, 6.0, 13.0), pitch=0.45, samples=1,
