@@ -56,7 +56,7 @@ struct rtb_ctx {
     DevBuf<BvhNode> nodes; DevBuf<Node8> nodes8; DevBuf<TravTri> travTris;
     uint32_t nodeCount = 0; rtb_accel_mode accelMode = RTB_ACCEL_BRUTE; bool accelValid = false;
     BvhStats stats;
-    DevBuf<float> nodeBox; DevBuf<uint32_t> maxBits;   // refit scratch: 6 floats per node, largest |coordinate|
+    DevBuf<float> nodeBox; DevBuf<uint32_t> maxBits; DevBuf<double> areaSums;   // refit scratch: 6 floats per node, largest |coordinate|, SAH sums
     uint32_t builtTriangles = 0, refits = 0;
 
     // frame resources
@@ -273,7 +273,7 @@ void rtb_destroy(rtb_ctx* c) {
     if (c->evReady) cudaEventDestroy(c->evReady);
     if (c->evCopied) cudaEventDestroy(c->evCopied);
     c->triangles.release(); c->spheres.release(); c->cubes.release(); c->planes.release(); c->lights.release(); c->materials.release();
-    c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release();
+    c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release(); c->nodeBox.release(); c->maxBits.release(); c->areaSums.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->rays.release(); c->hits.release(); c->workCounter.release(); c->counters.release();
     c->rinRays.release(); c->rinHits.release(); c->rinObj.release(); c->rinT.release(); c->rinUv.release(); c->rinOcc.release(); c->rinOcc2.release();
@@ -420,14 +420,21 @@ int rtb_refit_accel(rtb_ctx* c) {
     RTB_BIND(c);
     if (c->accelMode != RTB_ACCEL_BVH || !c->nodeCount || c->builtTriangles != c->info.triangleCount || c->stats.levelFirst.size() < 2)
         return rtb_build_accel(c, c->accelMode);
-    RTB_CUDA(c, c->nodeBox.alloc((size_t)c->nodeCount * 6)); RTB_CUDA(c, c->maxBits.alloc(1));
+    RTB_CUDA(c, c->nodeBox.alloc((size_t)c->nodeCount * 6)); RTB_CUDA(c, c->maxBits.alloc(1)); RTB_CUDA(c, c->areaSums.alloc(2));
     launch_refit(c->triangles.p, c->info.triangleCount, c->travTris.p, c->info.triangleCount, c->nodes8.p, c->stats.levelFirst.data(),
-                 (uint32_t)c->stats.levelFirst.size() - 1, c->nodeBox.p, c->maxBits.p, c->stream);
+                 (uint32_t)c->stats.levelFirst.size() - 1, c->nodeBox.p, c->maxBits.p, c->areaSums.p, c->stream);
     RTB_CUDA(c, cudaGetLastError());
     float root[6];   // scene bounds for the packet rule (primaryPackets)
     RTB_CUDA(c, cudaMemcpyAsync(root, c->nodeBox.p, sizeof root, cudaMemcpyDeviceToHost, c->stream));
+    double sums[2];
+    RTB_CUDA(c, cudaMemcpyAsync(sums, c->areaSums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int a = 0; a < 3; ++a) { c->stats.lo[a] = root[a]; c->stats.hi[a] = root[3 + a]; }
+    {   // the builder's cost: (sum of node-box areas + sum of leaf-slot areas x triangle counts) / area of the scene bounds
+        const double dx = (double)root[3] - root[0], dy = (double)root[4] - root[1], dz = (double)root[5] - root[2];
+        const double rootArea = 2.0 * (dx * dy + dy * dz + dz * dx);
+        if (rootArea > 0.0) c->stats.sahCost = (float)((sums[0] + sums[1]) / rootArea);
+    }
     ++c->refits;
     c->accelValid = true;
     return RTB_OK;

@@ -65,9 +65,10 @@ void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint
 // rank 0: gathered [nranks][slotsPerRank] tiled pixels -> scan-line rgba8
 void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsPerRank, uint32_t* rgba8, cudaStream_t s);
 
-// refit of the 8-wide tree from the current triangle buffer (rtb_refit.cu); levelFirst is a HOST array of levels + 1 entries
+// refit of the 8-wide tree from the current triangle buffer (rtb_refit.cu); levelFirst is a HOST array of levels + 1 entries;
+// areaSums (2 doubles, device) receives the two sums of the SAH cost: node-box areas, leaf-slot areas x triangle counts
 void launch_refit(const TriangleRec* tris, uint32_t triCount, TravTri* tt, uint32_t ttCount, Node8* nodes, const uint32_t* levelFirst,
-                  uint32_t levels, float* nodeBox, uint32_t* maxBits, cudaStream_t s);
+                  uint32_t levels, float* nodeBox, uint32_t* maxBits, double* areaSums, cudaStream_t s);
 
 // rtb_probe.cu: L2 read bandwidth (GB/s) over a buffer of `bytes` read `passes` times; negative = -cudaError_t
 double measure_l2_read_gbs(size_t bytes, uint32_t passes, cudaStream_t s);

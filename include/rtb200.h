@@ -162,7 +162,7 @@ int  rtb_build_accel(rtb_ctx* ctx, rtb_accel_mode mode);
  * the device instead of rebuilding it on the host — what a per-frame SceneGraph::update of dirty triangle ranges needs
  * (ref: igx/src/helpers/scene_graph.cpp:267-323, test/scene/niels_scene.cpp:61-70).  Stream-ordered, no host work
  * beyond the launches.  Topology is kept, so hits stay exact but traversal cost grows with the deformation; rebuild
- * when rtb_accel_info.sah_cost matters.  Falls back to rtb_build_accel when there is no 8-wide tree of the current
+ * when it matters: rtb_accel_info.sah_cost is recomputed by every refit.  Falls back to rtb_build_accel when there is no 8-wide tree of the current
  * triangle count (first call, other mode, count changed). */
 int  rtb_refit_accel(rtb_ctx* ctx);
 int  rtb_accel_info_get(const rtb_ctx* ctx, rtb_accel_info* out);

@@ -426,8 +426,10 @@ def test_refit_unmoved_reproduces_the_build(rtb):
     ctx = make_ctx(rtb, scene, None, 64, 64, 1, rtb.ACCEL_BVH, max_triangles=n_tri)
     nodes0, tris0 = ctx.accel_bytes(rtb.TGT_ACCEL_NODES), ctx.accel_bytes(rtb.TGT_ACCEL_TRIANGLES)
     assert nodes0.size == ctx.accel_info().node_count * 128 and tris0.size == n_tri * 48
+    cost0 = ctx.accel_info().sah_cost
     ctx.refit_accel()
     assert ctx.accel_info().refits == 1
+    assert abs(ctx.accel_info().sah_cost - cost0) <= 1e-3 * cost0, "the refit recomputes the builder's SAH cost"
     assert np.array_equal(ctx.accel_bytes(rtb.TGT_ACCEL_NODES), nodes0)
     assert np.array_equal(ctx.accel_bytes(rtb.TGT_ACCEL_TRIANGLES), tris0)
     ctx.close()
@@ -441,6 +443,7 @@ def test_refit_after_motion_equals_brute(rtb, packets):
     scene = soup_scene(rtb, n_tri)
     ctx = make_ctx(rtb, scene, None, w, h, 1, rtb.ACCEL_BVH, max_triangles=n_tri)
     ctx.set_option(rtb.OPT_PRIMARY_PACKETS, packets)
+    cost_built = ctx.accel_info().sah_cost
     tris = scene["triangles"].copy().view(np.float32).reshape(n_tri, 12)
     rng = np.random.default_rng(3)
     lo, hi = 20000, 60000                                    # the dirty range
@@ -459,6 +462,8 @@ def test_refit_after_motion_equals_brute(rtb, packets):
     ctx.dispatch(rtb.PASS_FRAME)
     got = (ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8))
     assert ctx.accel_info().refits == 1
+    cost_refit = ctx.accel_info().sah_cost   # relative to the area of the scene bounds, which the outliers enlarged
+    assert np.isfinite(cost_refit) and cost_refit > 0 and abs(cost_refit - cost_built) > 0.05 * cost_built, "sah_cost follows the deformation"
     ctx.close()
     scene2 = dict(scene, triangles=moved.copy())
     ref_ctx = make_ctx(rtb, scene2, None, w, h, 1, rtb.ACCEL_BRUTE, max_triangles=n_tri)
