@@ -273,3 +273,15 @@ def test_png_export_roundtrip(rtb, tmp_path, monkeypatch, stored):
     assert np.array_equal(np.array(Image.open(path)).view(np.uint32)[..., 0], big)
     size = os.path.getsize(path)
     assert (size > big.nbytes) == stored
+
+
+def test_example_app_builds_and_fails_loudly_without_a_gpu(rtb, tmp_path):
+    """examples/niels_export.cpp (the reference's demo, headless) compiles against the facade; without a device it says so."""
+    exe = str(tmp_path / "niels_export")
+    libdir = os.path.dirname(rtb.LIB_PATH)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "niels_export.cpp"),
+                           "-L", libdir, "-lrtb200", f"-Wl,-rpath,{libdir}", "-o", exe])
+    r = subprocess.run([exe, str(tmp_path / "frame")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode == 2 and "no usable CUDA device" in r.stdout

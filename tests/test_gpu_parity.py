@@ -628,3 +628,21 @@ def test_api_state_and_argument_errors(rtb):
         ctx.probe_l2_read_gbs(1024)
     assert ctx.probe_l2_read_gbs(8 << 20) > 1000.0
     ctx.close()
+
+
+def test_example_app_exports_a_png(rtb, tmp_path):
+    """examples/niels_export.cpp end to end: animated spheres for a few frames, then the export path at 480x270, 4 samples."""
+    import os
+    import subprocess
+    from PIL import Image
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "niels_export")
+    libdir = os.path.dirname(rtb.LIB_PATH)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "niels_export.cpp"),
+                    "-L", libdir, "-lrtb200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    out = str(tmp_path / "frame")
+    r = subprocess.run([exe, out, "480", "270", "4"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "wrote" in r.stdout, r.stdout
+    im = np.array(Image.open(out + ".png"))
+    assert im.shape == (270, 480, 4)
+    assert len(np.unique(im.reshape(-1, 4), axis=0)) > 500, "a real picture: ground plane, spheres, cubes, sky"
