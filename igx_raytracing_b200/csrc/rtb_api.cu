@@ -72,6 +72,7 @@ struct rtb_ctx {
     uint32_t packetsOpt = 2;          // RTB_OPT_PRIMARY_PACKETS: 0 off, 1 union packets, 2 auto, 3 frustum packets
     int lastPrimaryPackets = 0;       // PACKETS_* of the last camera-ray launch
     uint32_t fuseOpt = 1;             // RTB_OPT_FUSE_PRIMARY
+    uint32_t releaseBuild = 0;        // RTB_OPT_SHADER_BUILD: 0 = DEBUG build of the reference shaders (what ships), 1 = RELEASE
 
     // rays-in scratch
     DevBuf<RayRec> rinRays; DevBuf<TriHit> rinHits; DevBuf<uint32_t> rinObj; DevBuf<float> rinT; DevBuf<float2> rinUv; DevBuf<uint8_t> rinOcc, rinOcc2;
@@ -99,6 +100,7 @@ SceneView sceneView(const rtb_ctx* c) {
     v.skybox = c->skyW ? c->skybox.p : nullptr; v.skyW = c->skyW; v.skyH = c->skyH;
     v.info = c->info;
     v.nodes = c->nodes.p; v.nodes8 = c->nodes8.p; v.travTris = c->travTris.p; v.nodeCount = c->nodeCount;
+    v.releaseBuild = c->releaseBuild;
     v.useBvh = !c->accelValid ? ACCEL_KIND_BRUTE : (c->accelMode == RTB_ACCEL_BVH ? ACCEL_KIND_CWBVH : (c->accelMode == RTB_ACCEL_BVH2 ? ACCEL_KIND_BVH2 : ACCEL_KIND_BRUTE));
     return v;
 }
@@ -146,17 +148,23 @@ int drainCopy(rtb_ctx* c) {
     return RTB_OK;
 }
 
-int checkReady(rtb_ctx* c) {
-    if (!c->width || !c->height) return fail(c, RTB_ERR_STATE, "rtb_dispatch before rtb_resize");
-    if (!c->cameraSet) return fail(c, RTB_ERR_STATE, "rtb_dispatch before the camera was uploaded");
-    if (c->camera.width != c->width || c->camera.height != c->height)
-        return fail(c, RTB_ERR_STATE, "camera.width/height differ from the size given to rtb_resize");
+// scene counts against the capacities of rtb_create, and the acceleration structure against the triangle buffer:
+// shared by the dispatch path and the rays-in entry points (both index the scene buffers by these counts)
+int checkScene(rtb_ctx* c) {
     if (c->accelMode != RTB_ACCEL_BRUTE && !c->accelValid && c->info.triangleCount)
         return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
     if (c->info.triangleCount > c->limits.max_triangles || c->info.sphereCount > c->limits.max_spheres || c->info.cubeCount > c->limits.max_cubes ||
         c->info.planeCount > c->limits.max_planes || c->info.lightCount > c->limits.max_lights || c->info.materialCount > c->limits.max_materials)
         return fail(c, RTB_ERR_CAPACITY, "scene info counts exceed the capacities given to rtb_create");
     return RTB_OK;
+}
+
+int checkReady(rtb_ctx* c) {
+    if (!c->width || !c->height) return fail(c, RTB_ERR_STATE, "rtb_dispatch before rtb_resize");
+    if (!c->cameraSet) return fail(c, RTB_ERR_STATE, "rtb_dispatch before the camera was uploaded");
+    if (c->camera.width != c->width || c->camera.height != c->height)
+        return fail(c, RTB_ERR_STATE, "camera.width/height differ from the size given to rtb_resize");
+    return checkScene(c);
 }
 
 // Camera rays of an 8x4-pixel patch are walked through the 8-wide tree as one packet (rtb_trace8f.cuh) when the patch is
@@ -209,7 +217,8 @@ int passRaygen(rtb_ctx* c, bool mark) {
 int passShadow(rtb_ctx* c, bool mark) {
     { const int rc = waitCopy(c, {RTB_TGT_SHADOW_BITS}); if (rc) return rc; }
     const SceneView sv = sceneView(c);
-    RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, c->samples) * 4, c->stream));
+    if (c->releaseBuild) launch_clear_hit_strips(c->fm, c->dirT.p, c->samples, c->bits.p, c->stream);
+    else RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, c->samples) * 4, c->stream));
     launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, c->stream);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     launch_trace_any_bits(c->fm, sv, c->rays.p, c->fm.localSlots * c->samples, c->bits.p, c->workCounter.p, c->countersOn ? c->counters.p + 1 : nullptr, c->stream);
@@ -255,11 +264,11 @@ int rtb_create(rtb_ctx** out, int cudaDevice, const rtb_limits* limits) {
     if ((e = c->seed.alloc(1)) != cudaSuccess) return bail(e, "alloc seed");
     if ((e = c->workCounter.alloc(1)) != cudaSuccess) return bail(e, "alloc workCounter");
     if ((e = c->counters.alloc(2)) != cudaSuccess) return bail(e, "alloc counters");
-    cudaMemset(c->lights.p, 0, c->lights.bytes());
-    cudaMemset(c->materials.p, 0, c->materials.bytes());
-    cudaMemset(c->materialIndices.p, 0, c->materialIndices.bytes());
-    cudaMemset(c->seed.p, 0, sizeof(SeedRec));
-    cudaMemset(c->counters.p, 0, 2 * sizeof(TraceCounters));
+    if ((e = cudaMemsetAsync(c->lights.p, 0, c->lights.bytes(), c->stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
+    if ((e = cudaMemsetAsync(c->materials.p, 0, c->materials.bytes(), c->stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
+    if ((e = cudaMemsetAsync(c->materialIndices.p, 0, c->materialIndices.bytes(), c->stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
+    if ((e = cudaMemsetAsync(c->seed.p, 0, sizeof(SeedRec), c->stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
+    if ((e = cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(TraceCounters), c->stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     c->triangleMirror.resize((size_t)limits->max_triangles * sizeof(TriangleRec));
     *out = c;
     return RTB_OK;
@@ -293,16 +302,25 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             if (value > 3) return fail(c, RTB_ERR_ARG, "RTB_OPT_PRIMARY_PACKETS: 0 off, 1 union packets, 2 auto, 3 frustum packets");
             c->packetsOpt = value; return RTB_OK;
         case RTB_OPT_TILE_RANK:
-            c->tileRank = value;
-            if (c->width) { RTB_BIND(c); return allocFrame(c); }
+        case RTB_OPT_TILE_COUNT: {
+            // count is set before rank when both change (rtb.py, bench.py, the facade): a rank is valid against the count in force
+            const uint32_t rank = opt == RTB_OPT_TILE_RANK ? value : (value > c->tileRank ? c->tileRank : 0u);
+            const uint32_t count = opt == RTB_OPT_TILE_COUNT ? value : c->tileCount;
+            if (!count) return fail(c, RTB_ERR_ARG, "tile count must be >= 1");
+            if (rank >= count) return fail(c, RTB_ERR_ARG, "RTB_OPT_TILE_RANK must be below RTB_OPT_TILE_COUNT (set the count first)");
+            const uint32_t oldRank = c->tileRank, oldCount = c->tileCount;
+            c->tileRank = rank; c->tileCount = count;
+            if (c->width) {
+                RTB_BIND(c);
+                RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+                const int rc = allocFrame(c);
+                if (rc) { c->tileRank = oldRank; c->tileCount = oldCount; c->width = c->height = 0; makeFrameMap(c); return rc; }   // frame resources are gone: resize again
+            }
             return RTB_OK;
-        case RTB_OPT_TILE_COUNT:
-            if (!value) return fail(c, RTB_ERR_ARG, "tile count must be >= 1");
-            c->tileCount = value;
-            if (c->width) { RTB_BIND(c); return allocFrame(c); }
-            return RTB_OK;
-        case RTB_OPT_SKIP_PARITY_STORES:
-            return value ? fail(c, RTB_ERR_ARG, "RTB_OPT_SKIP_PARITY_STORES is reserved") : RTB_OK;
+        }
+        case RTB_OPT_SHADER_BUILD:
+            if (value > 1) return fail(c, RTB_ERR_ARG, "RTB_OPT_SHADER_BUILD: 0 = DEBUG build (default), 1 = RELEASE build");
+            c->releaseBuild = value; return RTB_OK;
     }
     return fail(c, RTB_ERR_ARG, "unknown option");
 }
@@ -324,7 +342,9 @@ int rtb_resize(rtb_ctx* c, uint32_t w, uint32_t h, uint32_t shadowSamples) {
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     { const int rc = drainCopy(c); if (rc) return rc; }
     c->width = w; c->height = h; c->samples = shadowSamples; c->shadowSamplesProp = shadowSamples;
-    return allocFrame(c);
+    const int rc = allocFrame(c);
+    if (rc) { c->width = c->height = 0; c->samples = 0; makeFrameMap(c); }   // a failed allocation leaves NO frame: dispatch reports "before rtb_resize"
+    return rc;
 }
 
 int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* src) {
@@ -333,18 +353,18 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
     void* dst = nullptr; size_t cap = 0;
     switch (id) {
         case RTB_BUF_CAMERA:
-            if (off + bytes > sizeof(CameraRec)) return fail(c, RTB_ERR_CAPACITY, "camera upload past 144 bytes");
+            if (off > sizeof(CameraRec) || bytes > sizeof(CameraRec) - off) return fail(c, RTB_ERR_CAPACITY, "camera upload past 144 bytes");
             std::memcpy(reinterpret_cast<uint8_t*>(&c->camera) + off, src, bytes); c->cameraSet = true;
             return RTB_OK;
         case RTB_BUF_SCENE_INFO: {
-            if (off + bytes > sizeof(SceneInfoRec)) return fail(c, RTB_ERR_CAPACITY, "scene info upload past 36 bytes");
+            if (off > sizeof(SceneInfoRec) || bytes > sizeof(SceneInfoRec) - off) return fail(c, RTB_ERR_CAPACITY, "scene info upload past 36 bytes");
             const uint32_t before = c->info.triangleCount;
             std::memcpy(reinterpret_cast<uint8_t*>(&c->info) + off, src, bytes);
             if (c->info.triangleCount != before) c->accelValid = false;
             return RTB_OK;
         }
         case RTB_BUF_SHADOW_PROPS:
-            if (off + bytes > 4) return fail(c, RTB_ERR_CAPACITY, "shadow properties upload past 4 bytes");
+            if (off > 4 || bytes > 4 - off) return fail(c, RTB_ERR_CAPACITY, "shadow properties upload past 4 bytes");
             std::memcpy(reinterpret_cast<uint8_t*>(&c->shadowSamplesProp) + off, src, bytes);
             if (c->width && c->shadowSamplesProp != c->samples) return rtb_resize(c, c->width, c->height, c->shadowSamplesProp);
             return RTB_OK;
@@ -361,7 +381,7 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
             break;
         default: return fail(c, RTB_ERR_ARG, "rtb_upload: unknown buffer id");
     }
-    if (off + bytes > cap) return fail(c, RTB_ERR_CAPACITY, "rtb_upload: range exceeds the capacity given to rtb_create");
+    if (off > cap || bytes > cap - off) return fail(c, RTB_ERR_CAPACITY, "rtb_upload: range exceeds the capacity given to rtb_create");
     if (!bytes) return RTB_OK;
     if (id == RTB_BUF_TRIANGLES) { std::memcpy(c->triangleMirror.data() + off, src, bytes); c->accelValid = false; }
     // pageable source: cudaMemcpyAsync stages it before returning, so the caller may reuse src at once (like GPUBuffer::flush)
@@ -385,6 +405,7 @@ int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     RTB_BIND(c);
     if (mode != RTB_ACCEL_BRUTE && mode != RTB_ACCEL_BVH && mode != RTB_ACCEL_BVH2) return fail(c, RTB_ERR_ARG, "rtb_build_accel: unknown mode");
     c->accelMode = mode;
+    c->accelValid = false;   // until this build has succeeded
     c->stats = BvhStats();
     c->nodeCount = 0; c->builtTriangles = 0; c->refits = 0;
     if (mode == RTB_ACCEL_BRUTE) { c->accelValid = true; return RTB_OK; }
@@ -394,8 +415,9 @@ int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     if (mode == RTB_ACCEL_BVH) {
         std::vector<Node8> nodes;
         buildCwbvh(tris, c->info.triangleCount, 0, nodes, tt, c->stats);
-        // every level can leave a node group and a postponed triangle group on the traversal stack (64 entries)
-        if (c->stats.maxDepth * 2 + 2 > 64) return fail(c, RTB_ERR_CAPACITY, "rtb_build_accel: 8-wide tree deeper than the traversal stack allows; use RTB_ACCEL_BVH2");
+        // every level can leave three entries on the per-ray traversal stack (64 entries): the remaining sibling group and,
+        // when a triangle group is postponed, that group plus the re-pushed node group (rtb_trace8.cuh, steps A and B)
+        if (c->stats.maxDepth * 3 + 2 > 64) return fail(c, RTB_ERR_CAPACITY, "rtb_build_accel: 8-wide tree deeper than the traversal stack allows; use RTB_ACCEL_BVH2");
         RTB_CUDA(c, cudaStreamSynchronize(c->stream));
         RTB_CUDA(c, c->nodes8.alloc(nodes.size()));
         if (!nodes.empty()) RTB_CUDA(c, cudaMemcpy(c->nodes8.p, nodes.data(), nodes.size() * sizeof(Node8), cudaMemcpyHostToDevice));
@@ -615,7 +637,7 @@ int rtb_trace_rays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* pr
     if (!c || (!rays && n)) return RTB_ERR_ARG;
     RTB_BIND(c);
     if (n > 0x7FFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_trace_rays: too many rays");
-    if (c->accelMode != RTB_ACCEL_BRUTE && !c->accelValid && c->info.triangleCount) return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
+    { const int rc = checkScene(c); if (rc) return rc; }
     if (!n) return RTB_OK;
     int rc = stageRays(c, rays, n, prev, nullptr);
     if (rc) return rc;
@@ -635,7 +657,7 @@ int rtb_occlusion_rays(rtb_ctx* c, const float* rays, uint64_t n, const float* m
     if (!c || (!rays && n) || (!occluded && n)) return RTB_ERR_ARG;
     RTB_BIND(c);
     if (n > 0x7FFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_occlusion_rays: too many rays");
-    if (c->accelMode != RTB_ACCEL_BRUTE && !c->accelValid && c->info.triangleCount) return fail(c, RTB_ERR_STATE, "triangles changed since the last rtb_build_accel");
+    { const int rc = checkScene(c); if (rc) return rc; }
     if (!n) return RTB_OK;
     int rc = stageRays(c, rays, n, prev, maxDist);
     if (rc) return rc;

@@ -307,7 +307,7 @@ template <int MODE>
 __global__ void __launch_bounds__(BRUTE_THREADS) k_trace_brute(const RayRec* __restrict__ rays, uint32_t n,
                                                                const TriangleRec* __restrict__ tris, uint32_t triCount,
                                                                TriHit* __restrict__ hits, uint32_t* __restrict__ bits, const FrameMap fm,
-                                                               uint8_t* __restrict__ bytes) {
+                                                               uint8_t* __restrict__ bytes, const bool rejectZeroEdge) {
     __shared__ float4 sTri[BRUTE_CHUNK * 3];
     const uint32_t slot = blockIdx.x * BRUTE_THREADS + threadIdx.x;
     const bool inRange = slot < n;
@@ -326,9 +326,10 @@ __global__ void __launch_bounds__(BRUTE_THREADS) k_trace_brute(const RayRec* __r
         if (!live) continue;
         for (uint32_t k = 0; k < cnt; ++k) {
             const float4 a0 = sTri[k * 3], a1 = sTri[k * 3 + 1], a2 = sTri[k * 3 + 2];
-            const vec3 p0 = mk3(a0.x, a0.y, a0.z);
+            const vec3 p0 = mk3(a0.x, a0.y, a0.z), e1 = mk3(a1.x, a1.y, a1.z) - p0;
+            if (rejectZeroEdge && e1.x == 0.0f && e1.y == 0.0f && e1.z == 0.0f) continue;   // DEBUG shader build: SH/primitive.glsl:248-253
             float u, v, t, aa;
-            if (!triCandidate(ro, rd, p0, mk3(a1.x, a1.y, a1.z) - p0, mk3(a2.x, a2.y, a2.z) - p0, u, v, t, aa)) continue;
+            if (!triCandidate(ro, rd, p0, e1, mk3(a2.x, a2.y, a2.z) - p0, u, v, t, aa)) continue;
             const uint32_t id = base + k;
             if (t <= 0.0f || id == prev || t >= hitT) continue;   // SH/primitive.glsl:268 (a NaN t passes, as in the reference)
             hitT = t; object = id; bu = u; bv = v;
@@ -393,7 +394,7 @@ void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, T
         launchTrace<MODE_CLOSEST>(sv, a, counters != nullptr, st);
     } else {
         FrameMap fm{};
-        k_trace_brute<MODE_CLOSEST><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, hits, nullptr, fm, nullptr);
+        k_trace_brute<MODE_CLOSEST><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, hits, nullptr, fm, nullptr, !sv.releaseBuild);
     }
 }
 
@@ -405,7 +406,7 @@ void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec
         a.bits = bits; a.fm = fm;
         launchTrace<MODE_ANY_BITS>(sv, a, counters != nullptr, st);
     } else {
-        k_trace_brute<MODE_ANY_BITS><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, bits, fm, nullptr);
+        k_trace_brute<MODE_ANY_BITS><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, bits, fm, nullptr, !sv.releaseBuild);
     }
 }
 
@@ -418,7 +419,7 @@ void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n,
         launchTrace<MODE_ANY_BYTES>(sv, a, false, st);
     } else {
         FrameMap fm{};
-        k_trace_brute<MODE_ANY_BYTES><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, nullptr, fm, occluded);
+        k_trace_brute<MODE_ANY_BYTES><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, nullptr, fm, occluded, !sv.releaseBuild);
     }
 }
 
@@ -471,7 +472,8 @@ __global__ void __launch_bounds__(256) k_finish_primary(const FrameMap fm, const
     encodeNormalGpu(objectNormal, ex, ey);
     const size_t px = (size_t)y * fm.w + x;
     dirT[px] = out0;
-    uvN[px] = make_float4(hit.uv.x, hit.uv.y, ubits(ex), ubits(ey));
+    if (!sv.releaseBuild || hit.hitT < NO_HIT)   // the RELEASE build stores uvObjectNormal for hits only (SH/raygen.comp:46-51)
+        uvN[px] = make_float4(hit.uv.x, hit.uv.y, ubits(ex), ubits(ey));
 }
 void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits, float4* dirT, float4* uvN, cudaStream_t st) {
     if (!fm.localSlots) return;
@@ -619,6 +621,25 @@ void launch_shadowgen(const FrameMap& fm, const SceneView& sv, const CameraRec* 
     k_shadowgen<<<(n + 255) / 256, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, rays, bits);
 }
 
+// RELEASE shader build: one thread per shadow word (a 16x2 pixel strip of one sample)
+__global__ void __launch_bounds__(256) k_clear_hit_strips(const FrameMap fm, const float4* __restrict__ dirT, uint32_t samples, uint32_t* __restrict__ bits) {
+    const uint32_t tilesX = (fm.w + 15u) >> 4, tilesY = (fm.h + 1u) >> 1, perSample = tilesX * tilesY;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= perSample) return;
+    const uint32_t tx = i % tilesX, ty = i / tilesX;
+    bool any = false;
+    for (uint32_t l = 0; l < 32u && !any; ++l) {
+        const uint32_t x = tx * 16u + (l & 15u), y = ty * 2u + (l >> 4);
+        if (x < fm.w && y < fm.h && fbits(__ldg(dirT + (size_t)y * fm.w + x).w) != NO_RAY_HIT) any = true;
+    }
+    if (any) for (uint32_t s = 0; s < samples; ++s) bits[i + s * perSample] = 0u;
+}
+void launch_clear_hit_strips(const FrameMap& fm, const float4* dirT, uint32_t samples, uint32_t* bits, cudaStream_t st) {
+    const uint32_t n = ((fm.w + 15u) >> 4) * ((fm.h + 1u) >> 1);
+    if (!n) return;
+    k_clear_hit_strips<<<(n + 255) / 256, 256, 0, st>>>(fm, dirT, samples, bits);
+}
+
 __global__ void __launch_bounds__(256) k_occlusion_others(const SceneView sv, RayRec* __restrict__ rays, uint32_t n, uint8_t* __restrict__ occluded) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -688,7 +709,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
         }
         // imageStore to rgba16f (alpha 1 on a hit; the shipped DEBUG shader stores vec4(0) on a miss)
         lx = f2h_rn(light.x); ly = f2h_rn(light.y); lz = f2h_rn(light.z);
-        if (lighting) lighting[px] = make_uint2(lx | (ly << 16), lz | ((isHit ? 0x3C00u : 0u) << 16));
+        if (lighting && (isHit || !sv.releaseBuild)) lighting[px] = make_uint2(lx | (ly << 16), lz | ((isHit ? 0x3C00u : 0u) << 16));
         if (!DO_COMP) return;
     } else {
         const uint2 lv = __ldg(lighting + px);
@@ -708,6 +729,8 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
         color = shade(m, NdotV, light, reflected);
     }
     color = mix(color, mk3(0.0f, 0.0f, 0.0f), 0.0f);   // cloud term is vec4(0) (SH/composite.comp:93-97)
+    if (!sv.releaseBuild && (isnan(color.x) || isnan(color.y) || isnan(color.z)))
+        color = mk3(0.0f, 0.0f, 10000.0f);             // DEBUG build: NaN shown as bright blue (SH/composite.comp:236-239)
     if (cam.flags & CAMERA_USE_SUPERSAMPLING) {          // SH/composite.comp:249-257
         const uint32_t sampleCount = __ldg(&seed->sampleCount);
         if (sampleCount > 1) { const float4 p = accum[px]; color = color + mk3(p.x, p.y, p.z); }

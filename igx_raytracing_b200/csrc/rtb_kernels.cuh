@@ -22,6 +22,7 @@ struct SceneView {
     SceneInfoRec info;            // host mirror of the reference's SceneData UBO, passed by value
     const BvhNode* nodes; const Node8* nodes8; const TravTri* travTris; uint32_t nodeCount;   // of the structure in use
     uint32_t useBvh;              // ACCEL_KIND_*
+    uint32_t releaseBuild;        // RTB_OPT_SHADER_BUILD: 0 = the reference's DEBUG shader build (what ships), 1 = RELEASE
 };
 enum : uint32_t { ACCEL_KIND_BRUTE = 0, ACCEL_KIND_CWBVH = 1, ACCEL_KIND_BVH2 = 2 };
 
@@ -50,6 +51,9 @@ void launch_shadowgen(const FrameMap& fm, const SceneView& sv, const CameraRec* 
 // any-hit over the triangles; sets the (pixel, sample) bit of every occluded slot
 void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits,
                            uint32_t* workCounter, TraceCounters* counters, cudaStream_t s);
+// RELEASE shader build only: zero the shadow words of the 16x2 strips that hold at least one hit pixel (the reference's
+// subgroups without hits leave early and store nothing: nv_all.shadow.comp:69-82); the DEBUG build zeroes every word
+void launch_clear_hit_strips(const FrameMap& fm, const float4* dirT, uint32_t samples, uint32_t* bits, cudaStream_t s);
 // any-hit, one byte per ray (rays-in mode)
 void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n, uint8_t* occluded, uint32_t* workCounter,
                             cudaStream_t s);

@@ -34,7 +34,8 @@ namespace rtb {
 #endif
 constexpr int TOP8_NODES = RTB_CW_TOP_NODES;   // 16 KB of shared memory: the breadth-first top of the tree (0 = not staged)
 constexpr int SM_STACK = 8;          // 16 KB of shared memory per 256-thread block
-constexpr int LOCAL_STACK = 56;      // rtb_build_accel refuses trees that could need more than SM_STACK + LOCAL_STACK entries
+constexpr int LOCAL_STACK = 56;      // a level can leave 3 entries (sibling group; postponed triangles + the re-pushed node group):
+                                     // rtb_build_accel refuses trees with 3 * depth + 2 > SM_STACK + LOCAL_STACK
 #ifndef RTB_CW_REFILL
 #define RTB_CW_REFILL 22
 #endif

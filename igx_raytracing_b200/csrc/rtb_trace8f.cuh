@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh
                 encodeNormalGpu(objectNormal, ex, ey);
                 const size_t px = (size_t)pxY * f.fm.w + pxX;
                 f.dirT[px] = out0;
-                f.uvN[px] = make_float4(hit.uv.x, hit.uv.y, ubits(ex), ubits(ey));
+                if (!f.sv.releaseBuild || hit.hitT < NO_HIT) f.uvN[px] = make_float4(hit.uv.x, hit.uv.y, ubits(ex), ubits(ey));
             }
         } else if (slot < a.n) {
             *reinterpret_cast<float4*>(a.hits + slot) = *reinterpret_cast<float4*>(&h);

@@ -358,9 +358,9 @@ public:
         cl->add([this](rtb_ctx* c) {
             if (skyboxDirty) { skyboxDirty = false; const int rc = rtb_upload_skybox(c, skyW, skyH, skyboxPixels.empty() ? nullptr : skyboxPixels.data()); if (rc) return rc; }
             if (geometryDirty) {
-                const bool rebuild = topologyDirty;
+                const int rc = topologyDirty ? rtb_build_accel(c, accelMode) : rtb_refit_accel(c);
+                if (rc) return rc;   // stays dirty: the next frame tries again
                 geometryDirty = topologyDirty = false;
-                return rebuild ? rtb_build_accel(c, accelMode) : rtb_refit_accel(c);
             }
             return 0;
         });
@@ -600,7 +600,9 @@ public:
             auto next = [this]() { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; return f32(f64(lcg >> 11) / f64(1ull << 53) * 2000.0 - 1000.0); };
             seed.cpuOffsetX = next(); seed.cpuOffsetY = next();
         }
-        rtb_upload(device.get(), RTB_BUF_SEED, 0, 24, &seed);   // seed->flush(0, 16) + the counters the GPU owns restart with it
+        // composite_task.cpp:243: seedBuffer->flush(0, offsetof(Seed, sampleOffset)) — 20 bytes; sampleOffset is owned by the GPU
+        // (init.comp increments it) and keeps counting across updates
+        rtb_upload(device.get(), RTB_BUF_SEED, 0, offsetof(Seed, sampleOffset), &seed);
         raygen.update(dt); shadow.update(dt);
     }
     // composite_task.cpp:249-277: FlushBuffer(seed), init, children, composite

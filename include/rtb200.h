@@ -119,8 +119,14 @@ typedef enum rtb_option {
                                  fetch serves 32 rays and counts once) */
     RTB_OPT_TILE_RANK = 1,    /* multi-GPU screen partition: this context renders tiles t with t % count == rank */
     RTB_OPT_TILE_COUNT = 2,
-    RTB_OPT_SKIP_PARITY_STORES = 3,/* 0/1: RELEASE-shader behaviour (no uvObjectNormal/lighting store on misses) is NOT
-                                      modelled; reserved, must be 0 */
+    RTB_OPT_SHADER_BUILD = 3,      /* which build of the reference shaders the passes behave like (ref: res/shaders/compile.sh:3-9).
+                                      0 (default) = DEBUG, what the shipped .spv binaries are: every pass stores for every pixel
+                                      (uvObjectNormal and a zero lighting texel on misses, zero shadow words for subgroups
+                                      without hits: raygen.comp:46-51, nv_all.shadow.comp:69-82, nv_all.lighting.comp:55-62),
+                                      triangles with p1 == p0 are rejected (primitive.glsl:248-253; only the reference loop
+                                      RTB_ACCEL_BRUTE can accept one at all), a NaN colour is shown as (0,0,10000)
+                                      (composite.comp:236-239).  1 = RELEASE: those stores are skipped (the targets keep what
+                                      they held; zero after rtb_resize), no reject, no NaN mapping. */
     RTB_OPT_PRIMARY_PACKETS = 4,   /* nearest-hit search of the camera rays with RTB_ACCEL_BVH.  0 = one traversal per ray.
                                       1 = one warp-cooperative traversal per 8x4-pixel patch, every ray testing every
                                       child box of the union ("union packets").  3 = the same walk with the box tests

@@ -18,9 +18,14 @@
  *       filter uses full binary32 weights and a (0,0,0,0) border.
  *   D8  lighting.comp reads an unbound Seed SSBO: seed.random = (0,0) there.
  *   D9  smoothstep(e0,e1,x) with e0 > e1 evaluates the Hermite form on clamp((x-e0)/(e1-e0),0,1).
- *   D10 every pass stores for every pixel like the shipped DEBUG shaders do (uvObjectNormal and lighting
- *       on misses, zero shadow words for warps without hits); the DEBUG-only zero-edge triangle reject
- *       (SH/primitive.glsl:248-253) is NOT applied (RELEASE maths).
+ *   D10 two shader builds exist (SH/compile.sh: -DDEBUG or -DRELEASE) and both are modelled (orc_set_mode):
+ *         ORC_MODE_DEBUG (default; the shipped .spv are DEBUG builds): every pass stores for every pixel
+ *           (uvObjectNormal and a zero lighting texel on misses, zero shadow words for subgroups without hits), triangles with
+ *           p1 == p0 are rejected (SH/primitive.glsl:248-253), composite maps a NaN colour to (0,0,10000) (SH/composite.comp:236-239);
+ *         ORC_MODE_RELEASE: those stores are skipped (the targets keep what they held), no zero-edge reject, no NaN mapping.
+ *
+ * PINNING: oracle/_ref is the reference's own shader source compiled for the host (oracle/ref_shim/); tests/test_oracle_vs_ref.py
+ * holds this restatement bit-equal to it in both modes, on whole frames and on explicit rays.
  */
 #include "oracle.h"
 
@@ -98,6 +103,8 @@ inline uint32_t f2u(float f) {   // D5
 }
 inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline float ubits(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+int g_mode = 0;   // ORC_MODE_DEBUG / ORC_MODE_RELEASE (D10)
 
 const float noHit = 3.4028235e38f;          // SH/primitive.glsl:6
 const uint32_t noRayHit = 0xFFFFFFFFu;      // SH/primitive.glsl:7
@@ -333,10 +340,11 @@ bool rayIntersectPlane(const Ray& r, const float* pl, Hit& hit, uint32_t obj, ui
     return false;
 }
 
-// primitive.glsl:239-284 (Möller–Trumbore; RELEASE maths, see D10)
+// primitive.glsl:239-284 (Möller–Trumbore; the zero-edge reject at :248-253 exists in DEBUG builds only, see D10)
 bool rayIntersectTri(const Ray& r, const TriangleRec& tri, Hit& hit, uint32_t obj, uint32_t prevObj) {
     vec3 p0 = v3(tri.p0), p1 = v3(tri.p1), p2 = v3(tri.p2);
     vec3 p1_p0 = p1 - p0, p2_p0 = p2 - p0;
+    if (g_mode == ORC_MODE_DEBUG && p1_p0.x == 0.0f && p1_p0.y == 0.0f && p1_p0.z == 0.0f) return false;
     vec3 h = cross(r.dir, p2_p0);
     float a = dot(p1_p0, h);
     if (std::fabs(a) < 0.0f) return false;   // never true; kept as in the reference
@@ -708,7 +716,9 @@ void raygenPixel(const Scene& sc, const CameraRec& cam, const SeedRec& seed, uin
     if (hit.hitT == noHit) { dirT[0] = hit.rayDir.x; dirT[1] = hit.rayDir.y; dirT[2] = hit.rayDir.z; dirT[3] = ubits(noRayHit); }
     uint32_t en[2];
     encodeNormalGpu(hit.objectNormal, en);
-    uvN[0] = hit.uv.x; uvN[1] = hit.uv.y; uvN[2] = ubits(en[0]); uvN[3] = ubits(en[1]);   // D10: always stored
+    if (g_mode == ORC_MODE_DEBUG || hit.hitT < noHit) {   // raygen.comp:46-51 (D10)
+        uvN[0] = hit.uv.x; uvN[1] = hit.uv.y; uvN[2] = ubits(en[0]); uvN[3] = ubits(en[1]);
+    }
     if (rayOut) { rayOut[0] = ray.pos.x; rayOut[1] = ray.pos.y; rayOut[2] = ray.pos.z; rayOut[3] = ray.dir.x; rayOut[4] = ray.dir.y; rayOut[5] = ray.dir.z; }
     if (flagOut) *flagOut = rayFlags(sc, ray, noRayHit, hit.hitT);
 }
@@ -796,6 +806,8 @@ uint32_t compositePixel(const Scene& sc, const CameraRec& cam, const SeedRec& se
         color = shade(sc.mat[sc.matIdx[object]], hitPos, n, v, NdotV, light, reflected);
     }
     color = mix(color, vec3{0, 0, 0}, 0.0f);   // composite.comp:93-97: cloud = vec4(0)
+    if (g_mode == ORC_MODE_DEBUG && (std::isnan(color.x) || std::isnan(color.y) || std::isnan(color.z)))
+        color = {0.0f, 0.0f, 10000.0f};        // composite.comp:236-239 (DEBUG builds; nanOnly = 0)
     if (cam.flags & 2u) {                      // composite.comp:249-257
         if (seed.sampleCount > 1) color = color + vec3{accum[0], accum[1], accum[2]};
         accum[0] = color.x; accum[1] = color.y; accum[2] = color.z; accum[3] = 0.0f;
@@ -842,6 +854,8 @@ void parallelFor(int64_t n, int64_t chunk, F&& body) {
 extern "C" {
 
 void orc_set_threads(int n) { g_threads = n; }
+void orc_set_mode(int mode) { g_mode = mode == ORC_MODE_RELEASE ? ORC_MODE_RELEASE : ORC_MODE_DEBUG; }
+int orc_get_mode(void) { return g_mode; }
 int orc_get_threads(void) { return threadCount(); }
 
 uint16_t orc_f16_trunc(float v) { return f16_trunc(v); }
@@ -1108,7 +1122,6 @@ void orc_shadow(const orc_scene* s, const void* cam144, const void* seed24, uint
     CameraRec cam; std::memcpy(&cam, cam144, 144);
     SeedRec seed; std::memcpy(&seed, seed24, 24);
     const uint32_t W = cam.width, H = cam.height;
-    std::memset(bits, 0, sizeof(uint32_t) * shadowWords(W, H, samples));   // D10
     const int64_t stripsY = (H + 1) / 2, stripsX = (W + 15) / 16;
     // one "warp" = one 16x2 strip of one sample (nv_all.shadow.comp:40-48); the ballot early-out at :69-82
     // leaves the word zero, and lanes whose own pixel missed contribute hit = false.
@@ -1130,7 +1143,8 @@ void orc_shadow(const orc_scene* s, const void* cam144, const void* seed24, uint
                         float* ro = shadow_rays_out ? shadow_rays_out + 6 * ((size_t)i * W * H + px) : nullptr;
                         if (shadowPixel(sc, cam, seed, samples, x, y, (uint32_t)i, dirT + 4 * px, ro)) word |= 1u << l;
                     }
-                bits[indexToLightNV((uint32_t)sx * 16, (uint32_t)sy * 2, W, H, (uint32_t)i)] = word;
+                // nv_all.shadow.comp:69-82: a subgroup without hits leaves early; only DEBUG builds store the zero word (D10)
+                if (any || g_mode == ORC_MODE_DEBUG) bits[indexToLightNV((uint32_t)sx * 16, (uint32_t)sy * 2, W, H, (uint32_t)i)] = word;
             }
         }
     });
@@ -1147,6 +1161,7 @@ void orc_lighting(const orc_scene* s, const void* cam144, uint32_t samples, cons
             vec3 l;
             bool hit = lightingPixel(sc, cam, samples, (uint32_t)x, (uint32_t)y, dirT + 4 * i, uvN + 4 * i, bits, (uint32_t)W, (uint32_t)H, l);
             float a = hit ? 1.0f : 0.0f;   // imageStore(lighting, vec4(light, 1)) / DEBUG vec4(0) on a miss
+            if (!hit && g_mode != ORC_MODE_DEBUG) continue;   // nv_all.lighting.comp:55-62: RELEASE builds store nothing on a miss (D10)
             if (lighting_f32) { lighting_f32[4 * i] = l.x; lighting_f32[4 * i + 1] = l.y; lighting_f32[4 * i + 2] = l.z; lighting_f32[4 * i + 3] = a; }
             lighting_f16[4 * i] = f32_to_f16_rtne(l.x); lighting_f16[4 * i + 1] = f32_to_f16_rtne(l.y);
             lighting_f16[4 * i + 2] = f32_to_f16_rtne(l.z); lighting_f16[4 * i + 3] = f32_to_f16_rtne(a);

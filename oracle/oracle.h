@@ -11,11 +11,14 @@
  * nv_all.lighting,composite}.comp with their includes. Every function in oracle.cpp cites the
  * reference file:line it follows.
  *
- * PARITY PINNING: the reference cannot be executed here (Windows/WGL OpenGL host, OpenGL SPIR-V;
- * SURVEY.md §8c) and ships no golden vectors for ray/shade results. The only known-answer vectors
- * in the reference tree are the 22 f32->f16 conversions in core2/test/test.cpp:8-29; the oracle is
- * pinned against those (tests/test_oracle_packing.py). Everything else is "parity unpinned": it is
- * pinned by formula, not by reference output.
+ * PARITY PINNING: the reference's host (Windows/WGL OpenGL) cannot run here, but its SHADER SOURCES can: oracle/ref_shim/
+ * compiles res/shaders/{init,raygen,nv_all.shadow,nv_all.lighting,composite}.comp and their includes, read where they lie
+ * under /root/reference and adapted for syntax only, into oracle/_ref/libigxref_{debug,release}.so.  This oracle is held
+ * bit-equal to that library (tests/test_oracle_vs_ref.py: whole frames of every fixture, explicit rays through
+ * traceGeometry / traceOcclusion, both shader builds), and the committed fixtures under tests/golden/ are that library's
+ * output (scripts/make_golden.py).  Host packing is pinned by the 22 f32->f16 known answers of core2/test/test.cpp:8-29.
+ * What stays decreed rather than pinned is what GLSL leaves to the driver (D1-D9 in oracle.cpp: operation rounding,
+ * transcendental precision, sampler arithmetic); the shim and the oracle implement the same decrees.
  */
 #ifndef ORACLE_H
 #define ORACLE_H
@@ -47,6 +50,9 @@ enum {
     ORC_FLAG_NAN = 8        /* NaN or inf met while evaluating a candidate */
 };
 
+enum { ORC_MODE_DEBUG = 0, ORC_MODE_RELEASE = 1 };   /* which build of the shaders is modelled (oracle.cpp D10) */
+void orc_set_mode(int mode);
+int  orc_get_mode(void);
 void orc_set_threads(int n);
 int  orc_get_threads(void);
 

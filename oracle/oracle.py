@@ -82,10 +82,37 @@ def shadow_words(w, h, samples):
     return ((w + 15) // 16) * ((h + 1) // 2) * samples
 
 
+MODE_DEBUG, MODE_RELEASE = 0, 1   # which build of the reference shaders is modelled (oracle.cpp D10)
+
+
+def build_native() -> str:
+    """liboracle_native.so: the optimised build with -march=native, compiled ON THE MACHINE THAT RUNS IT (bench.py's CPU
+    legs call this on the GPU box; a library built with the build container's -march=native must not travel)."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    tag = hashlib.sha1(flags.encode()).hexdigest()[:10]
+    out = os.path.join(_BUILD, f"liboracle_native_{tag}.so")
+    src = os.path.join(_HERE, "oracle.cpp")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(_BUILD, exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O3", "-march=native", "-funroll-loops", "-ffp-contract=off", "-fno-fast-math",
+                               "-fPIC", "-shared", "-pthread", "-o", out, src])
+    return out
+
+
 class Oracle:
-    def __init__(self, fast: bool = False):
+    def __init__(self, fast: bool = False, native: bool = False):
         build()
-        self.lib = C.CDLL(os.path.join(_BUILD, "liboracle_fast.so" if fast else "liboracle.so"))
+        path = build_native() if native else os.path.join(_BUILD, "liboracle_fast.so" if fast else "liboracle.so")
+        self.lib = C.CDLL(path)
         L = self.lib
         L.orc_f16_trunc.restype = C.c_uint16
         L.orc_f16_trunc.argtypes = [C.c_float]
@@ -119,6 +146,13 @@ class Oracle:
 
     def threads(self):
         return int(self.lib.orc_get_threads())
+
+    def set_mode(self, mode):
+        """MODE_DEBUG (default: the shipped .spv) or MODE_RELEASE; process-wide for this library."""
+        self.lib.orc_set_mode(C.c_int(mode))
+
+    def mode(self):
+        return int(self.lib.orc_get_mode())
 
     # ---- packing -------------------------------------------------------------------------------
     def f16_trunc(self, v):
@@ -269,12 +303,14 @@ class Oracle:
         self.lib.orc_composite(C.byref(cs), _ptr(cam), _ptr(seed), _ptr(dirT), _ptr(uvN), _ptr(l16), _ptr(accum), _ptr(rgba))
         return rgba
 
-    def frame(self, scene, cam, seed, samples, accum=None):
-        """K0..K4. Returns dict of every intermediate; `seed` is updated in place."""
+    def frame(self, scene, cam, seed, samples, accum=None, prefill=None):
+        """K0..K4. Returns dict of every intermediate; `seed` is updated in place.  `prefill`: what the targets hold before
+        the frame (a RELEASE build leaves the texels it does not store as they were)."""
         w, h = self._wh(cam)
-        out = dict(dirT=np.zeros((h, w, 4), np.float32), uvN=np.zeros((h, w, 4), np.float32),
-                   bits=np.zeros(shadow_words(w, h, samples), np.uint32), lighting=np.zeros((h, w, 4), np.uint16),
-                   rgba8=np.zeros((h, w), np.uint32))
+        pre = prefill or {}
+        out = dict(dirT=pre.get("dirT", np.zeros((h, w, 4), np.float32)).copy(), uvN=pre.get("uvN", np.zeros((h, w, 4), np.float32)).copy(),
+                   bits=pre.get("bits", np.zeros(shadow_words(w, h, samples), np.uint32)).copy(),
+                   lighting=pre.get("lighting", np.zeros((h, w, 4), np.uint16)).copy(), rgba8=np.zeros((h, w), np.uint32))
         cs = scene.c()
         self.lib.orc_frame(C.byref(cs), _ptr(cam), _ptr(seed), samples, _ptr(out["dirT"]), _ptr(out["uvN"]),
                            _ptr(out["bits"]), _ptr(out["lighting"]), _ptr(accum), _ptr(out["rgba8"]))

@@ -1,15 +1,19 @@
-"""Writes tests/golden/*.npz: frames of the CPU oracle (strict-FP build) on fixed inputs, committed so that
+"""Writes tests/golden/*.npz: frames rendered by THE REFERENCE'S OWN SHADERS on fixed inputs.
 
-  * the oracle cannot drift unnoticed (tests/test_golden.py, CPU), and
-  * the CUDA path is compared against bytes that exist independently of the oracle build on the GPU box
-    (tests/test_gpu_golden.py).
+The generator is oracle/_ref (oracle/ref_shim/: the reference's res/shaders sources, read where they lie under
+/root/reference, adapted for syntax and compiled for the host; -DDEBUG build = what the shipped .spv are, -DRELEASE for the
+cases marked "release").  The hand-written oracle must reproduce every fixture bit for bit, or this script refuses to write.
+The fixtures are committed so that
 
-    python scripts/make_golden.py            # rewrites every fixture
+  * the oracle cannot drift from the reference unnoticed, also where /root/reference does not exist (tests/test_golden.py, CPU), and
+  * the CUDA path is compared against bytes that came out of the reference's code, not out of our restatement
+    (tests/test_golden.py::test_cuda_equals_golden, GPU).
+
+    python scripts/make_golden.py            # rewrites every fixture (needs /root/reference)
     python scripts/make_golden.py --check    # regenerates in memory and compares with the committed files
 
-The reference ships no golden vectors for ray / shade results and cannot be executed here, so these
-are *oracle* outputs: they pin the restatement, not the reference.  The only reference-owned known answers are the
-22 f32 -> f16 conversions of core2/test/test.cpp:8-29; they are stored in f16_kat.json next to the frames.
+The only reference-owned known answers for HOST packing are the 22 f32 -> f16 conversions of core2/test/test.cpp:8-29; they
+are stored in f16_kat.json next to the frames.
 """
 from __future__ import annotations
 
@@ -25,7 +29,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-# name -> (scene time, width, height, shadow samples, camera kwargs, cpuOffset, frames, skybox?)
+# name -> scene time, size, shadow samples, camera kwargs, cpuOffset, frames, skybox?, [degenerate: triangle 1 gets p1 = p0],
+#         [release: the -DRELEASE build of the shaders, targets zero before the frame]
 CASES = {
     "niels_default_96x54": dict(time=0.0, w=96, h=54, samples=1, cam=dict(eye=(4, 2, -2)), off=(0.0, 0.0), frames=1, sky=True),
     "niels_all_objects_128x72": dict(time=0.0, w=128, h=72, samples=2, cam=dict(eye=(6, 5, 12)), off=(0.0, 0.0), frames=1, sky=True),
@@ -35,6 +40,11 @@ CASES = {
     "niels_accumulate4_64x36": dict(time=0.0, w=64, h=36, samples=1, cam=dict(eye=(6, 5, 12), flags=2), off=(3.0, 9.0), frames=4, sky=True),
     "niels_omni_64x32": dict(time=0.0, w=64, h=32, samples=1, cam=dict(eye=(6, 5, 12), projection=1, yaw=0.3), off=(0.0, 0.0), frames=1, sky=True),
     "niels_stereo_tb_64x32": dict(time=0.0, w=64, h=32, samples=1, cam=dict(eye=(6, 5, 12), projection=2, yaw=0.3), off=(0.0, 0.0), frames=1, sky=True),
+    "niels_degenerate_tri_96x54": dict(time=0.0, w=96, h=54, samples=1, cam=dict(eye=(2, 5, 6), pitch=-0.25), off=(0.0, 0.0), frames=1, sky=True,
+                                       degenerate=True),
+    "niels_release_96x54": dict(time=0.0, w=96, h=54, samples=2, cam=dict(eye=(6, 5, 12)), off=(0.0, 0.0), frames=1, sky=True, release=True),
+    "niels_release_degenerate_80x45": dict(time=0.0, w=80, h=45, samples=1, cam=dict(eye=(2, 5, 6), pitch=-0.25), off=(0.0, 0.0), frames=1,
+                                           sky=True, degenerate=True, release=True),
 }
 
 F16_KAT = [   # core2/test/test.cpp:8-29 (f32 bits, expected f16 bits)
@@ -46,19 +56,21 @@ F16_KAT = [   # core2/test/test.cpp:8-29 (f32 bits, expected f16 bits)
 ]
 
 
-def render(oracle, case):
-    from conftest import synthetic_sky
-    sky = synthetic_sky() if case["sky"] else None
-    scene = oracle.niels_scene(case["time"], sky)
+def render(engine, oracle, case):
+    """engine: oracle.ref.Ref or oracle.oracle.Oracle (same frame() signature); scenes and cameras come from the oracle's
+    host packing (pinned separately by the f16 known answers and the SURVEY Appendix-B anchors)."""
+    from conftest import case_scene
+    scene = case_scene(oracle, case)
     w, h = case["w"], case["h"]
     cam = oracle.camera(w, h, **case["cam"])
-    seed = oracle.seed(case["off"])
+    seed = oracle.seed(tuple(case["off"]))
     accum = np.zeros((h, w, 4), np.float32)
+    pre = None
     for _ in range(case["frames"]):
-        ref = oracle.frame(scene, cam, seed, case["samples"], accum=accum)
-    out = dict(camera=np.frombuffer(bytes(cam), np.uint8).copy(), seed_after=np.frombuffer(bytes(seed), np.uint8).copy(),
-               dirT=ref["dirT"], uvN=ref["uvN"], bits=ref["bits"], lighting=ref["lighting"], rgba8=ref["rgba8"], accum=accum)
-    return out
+        ref = engine.frame(scene, cam, seed, case["samples"], accum=accum, prefill=pre)
+        pre = {k: ref[k] for k in ("dirT", "uvN", "bits", "lighting")}
+    return dict(camera=np.frombuffer(bytes(cam), np.uint8).copy(), seed_after=np.frombuffer(bytes(seed), np.uint8).copy(),
+                dirT=ref["dirT"], uvN=ref["uvN"], bits=ref["bits"], lighting=ref["lighting"], rgba8=ref["rgba8"], accum=accum)
 
 
 def main():
@@ -66,11 +78,22 @@ def main():
     ap.add_argument("--check", action="store_true")
     args = ap.parse_args()
     from oracle.oracle import Oracle
+    from oracle import ref as refmod
     orc = Oracle()
+    if not refmod.build():
+        sys.exit("scripts/make_golden.py needs the reference tree (oracle/_ref is built from it)")
+    refs = {False: refmod.Ref(debug=True), True: refmod.Ref(debug=False)}
     os.makedirs(GOLDEN, exist_ok=True)
     bad = 0
     for name, case in CASES.items():
-        out = render(orc, case)
+        release = bool(case.get("release"))
+        out = render(refs[release], orc, case)
+        orc.set_mode(1 if release else 0)
+        mine = render(orc, orc, case)
+        orc.set_mode(0)
+        for k, v in out.items():
+            if not np.array_equal(np.asarray(v).view(np.uint8), np.asarray(mine[k]).view(np.uint8)):
+                sys.exit(f"{name}: the oracle's {k} differs from the reference shaders — fix the oracle before writing fixtures")
         path = os.path.join(GOLDEN, name + ".npz")
         if args.check:
             have = np.load(path)
@@ -86,7 +109,7 @@ def main():
         with open(kat, "w") as f:
             json.dump({"source": "igx/igxi-tool/igxi/ignis/core2/test/test.cpp:8-29", "f32_bits_to_f16_bits": F16_KAT}, f, indent=1)
         with open(os.path.join(GOLDEN, "cases.json"), "w") as f:
-            json.dump(CASES, f, indent=1)
+            json.dump(dict(generator="oracle/_ref (the reference's shaders compiled for the host; scripts/make_golden.py)", cases=CASES), f, indent=1)
     sys.exit(1 if bad else 0)
 
 

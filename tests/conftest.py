@@ -44,3 +44,18 @@ def synthetic_sky(w=64, h=32, seed=7):
 @pytest.fixture(scope="session")
 def sky():
     return synthetic_sky()
+
+
+def degenerate_triangles(tri_bytes):
+    """fixture variant: triangle 1 gets p1 = p0 (a zero first edge: rejected by the DEBUG shaders, primitive.glsl:248-253)"""
+    t = np.array(tri_bytes, copy=True).view(np.uint8).reshape(-1, 48)
+    t[1, 16:28] = t[1, 0:12]
+    return t.reshape(-1)
+
+
+def case_scene(oracle, case):
+    """the oracle-side Scene of a tests/golden case"""
+    scene = oracle.niels_scene(case["time"], synthetic_sky() if case["sky"] else None)
+    if case.get("degenerate"):
+        scene.triangles = degenerate_triangles(scene.triangles)
+    return scene

@@ -1,7 +1,10 @@
-"""Committed golden fixtures (tests/golden/, written by scripts/make_golden.py).
+"""Committed golden fixtures (tests/golden/, written by scripts/make_golden.py FROM THE REFERENCE'S OWN SHADERS compiled for
+the host: oracle/_ref, see oracle/ref_shim/).
 
-CPU half: the oracle reproduces every fixture byte for byte (so the checker cannot drift), and the reference's own
-f16 known answers are read from the fixture file.  GPU half: the CUDA path, through the C ABI, against the same bytes.
+CPU half: the oracle reproduces every fixture byte for byte (so the checker cannot drift from the reference, also where
+/root/reference is absent), and the reference's own f16 known answers are read from the fixture file.  GPU half: the CUDA
+path, through the C ABI, against the same bytes — DEBUG-build fixtures (what the shipped .spv are), RELEASE-build fixtures
+(RTB_OPT_SHADER_BUILD = 1) and a scene with a degenerate triangle.
 """
 import json
 import os
@@ -9,10 +12,10 @@ import os
 import numpy as np
 import pytest
 
-from conftest import synthetic_sky
+from conftest import case_scene, degenerate_triangles, synthetic_sky
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = json.load(open(os.path.join(GOLDEN, "cases.json")))
+CASES = json.load(open(os.path.join(GOLDEN, "cases.json")))["cases"]
 KEYS = ("dirT", "uvN", "bits", "lighting", "rgba8", "accum")
 
 
@@ -31,15 +34,20 @@ def test_f16_kat_fixture(oracle):
 @pytest.mark.parametrize("name", list(CASES))
 def test_oracle_reproduces_golden(oracle, name):
     case, gold = CASES[name], load(name)
-    sky = synthetic_sky() if case["sky"] else None
-    scene = oracle.niels_scene(case["time"], sky)
+    scene = case_scene(oracle, case)
     w, h = case["w"], case["h"]
     cam = oracle.camera(w, h, **case["cam"])
     assert np.array_equal(cam, gold["camera"])
     seed = oracle.seed(tuple(case["off"]))
     accum = np.zeros((h, w, 4), np.float32)
-    for _ in range(case["frames"]):
-        ref = oracle.frame(scene, cam, seed, case["samples"], accum=accum)
+    oracle.set_mode(1 if case.get("release") else 0)
+    try:
+        pre = None
+        for _ in range(case["frames"]):
+            ref = oracle.frame(scene, cam, seed, case["samples"], accum=accum, prefill=pre)
+            pre = {k: ref[k] for k in ("dirT", "uvN", "bits", "lighting")}
+    finally:
+        oracle.set_mode(0)
     ref["accum"] = accum
     assert np.array_equal(seed, gold["seed_after"])
     for k in KEYS:
@@ -57,7 +65,11 @@ def test_cuda_equals_golden(rtb, name, accel):
     w, h = case["w"], case["h"]
     ctx = rtb.Context()
     ctx.resize(w, h, case["samples"])
-    ctx.upload_scene(rtb.niels_scene(case["time"]), sky)
+    scene = rtb.niels_scene(case["time"])
+    if case.get("degenerate"):
+        scene["triangles"] = degenerate_triangles(scene["triangles"])
+    ctx.upload_scene(scene, sky)
+    ctx.set_option(rtb.OPT_SHADER_BUILD, rtb.SHADER_RELEASE if case.get("release") else rtb.SHADER_DEBUG)
     ctx.build_accel(accel)
     cam = rtb.pack_camera(w, h, **case["cam"])
     assert np.array_equal(cam, gold["camera"]), "host camera packing differs from the fixture"
