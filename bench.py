@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--packets", default="auto", choices=["off", "union", "frustum", "auto"],
                     help="camera rays as 8x4-pixel packets (RTB_OPT_PRIMARY_PACKETS); auto = the library's patch-size rule")
+    ap.add_argument("--shadow-order", default="queue", choices=["slots", "queue", "sorted"],
+                    help="RTB_OPT_SHADOW_ORDER: occlusion rays in wavefront-slot order, as a queue of live rays, or that queue sorted in light space")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -254,6 +256,7 @@ def main():
     ctx.set_option(rtb.OPT_TILE_COUNT, world)
     ctx.set_option(rtb.OPT_TILE_RANK, rank)
     ctx.set_option(rtb.OPT_PRIMARY_PACKETS, {"off": 0, "union": 1, "auto": 2, "frustum": 3}[args.packets])
+    ctx.set_option(rtb.OPT_SHADOW_ORDER, {"slots": 0, "queue": 1, "sorted": 2}[args.shadow_order])
     ctx.resize(w, h, samples)
     ctx.upload_scene(scene, None)
     ctx.build_accel(rtb.ACCEL_BVH)

@@ -3,7 +3,9 @@
 // reference's render tasks.  No CPU fallback exists: without a usable CUDA device every call fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <initializer_list>
 #include <cstdio>
 #include <cstring>
@@ -72,6 +74,9 @@ struct rtb_ctx {
     uint32_t packetsOpt = 2;          // RTB_OPT_PRIMARY_PACKETS: 0 off, 1 union packets, 2 auto, 3 frustum packets
     int lastPrimaryPackets = 0;       // PACKETS_* of the last camera-ray launch
     uint32_t fuseOpt = 1;             // RTB_OPT_FUSE_PRIMARY
+    uint32_t shadowOrder = 1;         // RTB_OPT_SHADOW_ORDER: 0 slot order, 1 queue of live rays (default), 2 queue sorted in light space
+    LightRec light0{};                // host mirror of lights[0] (the one light the shadow pass samples): picks the sort key
+    DevBuf<RayRec> queueRays; DevBuf<uint32_t> queueSlots, sortedSlots, queueCell, queueRank, queueHist, queueSums, queueCount;
     uint32_t releaseBuild = 0;        // RTB_OPT_SHADER_BUILD: 0 = DEBUG build of the reference shaders (what ships), 1 = RELEASE
 
     // rays-in scratch
@@ -214,14 +219,77 @@ int passRaygen(rtb_ctx* c, bool mark) {
     if (c->countersOn) launch_count_hits(c->fm, c->dirT.p, c->counters.p, c->stream);
     return RTB_OK;
 }
+// Light-space binning of the occlusion rays (rtb_sort.cu): a sun gets two axes perpendicular to its direction, a point light
+// the octahedral map of the direction from the light; the cell grid covers the scene bounds seen from the light.
+RayBin shadowBin(const rtb_ctx* c, uint32_t maxRays) {
+    RayBin b{};
+    uint32_t bits = 4;
+    while (bits < 10 && (1ull << (2 * bits)) * 4ull < maxRays) ++bits;   // about four rays per cell
+    b.bits = bits;
+    const float cells = (float)(1u << bits);
+    const LightRec& l = c->light0;
+    if ((l.colorBType >> 16) == LIGHT_POINT) {
+        b.kind = 2; b.lpos[0] = l.pos[0]; b.lpos[1] = l.pos[1]; b.lpos[2] = l.pos[2];
+        b.u0 = -1.0f; b.v0 = -1.0f; b.su = b.sv = cells * 0.5f;
+        return b;
+    }
+    // decodeNormal (SH/primitive.glsl:90-93); any vector near the light direction will do for a sort key
+    float d[3] = {(float)(l.dir[0] >> 16) / 65535.0f * 2.0f - 1.0f, (float)(l.dir[0] & 65535u) / 65535.0f * 2.0f - 1.0f, (float)l.dir[1] / 65535.0f * 2.0f - 1.0f};
+    const float len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (!(len > 1e-6f)) return b;   // kind 0: no binning
+    for (float& v : d) v /= len;
+    const int k = std::fabs(d[0]) < std::fabs(d[1]) ? (std::fabs(d[0]) < std::fabs(d[2]) ? 0 : 2) : (std::fabs(d[1]) < std::fabs(d[2]) ? 1 : 2);
+    float e[3] = {0, 0, 0}; e[k] = 1.0f;
+    float b1[3] = {d[1] * e[2] - d[2] * e[1], d[2] * e[0] - d[0] * e[2], d[0] * e[1] - d[1] * e[0]};
+    const float l1 = std::sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+    for (float& v : b1) v /= l1;
+    const float b2[3] = {d[1] * b1[2] - d[2] * b1[1], d[2] * b1[0] - d[0] * b1[2], d[0] * b1[1] - d[1] * b1[0]};
+    float lo[2] = {3e38f, 3e38f}, hi[2] = {-3e38f, -3e38f};
+    for (int corner = 0; corner < 8; ++corner) {
+        const float p[3] = {corner & 1 ? c->stats.hi[0] : c->stats.lo[0], corner & 2 ? c->stats.hi[1] : c->stats.lo[1], corner & 4 ? c->stats.hi[2] : c->stats.lo[2]};
+        const float u = p[0] * b1[0] + p[1] * b1[1] + p[2] * b1[2], v = p[0] * b2[0] + p[1] * b2[1] + p[2] * b2[2];
+        lo[0] = std::min(lo[0], u); hi[0] = std::max(hi[0], u); lo[1] = std::min(lo[1], v); hi[1] = std::max(hi[1], v);
+    }
+    if (!(hi[0] > lo[0]) || !(hi[1] > lo[1])) return b;
+    b.kind = 1;
+    for (int a = 0; a < 3; ++a) { b.b1[a] = b1[a]; b.b2[a] = b2[a]; }
+    b.u0 = lo[0]; b.v0 = lo[1]; b.su = cells / (hi[0] - lo[0]); b.sv = cells / (hi[1] - lo[1]);
+    return b;
+}
+
 int passShadow(rtb_ctx* c, bool mark) {
     { const int rc = waitCopy(c, {RTB_TGT_SHADOW_BITS}); if (rc) return rc; }
     const SceneView sv = sceneView(c);
     if (c->releaseBuild) launch_clear_hit_strips(c->fm, c->dirT.p, c->samples, c->bits.p, c->stream);
     else RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, c->samples) * 4, c->stream));
-    launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, c->stream);
+    const uint32_t maxRays = c->fm.localSlots * c->samples;
+    TraceCounters* counters = c->countersOn ? c->counters.p + 1 : nullptr;
+    if (!c->shadowOrder || sv.useBvh != ACCEL_KIND_CWBVH || !sv.info.triangleCount || !maxRays) {
+        // slot order: one record per (sample, slot), what the first-generation kernels and the reference loop consume
+        launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, nullptr, nullptr, c->stream);
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        launch_trace_any_bits(c->fm, sv, c->rays.p, maxRays, c->bits.p, c->workCounter.p, counters, nullptr, nullptr, c->stream);
+        return RTB_OK;
+    }
+    // queue of live rays, optionally sorted in light space
+    RayBin bin = c->shadowOrder >= 2 ? shadowBin(c, maxRays) : RayBin{};
+    const uint32_t cells = bin.kind ? 1u << (2 * bin.bits) : 0u;
+    RTB_CUDA(c, c->queueCount.alloc(1)); RTB_CUDA(c, c->queueSlots.alloc(maxRays));
+    RTB_CUDA(c, cudaMemsetAsync(c->queueCount.p, 0, 4, c->stream));
+    RayQueue q{};
+    q.count = c->queueCount.p; q.slotIds = c->queueSlots.p;
+    if (bin.kind) {
+        RTB_CUDA(c, c->queueRays.alloc(maxRays)); RTB_CUDA(c, c->sortedSlots.alloc(maxRays)); RTB_CUDA(c, c->queueCell.alloc(maxRays)); RTB_CUDA(c, c->queueRank.alloc(maxRays));
+        RTB_CUDA(c, c->queueHist.alloc(cells)); RTB_CUDA(c, c->queueSums.alloc(1024));
+        RTB_CUDA(c, cudaMemsetAsync(c->queueHist.p, 0, (size_t)cells * 4, c->stream));
+        q.rays = c->queueRays.p; q.cell = c->queueCell.p; q.rank = c->queueRank.p; q.hist = c->queueHist.p; q.blockSums = c->queueSums.p;
+    } else
+        q.rays = c->rays.p;
+    launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, &q, &bin, c->stream);
+    const uint32_t* slots = c->queueSlots.p;
+    if (bin.kind) { launch_sort_rays(q, cells, maxRays, c->rays.p, c->sortedSlots.p, c->stream); slots = c->sortedSlots.p; }
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
-    launch_trace_any_bits(c->fm, sv, c->rays.p, c->fm.localSlots * c->samples, c->bits.p, c->workCounter.p, c->countersOn ? c->counters.p + 1 : nullptr, c->stream);
+    launch_trace_any_bits(c->fm, sv, c->rays.p, maxRays, c->bits.p, c->workCounter.p, counters, slots, c->queueCount.p, c->stream);
     return RTB_OK;
 }
 int passShade(rtb_ctx* c, int what) {
@@ -285,6 +353,7 @@ void rtb_destroy(rtb_ctx* c) {
     c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release(); c->nodeBox.release(); c->maxBits.release(); c->areaSums.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->rays.release(); c->hits.release(); c->workCounter.release(); c->counters.release();
+    c->queueRays.release(); c->queueSlots.release(); c->sortedSlots.release(); c->queueCell.release(); c->queueRank.release(); c->queueHist.release(); c->queueSums.release(); c->queueCount.release();
     c->rinRays.release(); c->rinHits.release(); c->rinObj.release(); c->rinT.release(); c->rinUv.release(); c->rinOcc.release(); c->rinOcc2.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -318,6 +387,9 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             }
             return RTB_OK;
         }
+        case RTB_OPT_SHADOW_ORDER:
+            if (value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_SHADOW_ORDER: 0 slot order, 1 queue of live rays, 2 queue sorted in light space");
+            c->shadowOrder = value; return RTB_OK;
         case RTB_OPT_SHADER_BUILD:
             if (value > 1) return fail(c, RTB_ERR_ARG, "RTB_OPT_SHADER_BUILD: 0 = DEBUG build (default), 1 = RELEASE build");
             c->releaseBuild = value; return RTB_OK;
@@ -384,6 +456,7 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
     if (off > cap || bytes > cap - off) return fail(c, RTB_ERR_CAPACITY, "rtb_upload: range exceeds the capacity given to rtb_create");
     if (!bytes) return RTB_OK;
     if (id == RTB_BUF_TRIANGLES) { std::memcpy(c->triangleMirror.data() + off, src, bytes); c->accelValid = false; }
+    if (id == RTB_BUF_LIGHTS && off < sizeof(LightRec)) std::memcpy(reinterpret_cast<uint8_t*>(&c->light0) + off, src, std::min(bytes, sizeof(LightRec) - off));
     // pageable source: cudaMemcpyAsync stages it before returning, so the caller may reuse src at once (like GPUBuffer::flush)
     RTB_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, src, bytes, cudaMemcpyHostToDevice, c->stream));
     return RTB_OK;

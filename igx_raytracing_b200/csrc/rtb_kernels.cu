@@ -84,6 +84,8 @@ struct TraceArgs {
     const uint4* nodes8Alias;   // == nodes8, a second name the compiler cannot prove equal (rtb_trace8.cuh, ldg256swap)
     TriHit* hits;               // MODE_CLOSEST
     uint32_t* bits; FrameMap fm;// MODE_ANY_BITS
+    const uint32_t* slotIds;    // MODE_ANY_BITS on a queue: the wavefront slot of ray r (nullptr: r itself)
+    const uint32_t* countPtr;   // rays in the queue (device; nullptr: n)
     uint8_t* bytes;             // MODE_ANY_BYTES
     uint32_t* workCounter;
     TraceCounters* counters;
@@ -399,11 +401,11 @@ void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, T
 }
 
 void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits,
-                           uint32_t* workCounter, TraceCounters* counters, cudaStream_t st) {
+                           uint32_t* workCounter, TraceCounters* counters, const uint32_t* slotIds, const uint32_t* countPtr, cudaStream_t st) {
     if (!n || sv.info.triangleCount == 0) return;
     if (sv.useBvh) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
-        a.bits = bits; a.fm = fm;
+        a.bits = bits; a.fm = fm; a.slotIds = slotIds; a.countPtr = countPtr;
         launchTrace<MODE_ANY_BITS>(sv, a, counters != nullptr, st);
     } else {
         k_trace_brute<MODE_ANY_BITS><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, bits, fm, nullptr, !sv.releaseBuild);
@@ -567,7 +569,7 @@ RTB_DI uint32_t hitsFirst(bool isHit) {
 #endif
 __global__ void __launch_bounds__(256, RTB_SHADOWGEN_MINBLOCKS) k_shadowgen(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
                                                    uint32_t samples, const float4* __restrict__ dirT, RayRec* __restrict__ rays,
-                                                   uint32_t* __restrict__ bits) {
+                                                   uint32_t* __restrict__ bits, const RayQueue q, const RayBin bin) {
     // localSlots is a multiple of 1024: a block of 256 slots lies in one sample and is never ragged
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     {
@@ -576,11 +578,11 @@ __global__ void __launch_bounds__(256, RTB_SHADOWGEN_MINBLOCKS) k_shadowgen(cons
         const bool hit0 = j < fm.localSlots * samples && slotToPixel(fm, i0, x0, y0) && fbits(__ldg(dirT + (size_t)y0 * fm.w + x0).w) != NO_RAY_HIT;
         j = blockIdx.x * blockDim.x + hitsFirst(hit0);
     }
-    if (j >= fm.localSlots * samples) return;
+    const bool inRange = j < fm.localSlots * samples;   // always true: the grid covers localSlots * samples exactly
     const uint32_t sample = j / fm.localSlots, i = j - sample * fm.localSlots;
     float4 ro = make_float4(0.f, 0.f, 0.f, ubits(NO_RAY_HIT)), rd = make_float4(0.f, 0.f, 1.f, -1.0f);
     uint32_t x, y;
-    if (slotToPixel(fm, i, x, y)) {
+    if (inRange && slotToPixel(fm, i, x, y)) {
         const float4 dt = __ldg(dirT + (size_t)y * fm.w + x);
         const uint32_t object = fbits(dt.w);
         if (object != NO_RAY_HIT) {
@@ -611,14 +613,47 @@ __global__ void __launch_bounds__(256, RTB_SHADOWGEN_MINBLOCKS) k_shadowgen(cons
             }
         }
     }
-    float4* out = reinterpret_cast<float4*>(rays + j);
+    if (!q.count) {   // slot order: one record per slot, dead ones marked
+        if (inRange) { float4* out = reinterpret_cast<float4*>(rays + j); out[0] = ro; out[1] = rd; }
+        return;
+    }
+    // queue: live rays only, one atomic per warp
+    const bool live = rd.w >= 0.0f;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+    if (!m) return;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(q.count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if (!live) return;
+    const uint32_t r = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    float4* out = reinterpret_cast<float4*>(q.rays + r);
     out[0] = ro; out[1] = rd;
+    q.slotIds[r] = j;
+    if (bin.kind) {
+        float u, v;
+        if (bin.kind == 1u) {
+            u = ro.x * bin.b1[0] + ro.y * bin.b1[1] + ro.z * bin.b1[2];
+            v = ro.x * bin.b2[0] + ro.y * bin.b2[1] + ro.z * bin.b2[2];
+        } else {   // octahedral map of the direction from the light to the ray origin
+            const float dx = ro.x - bin.lpos[0], dy = ro.y - bin.lpos[1], dz = ro.z - bin.lpos[2];
+            const float inv = 1.0f / fmaxf(fabsf(dx) + fabsf(dy) + fabsf(dz), 1e-30f);
+            u = dx * inv; v = dy * inv;
+            if (dz < 0.0f) { const float tu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f); v = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f); u = tu; }
+        }
+        const float cmax = (float)((1u << bin.bits) - 1u);
+        const uint32_t cu = (uint32_t)fminf(fmaxf((u - bin.u0) * bin.su, 0.0f), cmax), cv = (uint32_t)fminf(fmaxf((v - bin.v0) * bin.sv, 0.0f), cmax);
+        auto spread = [](uint32_t a) { a = (a | (a << 8)) & 0x00FF00FFu; a = (a | (a << 4)) & 0x0F0F0F0Fu; a = (a | (a << 2)) & 0x33333333u; a = (a | (a << 1)) & 0x55555555u; return a; };
+        const uint32_t cell = spread(cu) | (spread(cv) << 1);
+        q.cell[r] = cell;
+        q.rank[r] = atomicAdd(q.hist + cell, 1u);
+    }
 }
 void launch_shadowgen(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
-                      const float4* dirT, RayRec* rays, uint32_t* bits, cudaStream_t st) {
+                      const float4* dirT, RayRec* rays, uint32_t* bits, const RayQueue* queue, const RayBin* bin, cudaStream_t st) {
     const uint32_t n = fm.localSlots * samples;
     if (!n) return;
-    k_shadowgen<<<(n + 255) / 256, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, rays, bits);
+    k_shadowgen<<<(n + 255) / 256, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, rays, bits, queue ? *queue : RayQueue{}, bin ? *bin : RayBin{});
 }
 
 // RELEASE shader build: one thread per shadow word (a 16x2 pixel strip of one sample)

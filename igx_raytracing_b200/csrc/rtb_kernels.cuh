@@ -28,6 +28,19 @@ enum : uint32_t { ACCEL_KIND_BRUTE = 0, ACCEL_KIND_CWBVH = 1, ACCEL_KIND_BVH2 = 
 
 struct TraceCounters { unsigned long long rays, nodes, tris, hits; };
 
+// Light-space 2D coordinate of an occlusion ray (rtb_sort.cu): rays with equal coordinates travel along the same line.
+struct RayBin {
+    uint32_t kind;         // 0: no binning, 1: directional light (u, v = origin . b1, origin . b2), 2: point light (octahedral map of origin - lpos)
+    uint32_t bits;         // cells per axis = 1 << bits (<= 10); cell index = Morton code of the two cell coordinates
+    float b1[3], b2[3], lpos[3];
+    float u0, v0, su, sv;  // cell coordinate = clamp((u - u0) * su, 0, cells - 1)
+};
+// Queue of live rays appended by k_shadowgen (and the path kernels): count[0] rays, each with the wavefront slot it belongs to.
+struct RayQueue {
+    RayRec* rays; uint32_t* slotIds; uint32_t* count;
+    uint32_t* cell; uint32_t* rank; uint32_t* hist; uint32_t* blockSums;   // binning (RayBin.kind != 0)
+};
+
 void launch_init(SeedRec* seed, cudaStream_t s);
 void launch_raygen(const FrameMap& fm, const CameraRec* cam, const SeedRec* seed, RayRec* rays, cudaStream_t s);
 // nearest triangle for every ray slot (BVH or brute force according to sv.useBvh).  packets != PACKETS_OFF: 32 consecutive
@@ -46,11 +59,16 @@ void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec
 // instrumented frames: counters->hits = pixels of this rank whose nearest hit is any primitive
 void launch_count_hits(const FrameMap& fm, const float4* dirT, TraceCounters* counters, cudaStream_t s);
 // shadow.comp ray set-up + occlusion by the non-triangle primitives; leaves triangle work in `rays`
+// queue == nullptr: one record per (sample, slot), dead slots marked tmax < 0 (slot order).  Otherwise the live rays are
+// appended to the queue and, with bin.kind != 0, binned for launch_sort_rays.
 void launch_shadowgen(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
-                      const float4* dirT, RayRec* rays, uint32_t* bits, cudaStream_t s);
-// any-hit over the triangles; sets the (pixel, sample) bit of every occluded slot
+                      const float4* dirT, RayRec* rays, uint32_t* bits, const RayQueue* queue, const RayBin* bin, cudaStream_t s);
+// counting sort of a binned queue into (outRays, outSlots); cells = 4^bin.bits, maxRays bounds the queue length
+void launch_sort_rays(const RayQueue& q, uint32_t cells, uint32_t maxRays, RayRec* outRays, uint32_t* outSlots, cudaStream_t s);
+// any-hit over the triangles; sets the (pixel, sample) bit of every occluded slot.  slotIds / countPtr (8-wide tree only):
+// the rays are a queue — ray r belongs to wavefront slot slotIds[r], and *countPtr (device) rays are valid (n = upper bound)
 void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits,
-                           uint32_t* workCounter, TraceCounters* counters, cudaStream_t s);
+                           uint32_t* workCounter, TraceCounters* counters, const uint32_t* slotIds, const uint32_t* countPtr, cudaStream_t s);
 // RELEASE shader build only: zero the shadow words of the 16x2 strips that hold at least one hit pixel (the reference's
 // subgroups without hits leave early and store nothing: nv_all.shadow.comp:69-82); the DEBUG build zeroes every word
 void launch_clear_hit_strips(const FrameMap& fm, const float4* dirT, uint32_t samples, uint32_t* bits, cudaStream_t s);

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
     uint2 lstack[LOCAL_STACK];
+    const uint32_t nRays = (MODE == MODE_ANY_BITS && a.countPtr) ? __ldg(a.countPtr) : a.n;   // a queue's length lives on the device
 
     bool active = false, exhausted = false;
     uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT, octinv = 0;
@@ -117,10 +118,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh
             const int leader = __ffs(need) - 1;
             if ((int)lane == leader) base = atomicAdd(a.workCounter, (uint32_t)__popc(need));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            exhausted = base + (uint32_t)__popc(need) >= a.n;
+            exhausted = base + (uint32_t)__popc(need) >= nRays;
             if (!active) {
                 slot = base + (uint32_t)__popc(need & lanesBelow);
-                if (slot < a.n) {
+                if (slot < nRays) {
                     const float4 o = __ldg(reinterpret_cast<const float4*>(a.rays + slot));
                     const float4 d = __ldg(reinterpret_cast<const float4*>(a.rays + slot) + 1);
                     if (d.w >= 0.0f) {
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh
                     if (COUNT && bestId != NO_RAY_HIT) cHits++;
                 } else if (MODE == MODE_ANY_BITS) {
                     if (bestId != NO_RAY_HIT) {
-                        const uint32_t sample = slot / a.fm.localSlots, i = slot - sample * a.fm.localSlots;
+                        const uint32_t j = a.slotIds ? __ldg(a.slotIds + slot) : slot;
+                        const uint32_t sample = j / a.fm.localSlots, i = j - sample * a.fm.localSlots;
                         uint32_t x, y;
                         slotToPixel(a.fm, i, x, y);
                         atomicOr(a.bits + indexToLight(x, y, a.fm.w, a.fm.h, sample), 1u << ((x & 15u) | ((y & 1u) << 4)));

@@ -136,9 +136,17 @@ typedef enum rtb_option {
                                       is Default and the patch is small against the tree's leaf nodes, else per ray.
                                       The hits are identical in every mode.  With 1 or 3 the rays-in call rtb_trace_rays
                                       also walks its rays in packets of 32 consecutive rays. */
-    RTB_OPT_FUSE_PRIMARY = 5       /* 0/1 (default 1): with frustum packets, generate the camera rays inside the traversal launch and
+    RTB_OPT_FUSE_PRIMARY = 5,      /* 0/1 (default 1): with frustum packets, generate the camera rays inside the traversal launch and
                                       write the G-buffer from its epilogue (one launch instead of three; same bits).  0 keeps
                                       the three launches, e.g. to time them apart. */
+    RTB_OPT_SHADOW_ORDER = 6       /* how the occlusion rays reach the traversal kernel (RTB_ACCEL_BVH; same shadow bits in every
+                                      mode).  0 = one record per pixel and sample in wavefront-slot order, misses included.
+                                      1 (default) = the live rays appended to a queue (no dead records travel: occlusion launch
+                                      2.14 -> 1.99 ms on the 4K soup frame).  2 = that queue sorted by a 2D light-space
+                                      coordinate (counting sort over Morton-ordered cells), so that rays travelling along
+                                      neighbouring lines — whatever depth they start from — sit in one warp: 1.92 ms, but the
+                                      sort costs 0.13 ms, because a per-ray traversal pays its L1 wavefronts per lane whether
+                                      or not its neighbours want the same node. */
 } rtb_option;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

@@ -9,6 +9,8 @@ transcendentals (each test states its budget).
 import numpy as np
 import pytest
 
+from conftest import synthetic_sky
+
 pytestmark = pytest.mark.gpu
 
 NO_RAY_HIT = 0xFFFFFFFF
@@ -646,3 +648,38 @@ def test_example_app_exports_a_png(rtb, tmp_path):
     im = np.array(Image.open(out + ".png"))
     assert im.shape == (270, 480, 4)
     assert len(np.unique(im.reshape(-1, 4), axis=0)) > 500, "a real picture: ground plane, spheres, cubes, sky"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene_kind", ["niels_sun", "niels_point_first", "soup"])
+def test_shadow_order_modes_identical(rtb, scene_kind):
+    """RTB_OPT_SHADOW_ORDER: slot order (one record per pixel and sample), queue of live rays, queue sorted in light space —
+    the shadow words and the frame must be the same bits whatever order the occlusion rays are traced in."""
+    if scene_kind == "soup":
+        n = 200_000
+        scene = dict(triangles=rtb.gen_soup(n, 0xB200), lights=rtb.niels_scene()["lights"][:32],
+                     materials=rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0),
+                     material_indices=np.zeros(n, np.uint32), info=np.array([1, 1, n, 0, 0, 0, 1, 0, 0], np.uint32))
+        w, h, samples, eye, limits = 640, 360, 2, (0.0, 0.0, 13.9), dict(max_triangles=n)
+    else:
+        scene = rtb.niels_scene(0.0)
+        if scene_kind == "niels_point_first":
+            scene["lights"] = np.ascontiguousarray(np.asarray(scene["lights"]).reshape(3, 32)[[2, 1, 0]]).reshape(-1)
+        w, h, samples, eye, limits = 333, 187, 3, (6, 5, 12), dict()
+    outs = []
+    for order in (0, 1, 2):
+        ctx = rtb.Context(**limits)
+        ctx.resize(w, h, samples)
+        ctx.upload_scene(scene, synthetic_sky())
+        ctx.build_accel(rtb.ACCEL_BVH)
+        ctx.set_option(rtb.OPT_SHADOW_ORDER, order)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=eye))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((2.0, 5.0)))
+        for _ in range(2):
+            ctx.dispatch(rtb.PASS_FRAME)
+        outs.append((ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8), ctx.readback(rtb.TGT_LIGHTING)))
+        ctx.close()
+    assert outs[0][0].any(), "no occluded ray in the test frame"
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
