@@ -640,15 +640,32 @@ int rtb_readback_wait(rtb_ctx* c) {
 }
 
 int rtb_untile(rtb_ctx* c, const void* tiledAll, uint32_t nranks, uint32_t slotsPerRank, void* out) {
+    return rtb_untile_on(c, tiledAll, nranks, slotsPerRank, out, nullptr);
+}
+
+int rtb_untile_on(rtb_ctx* c, const void* tiledAll, uint32_t nranks, uint32_t slotsPerRank, void* out, void* cudaStream) {
     if (!c || !tiledAll || !nranks) return c ? fail(c, RTB_ERR_ARG, "rtb_untile: bad argument") : RTB_ERR_ARG;
     RTB_BIND(c);
+    if (cudaStream && !out) return fail(c, RTB_ERR_ARG, "rtb_untile_on: a caller-owned stream needs a caller-owned output frame");
     if (!out) { const int rc = waitCopy(c, {RTB_TGT_RGBA8}); if (rc) return rc; }
     if (!c->width) return fail(c, RTB_ERR_STATE, "rtb_untile before rtb_resize");
     FrameMap fm = c->fm;
     fm.nranks = nranks; fm.rank = 0;
     const uint32_t total = fm.blocksX * fm.blocksY;
     if ((uint64_t)((total + nranks - 1) / nranks) * 1024ull > slotsPerRank) return fail(c, RTB_ERR_ARG, "rtb_untile: slots_per_rank too small for this frame");
-    launch_untile(fm, static_cast<const uint32_t*>(tiledAll), slotsPerRank, out ? static_cast<uint32_t*>(out) : c->rgba8.p, c->stream);
+    launch_untile(fm, static_cast<const uint32_t*>(tiledAll), slotsPerRank, out ? static_cast<uint32_t*>(out) : c->rgba8.p,
+                  cudaStream ? static_cast<cudaStream_t>(cudaStream) : c->stream);
+    RTB_CUDA(c, cudaGetLastError());
+    return RTB_OK;
+}
+
+int rtb_present_host(rtb_ctx* c, void* hostFrame) {
+    if (!c || !hostFrame) return c ? fail(c, RTB_ERR_ARG, "rtb_present_host: null frame") : RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (!c->width) return fail(c, RTB_ERR_STATE, "rtb_present_host before rtb_resize");
+    void* dev = nullptr;
+    RTB_CUDA(c, cudaHostGetDevicePointer(&dev, hostFrame, 0));   // fails unless the frame is page-locked and mapped (cudaHostAlloc / cudaHostRegister)
+    launch_present_host(c->fm, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, c->rgba8.p, static_cast<uint32_t*>(dev), c->stream);
     RTB_CUDA(c, cudaGetLastError());
     return RTB_OK;
 }

@@ -809,4 +809,27 @@ void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsP
     k_untile<<<(n + 255) / 256, 256, 0, st>>>(fm, tiledAll, slotsPerRank, rgba8);
 }
 
+
+// --------------------------------------------------------------------------------------------------------
+// presentation straight into host memory: this rank's pixels to their scan-line positions of a mapped, page-locked frame.
+// One warp writes one 32-pixel row of a block = 128 contiguous bytes (one PCIe write of a useful size).
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_present_host(const FrameMap fm, const uint32_t* __restrict__ tiled, const uint32_t* __restrict__ rgba8,
+                                                      uint32_t* __restrict__ hostFrame) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;      // local block k, then 5 bits of row, 5 bits of column
+    const uint32_t k = t >> 10, r = (t >> 5) & 31u, cx = t & 31u;
+    if (k >= fm.localBlocks) return;
+    const uint32_t g = k * fm.nranks + fm.rank;
+    const uint32_t bx = g % fm.blocksX, by = g / fm.blocksX;
+    const uint32_t x = bx * 32u + cx, y = by * 32u + r;
+    if (x >= fm.w || y >= fm.h) return;
+    const uint32_t slot = k * 1024u + ((r >> 2) * 4u + (cx >> 3)) * 32u + (r & 3u) * 8u + (cx & 7u);
+    hostFrame[(size_t)y * fm.w + x] = tiled ? __ldg(tiled + slot) : __ldg(rgba8 + (size_t)y * fm.w + x);
+}
+void launch_present_host(const FrameMap& fm, const uint32_t* tiled, const uint32_t* rgba8, uint32_t* hostFrame, cudaStream_t st) {
+    const uint32_t n = fm.localBlocks * 1024u;
+    if (!n) return;
+    k_present_host<<<(n + 255) / 256, 256, 0, st>>>(fm, tiled, rgba8, hostFrame);
+}
+
 }  // namespace rtb

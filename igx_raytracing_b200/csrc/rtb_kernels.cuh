@@ -87,6 +87,9 @@ void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint
 // rank 0: gathered [nranks][slotsPerRank] tiled pixels -> scan-line rgba8
 void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsPerRank, uint32_t* rgba8, cudaStream_t s);
 
+// this rank's pixels (from the tiled target when tiled != nullptr, else from the scan-line rgba8 target) into a mapped host frame
+void launch_present_host(const FrameMap& fm, const uint32_t* tiled, const uint32_t* rgba8, uint32_t* hostFrame, cudaStream_t s);
+
 // refit of the 8-wide tree from the current triangle buffer (rtb_refit.cu); levelFirst is a HOST array of levels + 1 entries;
 // areaSums (2 doubles, device) receives the two sums of the SAH cost: node-box areas, leaf-slot areas x triangle counts
 void launch_refit(const TriangleRec* tris, uint32_t triCount, TravTri* tt, uint32_t ttCount, Node8* nodes, const uint32_t* levelFirst,

@@ -27,7 +27,7 @@ NO_HIT = np.float32(3.4028235e38)
 EXPORTS = [
     "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_option", "rtb_set_stream", "rtb_resize", "rtb_upload",
     "rtb_upload_skybox", "rtb_build_accel", "rtb_refit_accel", "rtb_accel_info_get", "rtb_dispatch", "rtb_readback", "rtb_readback_async", "rtb_readback_wait", "rtb_device_ptr", "rtb_sync",
-    "rtb_counters_get", "rtb_probe_l2_read_gbs", "rtb_last_frame_ms", "rtb_trace_rays", "rtb_occlusion_rays", "rtb_untile", "rtb_pack_triangle",
+    "rtb_counters_get", "rtb_probe_l2_read_gbs", "rtb_last_frame_ms", "rtb_trace_rays", "rtb_occlusion_rays", "rtb_untile", "rtb_untile_on", "rtb_present_host", "rtb_pack_triangle",
     "rtb_pack_light_directional", "rtb_pack_light_point", "rtb_pack_material", "rtb_pack_camera", "rtb_load_hdr", "rtb_write_png",
     "rtb_gen_soup", "rtb_gen_heightfield",
 ]
@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         L.rtb_trace_rays.argtypes = [vp, vp, u64, vp, vp, vp, vp]
         L.rtb_occlusion_rays.argtypes = [vp, vp, u64, vp, vp, vp]
         L.rtb_untile.argtypes = [vp, vp, u32, u32, vp]
+        L.rtb_untile_on.argtypes = [vp, vp, u32, u32, vp, vp]
+        L.rtb_present_host.argtypes = [vp, vp]
         L.rtb_pack_triangle.argtypes = [vp, vp, vp]; L.rtb_pack_triangle.restype = None
         L.rtb_pack_light_directional.argtypes = [vp, vp, f, vp]; L.rtb_pack_light_directional.restype = None
         L.rtb_pack_light_point.argtypes = [vp, vp, f, f, f, vp]; L.rtb_pack_light_point.restype = None
@@ -344,6 +346,11 @@ class Context:
         prev = None if prev is None else np.ascontiguousarray(prev, np.uint32)
         self._ck(self.L.rtb_occlusion_rays(self.h, _p(rays), n, _p(md), _p(prev), _p(occ)))
         return occ
+
+    def untile_on(self, tiled_all_ptr, nranks, slots_per_rank, out_ptr, stream_ptr):
+        self._ck(self.L.rtb_untile_on(self.h, C.c_void_p(tiled_all_ptr), nranks, slots_per_rank, C.c_void_p(out_ptr), C.c_void_p(stream_ptr)))
+
+    def present_host(self, host_ptr): self._ck(self.L.rtb_present_host(self.h, C.c_void_p(host_ptr)))
 
     def untile(self, tiled_all_ptr, nranks, slots_per_rank, out_ptr):
         self._ck(self.L.rtb_untile(self.h, C.c_void_p(tiled_all_ptr), nranks, slots_per_rank, C.c_void_p(out_ptr)))

@@ -202,6 +202,15 @@ int  rtb_device_ptr(rtb_ctx* ctx, rtb_target target, void** out_ptr, size_t* out
  * caller has gathered the n tiled buffers (NCCL) into one DEVICE array of n * slots_per_rank words on this context's
  * GPU, rtb_untile writes the scan-line rgba8 frame to rgba8_out_device (NULL: into RTB_TGT_RGBA8).  Stream-ordered. */
 int  rtb_untile(rtb_ctx* ctx, const void* tiled_all_device, uint32_t nranks, uint32_t slots_per_rank, void* rgba8_out_device);
+/* the same on a caller-owned cudaStream_t (NULL = the context's stream), so that the gather and the lay-out of frame k can run
+ * under the rendering of frame k + 1; rgba8_out_device must then be the caller's own frame */
+int  rtb_untile_on(rtb_ctx* ctx, const void* tiled_all_device, uint32_t nranks, uint32_t slots_per_rank, void* rgba8_out_device, void* cuda_stream);
+/* Presentation to the host without a gather: this context's pixels (all of them, or its tiles with RTB_OPT_TILE_COUNT > 1) are
+ * written by a kernel to their scan-line positions of a page-locked, MAPPED host frame of width*height*4 bytes (cudaHostAlloc /
+ * cudaHostRegister with the mapped flag; with several ranks: one frame in shared memory registered by every rank, so that every
+ * GPU uses its own PCIe link instead of rank 0's).  Stream-ordered; the frame may be read after rtb_sync on every rank.
+ * Replaces Graphics::presentToCpu's PBO copy (ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:221-242). */
+int  rtb_present_host(rtb_ctx* ctx, void* host_frame_rgba8);
 /* replaces Graphics::wait (ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:546-595) */
 int  rtb_sync(rtb_ctx* ctx);
 int  rtb_counters_get(rtb_ctx* ctx, rtb_counters* out);

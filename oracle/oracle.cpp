@@ -1067,6 +1067,71 @@ int orc_load_hdr(const char* path, uint16_t* out, uint32_t* w, uint32_t* h) {
     return 0;
 }
 
+// ---- the synthetic scenes of BASELINE.json configs[2] / configs[3] (no reference counterpart).  The oracle carries its own
+// statement of the generators so that the CPU legs of bench.py need nothing from the product library; tests/test_cpu_host.py
+// holds them byte-equal to rtb_gen_soup / rtb_gen_heightfield. ----
+static inline uint64_t gen_mix64(uint64_t z) {   // splitmix64 finaliser
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline float gen_u01(uint64_t seed, uint64_t k) { return (float)(gen_mix64(seed ^ gen_mix64(k)) >> 40) * (1.0f / 16777216.0f); }
+
+// n flat triangles: centre uniform in [-10,10]^3, three vertex offsets uniform in [-0.05,0.05]^3
+void orc_gen_soup(uint64_t n, uint64_t seed, void* out48) {
+    parallelFor((int64_t)n, 4096, [&](int64_t i) {
+        const uint64_t k = (uint64_t)i * 12;
+        const float c[3] = {gen_u01(seed, k) * 20.0f - 10.0f, gen_u01(seed, k + 1) * 20.0f - 10.0f, gen_u01(seed, k + 2) * 20.0f - 10.0f};
+        float p[9];
+        for (int v = 0; v < 3; ++v)
+            for (int a = 0; a < 3; ++a) p[3 * v + a] = c[a] + (gen_u01(seed, k + 3 + 3 * v + a) * 0.1f - 0.05f);
+        orc_triangle_flat(p, (char*)out48 + 48 * (size_t)i);
+    });
+}
+
+// (grid x grid) quads over [-10,10]^2, height = four octaves of lattice value noise, smooth vertex normals (config 4)
+void orc_gen_heightfield(uint32_t grid, uint64_t seed, void* out48) {
+    const uint32_t V = grid + 1;
+    const float step = 20.0f / (float)grid;
+    std::vector<float> h((size_t)V * V);
+    auto heightAt = [&](float x, float z) {
+        float hh = 0.0f, amp = 1.0f, freq = 0.15f;
+        for (int o = 0; o < 4; ++o) {
+            const float fx = x * freq, fz = z * freq;
+            const float x0 = std::floor(fx), z0 = std::floor(fz);
+            const float tx = fx - x0, tz = fz - z0;
+            auto lat = [&](float ix, float iz) {
+                const uint64_t k = ((uint64_t)(int64_t)ix * 0x1F1F1F1Full) ^ ((uint64_t)(int64_t)iz * 0x3D4D51CBull) ^ ((uint64_t)o << 56);
+                return gen_u01(seed, k) * 2.0f - 1.0f;
+            };
+            auto fade = [](float t) { return t * t * t * (t * (t * 6.0f - 15.0f) + 10.0f); };
+            const float sx = fade(tx), sz = fade(tz);
+            const float a = lat(x0, z0), b = lat(x0 + 1, z0), c = lat(x0, z0 + 1), d = lat(x0 + 1, z0 + 1);
+            hh += amp * ((a * (1 - sx) + b * sx) * (1 - sz) + (c * (1 - sx) + d * sx) * sz);
+            amp *= 0.5f; freq *= 2.0f;
+        }
+        return hh * 1.5f;
+    };
+    parallelFor((int64_t)V * V, 4096, [&](int64_t i) { const uint32_t ix = (uint32_t)(i % V), iz = (uint32_t)(i / V); h[(size_t)i] = heightAt(-10.0f + ix * step, -10.0f + iz * step); });
+    auto P = [&](uint32_t ix, uint32_t iz, float* o) { o[0] = -10.0f + ix * step; o[1] = h[(size_t)iz * V + ix]; o[2] = -10.0f + iz * step; };
+    auto N = [&](uint32_t ix, uint32_t iz, float* o) {   // central differences, pointing up
+        const uint32_t xm = ix ? ix - 1 : ix, xp = ix + 1 < V ? ix + 1 : ix, zm = iz ? iz - 1 : iz, zp = iz + 1 < V ? iz + 1 : iz;
+        const float dx = (h[(size_t)iz * V + xp] - h[(size_t)iz * V + xm]) / ((float)(xp - xm) * step);
+        const float dz = (h[(size_t)zp * V + ix] - h[(size_t)zm * V + ix]) / ((float)(zp - zm) * step);
+        const vec3 n = host_normalize3({-dx, 1.0f, -dz});
+        o[0] = n.x; o[1] = n.y; o[2] = n.z;
+    };
+    parallelFor((int64_t)grid * grid, 2048, [&](int64_t q) {
+        const uint32_t ix = (uint32_t)(q % grid), iz = (uint32_t)(q / grid);
+        float p[9], n[9];
+        P(ix, iz, p); P(ix, iz + 1, p + 3); P(ix + 1, iz, p + 6); N(ix, iz, n); N(ix, iz + 1, n + 3); N(ix + 1, iz, n + 6);
+        orc_triangle_normals(p, n, (char*)out48 + 48 * (size_t)(2 * q));
+        P(ix + 1, iz, p); P(ix, iz + 1, p + 3); P(ix + 1, iz + 1, p + 6); N(ix + 1, iz, n); N(ix, iz + 1, n + 3); N(ix + 1, iz + 1, n + 6);
+        orc_triangle_normals(p, n, (char*)out48 + 48 * (size_t)(2 * q + 1));
+    });
+}
+
 // SH/init.comp:12-18
 void orc_init_pass(void* seed24) {
     SeedRec s;

@@ -78,6 +78,10 @@ void orc_niels_scene(double time, void* tris, void* spheres, void* cubes, void* 
 /* Radiance .hdr -> rgba16f as igxi convert.cpp does. out==NULL: only query w,h. Returns 0 on success. */
 int orc_load_hdr(const char* path, uint16_t* out, uint32_t* w, uint32_t* h);
 
+/* the synthetic scenes of BASELINE.json configs[2] / configs[3] (byte-equal to rtb_gen_soup / rtb_gen_heightfield) */
+void orc_gen_soup(uint64_t n, uint64_t seed, void* out_triangles48);
+void orc_gen_heightfield(uint32_t grid, uint64_t seed, void* out_triangles48);
+
 /* ---- device passes (K0-K4) ---- */
 void orc_init_pass(void* seed24);
 /* rays_out: 6 floats/pixel (origin, dir) or NULL; flags_out: 1 byte/pixel or NULL. */

@@ -224,6 +224,16 @@ class Oracle:
         self.lib.orc_niels_scene(float(time), _ptr(tri), _ptr(sph), _ptr(cub), _ptr(pla), _ptr(lig), _ptr(mat), _ptr(idx), _ptr(info))
         return Scene(tri, sph, cub, pla, lig, mat, idx, info, skybox)
 
+    def gen_soup(self, n, seed=0xB200):
+        out = np.zeros(int(n) * 48, np.uint8)
+        self.lib.orc_gen_soup(C.c_uint64(int(n)), C.c_uint64(seed), _ptr(out))
+        return out
+
+    def gen_heightfield(self, grid, seed=0xB200):
+        out = np.zeros(2 * int(grid) * int(grid) * 48, np.uint8)
+        self.lib.orc_gen_heightfield(C.c_uint32(int(grid)), C.c_uint64(seed), _ptr(out))
+        return out
+
     def load_hdr(self, path):
         w, h = C.c_uint32(0), C.c_uint32(0)
         rc = self.lib.orc_load_hdr(path.encode(), None, C.byref(w), C.byref(h))

@@ -285,3 +285,33 @@ def test_example_app_builds_and_fails_loudly_without_a_gpu(rtb, tmp_path):
     import torch
     if not torch.cuda.is_available():
         assert r.returncode == 2 and "no usable CUDA device" in r.stdout
+
+
+def test_oracle_generators_equal_the_product_generators(oracle, rtb):
+    """bench.py's CPU legs build their scenes from the oracle's own generators (nothing of the product is loaded there):
+    the two statements of the synthetic scenes must be the same bytes."""
+    assert np.array_equal(oracle.gen_soup(30000), np.asarray(rtb.gen_soup(30000, 0xB200)).view(np.uint8).reshape(-1))
+    assert np.array_equal(oracle.gen_heightfield(113), np.asarray(rtb.gen_heightfield(113, 0xB200)).view(np.uint8).reshape(-1))
+    a, b = oracle.niels_scene(0.7, None), rtb.niels_scene(0.7)
+    for k in ("triangles", "spheres", "cubes", "planes", "lights", "materials"):
+        assert np.array_equal(getattr(a, k), np.asarray(b[k]).view(np.uint8).reshape(-1)), k
+    assert np.array_equal(oracle.material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0),
+                          np.asarray(rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0)).view(np.uint8).reshape(-1))
+
+
+def test_reference_arm_runs_without_the_product_package():
+    """`bench.py --impl reference` must not import igx_raytracing_b200 (nor map librtb200.so): run it with the package blocked."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, runpy; sys.modules['igx_raytracing_b200'] = None; "
+            "sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'niels360', '--steps', '2', '--warmup', '1']; "
+            "runpy.run_path(%r, run_name='__main__'); "
+            "import os; maps = open('/proc/self/maps').read(); assert 'librtb200' not in maps, 'product library mapped'" % os.path.join(root, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
