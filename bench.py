@@ -348,25 +348,35 @@ def main():
         dist.broadcast_object_list(names, src=0)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=names[0])
+            try:   # attaching registers the segment with this process's resource tracker too (CPython < 3.13); only rank 0 owns it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         shared_np = np.frombuffer(shm.buf, dtype=np.uint32, count=w * h)
         shared_ptr = shared_np.ctypes.data
         rc = torch.cuda.cudart().cudaHostRegister(shared_ptr, w * h * 4, 3)   # portable | mapped
         if int(rc) != 0:
             raise SystemExit(f"cudaHostRegister of the shared frame failed: {rc}")
 
-    def present(k, e2e_gather):
-        """N > 1: gather + lay-out of frame k on the side stream (double-buffered), under the rendering of frame k + 1"""
+    def present(k, mode):
+        """N > 1: presentation of frame k on the side stream (double-buffered), under the rendering of frame k + 1.
+        'device' / 'e2e_gather': NCCL gather + rtb_untile on rank 0 (+ one device-to-host copy); 'e2e': every rank writes its own
+        tiles into the shared host frame."""
         i = k & 1
         stream.wait_event(done[i])                      # buffers i are free again (frame k - 2 has been presented)
         staging[i].copy_(tiled, non_blocking=True)
         ready[i].record(stream)
         with torch.cuda.stream(side):
             side.wait_event(ready[i])
-            dist.gather(staging[i], list(gathered[i].split(slots)) if rank == 0 else None, dst=0)
-            if rank == 0:
-                ctx.untile_on(gathered[i].data_ptr(), world, slots, untiled[i].data_ptr(), side.cuda_stream)
-                if e2e_gather:
-                    frame_pins[i].copy_(untiled[i], non_blocking=True)
+            if mode == "e2e":
+                ctx.present_host(shared_ptr, staging[i].data_ptr(), side.cuda_stream)
+            else:
+                dist.gather(staging[i], list(gathered[i].split(slots)) if rank == 0 else None, dst=0)
+                if rank == 0:
+                    ctx.untile_on(gathered[i].data_ptr(), world, slots, untiled[i].data_ptr(), side.cuda_stream)
+                    if mode == "e2e_gather":
+                        frame_pins[i].copy_(untiled[i], non_blocking=True)
             done[i].record(side)
 
     def frame(k, mode):
@@ -379,10 +389,7 @@ def main():
             ctx.upload_raw(rtb.BUF_SEED, seed_pin.data_ptr(), 24)
         render()
         if world > 1:
-            if mode == "e2e":
-                ctx.present_host(shared_ptr)
-            else:
-                present(k, mode == "e2e_gather")
+            present(k, mode)
         elif mode == "e2e":   # presentToCpu: the rgba8 frame lands in host memory (a copy + fence, like the reference's PBO read-back:
             # frame N is copied out while frame N+1 renders; the timed region ends with the last copy landed)
             ctx.readback_async_into(rtb.TGT_RGBA8, frame_pins[e2e_count[0] & 1].data_ptr(), w * h * 4)
@@ -446,8 +453,8 @@ def main():
     checksum = None
     if world > 1:
         checksum_frame()
-        present(0, False)
-        ctx.present_host(shared_ptr)
+        present(0, "device")
+        present(1, "e2e")
         drain()
         barrier()
         if rank == 0:

@@ -659,13 +659,15 @@ int rtb_untile_on(rtb_ctx* c, const void* tiledAll, uint32_t nranks, uint32_t sl
     return RTB_OK;
 }
 
-int rtb_present_host(rtb_ctx* c, void* hostFrame) {
+int rtb_present_host(rtb_ctx* c, void* hostFrame, const void* tiledSrc, void* cudaStream) {
     if (!c || !hostFrame) return c ? fail(c, RTB_ERR_ARG, "rtb_present_host: null frame") : RTB_ERR_ARG;
     RTB_BIND(c);
     if (!c->width) return fail(c, RTB_ERR_STATE, "rtb_present_host before rtb_resize");
+    if (cudaStream && !tiledSrc) return fail(c, RTB_ERR_ARG, "rtb_present_host: a caller-owned stream needs a caller-owned copy of the tiled pixels");
     void* dev = nullptr;
     RTB_CUDA(c, cudaHostGetDevicePointer(&dev, hostFrame, 0));   // fails unless the frame is page-locked and mapped (cudaHostAlloc / cudaHostRegister)
-    launch_present_host(c->fm, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, c->rgba8.p, static_cast<uint32_t*>(dev), c->stream);
+    const uint32_t* tiled = tiledSrc ? static_cast<const uint32_t*>(tiledSrc) : (c->tileCount > 1 ? c->rgba8Tiled.p : nullptr);
+    launch_present_host(c->fm, tiled, c->rgba8.p, static_cast<uint32_t*>(dev), cudaStream ? static_cast<cudaStream_t>(cudaStream) : c->stream);
     RTB_CUDA(c, cudaGetLastError());
     return RTB_OK;
 }

@@ -86,7 +86,7 @@ def lib() -> C.CDLL:
         L.rtb_occlusion_rays.argtypes = [vp, vp, u64, vp, vp, vp]
         L.rtb_untile.argtypes = [vp, vp, u32, u32, vp]
         L.rtb_untile_on.argtypes = [vp, vp, u32, u32, vp, vp]
-        L.rtb_present_host.argtypes = [vp, vp]
+        L.rtb_present_host.argtypes = [vp, vp, vp, vp]
         L.rtb_pack_triangle.argtypes = [vp, vp, vp]; L.rtb_pack_triangle.restype = None
         L.rtb_pack_light_directional.argtypes = [vp, vp, f, vp]; L.rtb_pack_light_directional.restype = None
         L.rtb_pack_light_point.argtypes = [vp, vp, f, f, f, vp]; L.rtb_pack_light_point.restype = None
@@ -350,7 +350,8 @@ class Context:
     def untile_on(self, tiled_all_ptr, nranks, slots_per_rank, out_ptr, stream_ptr):
         self._ck(self.L.rtb_untile_on(self.h, C.c_void_p(tiled_all_ptr), nranks, slots_per_rank, C.c_void_p(out_ptr), C.c_void_p(stream_ptr)))
 
-    def present_host(self, host_ptr): self._ck(self.L.rtb_present_host(self.h, C.c_void_p(host_ptr)))
+    def present_host(self, host_ptr, tiled_src_ptr=None, stream_ptr=None):
+        self._ck(self.L.rtb_present_host(self.h, C.c_void_p(host_ptr), C.c_void_p(tiled_src_ptr), C.c_void_p(stream_ptr)))
 
     def untile(self, tiled_all_ptr, nranks, slots_per_rank, out_ptr):
         self._ck(self.L.rtb_untile(self.h, C.c_void_p(tiled_all_ptr), nranks, slots_per_rank, C.c_void_p(out_ptr)))

@@ -208,9 +208,11 @@ int  rtb_untile_on(rtb_ctx* ctx, const void* tiled_all_device, uint32_t nranks, 
 /* Presentation to the host without a gather: this context's pixels (all of them, or its tiles with RTB_OPT_TILE_COUNT > 1) are
  * written by a kernel to their scan-line positions of a page-locked, MAPPED host frame of width*height*4 bytes (cudaHostAlloc /
  * cudaHostRegister with the mapped flag; with several ranks: one frame in shared memory registered by every rank, so that every
- * GPU uses its own PCIe link instead of rank 0's).  Stream-ordered; the frame may be read after rtb_sync on every rank.
- * Replaces Graphics::presentToCpu's PBO copy (ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:221-242). */
-int  rtb_present_host(rtb_ctx* ctx, void* host_frame_rgba8);
+ * GPU uses its own PCIe link instead of rank 0's).  Stream-ordered; the frame may be read after the stream has been synchronised
+ * on every rank.  tiled_src_device: NULL = this context's own pixels; otherwise a copy of its RTB_TGT_RGBA8_TILED buffer (so that
+ * the next frame may overwrite the target while this one travels), which is required with a caller-owned cuda_stream (NULL = the
+ * context's stream).  Replaces Graphics::presentToCpu's PBO copy (ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:221-242). */
+int  rtb_present_host(rtb_ctx* ctx, void* host_frame_rgba8, const void* tiled_src_device, void* cuda_stream);
 /* replaces Graphics::wait (ref: IGNIS/api/opengl/src/graphics/gl_graphics.cpp:546-595) */
 int  rtb_sync(rtb_ctx* ctx);
 int  rtb_counters_get(rtb_ctx* ctx, rtb_counters* out);

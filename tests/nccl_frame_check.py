@@ -68,9 +68,19 @@ def main():
         dist.broadcast_object_list(names, src=0)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=names[0])
+            try:   # attaching registers the segment with this process's resource tracker too (CPython < 3.13); only rank 0 owns it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         host = np.frombuffer(shm.buf, dtype=np.uint32, count=w * h)
         assert int(torch.cuda.cudart().cudaHostRegister(host.ctypes.data, w * h * 4, 3)) == 0
         ctx.present_host(host.ctypes.data)
+        staging = tiled.clone()
+        side = torch.cuda.Stream(device=local)
+        side.wait_stream(stream)
+        ctx.present_host(host.ctypes.data, staging.data_ptr(), side.cuda_stream)   # the overlapped form: a copy of the tiles, a second stream
+        side.synchronize()
         ctx.sync()
         torch.cuda.synchronize()
         dist.barrier()
