@@ -77,6 +77,11 @@ struct rtb_ctx {
     uint32_t shadowOrder = 1;         // RTB_OPT_SHADOW_ORDER: 0 slot order, 1 queue of live rays (default), 2 queue sorted in light space
     LightRec light0{};                // host mirror of lights[0] (the one light the shadow pass samples): picks the sort key
     DevBuf<RayRec> queueRays; DevBuf<uint32_t> queueSlots, sortedSlots, queueCell, queueRank, queueHist, queueSums, queueCount;
+    // wavefront path tracing (rtb_path_frame)
+    DevBuf<float4> pathT, pathL, pathDirect; DevBuf<RayRec> pathRays[2], pathShadowRays; DevBuf<uint32_t> pathSlots[2], pathShadowSlots, pathCounts;
+    DevBuf<uint8_t> pathOccA, pathOccB;
+    std::vector<cudaEvent_t> pathEv;   // 4 per depth: nearest-hit launch begin / end, occlusion launch begin / end; then frame begin / end
+    uint32_t pathDepths = 0, pathBounces = 0, pathKernelLaunches = 0; bool pathTimed = false;
     uint32_t releaseBuild = 0;        // RTB_OPT_SHADER_BUILD: 0 = DEBUG build of the reference shaders (what ships), 1 = RELEASE
 
     // rays-in scratch
@@ -353,6 +358,9 @@ void rtb_destroy(rtb_ctx* c) {
     c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release(); c->nodeBox.release(); c->maxBits.release(); c->areaSums.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->rays.release(); c->hits.release(); c->workCounter.release(); c->counters.release();
+    c->pathT.release(); c->pathL.release(); c->pathDirect.release(); c->pathRays[0].release(); c->pathRays[1].release(); c->pathShadowRays.release();
+    c->pathSlots[0].release(); c->pathSlots[1].release(); c->pathShadowSlots.release(); c->pathCounts.release(); c->pathOccA.release(); c->pathOccB.release();
+    for (auto& ev : c->pathEv) if (ev) cudaEventDestroy(ev);
     c->queueRays.release(); c->queueSlots.release(); c->sortedSlots.release(); c->queueCell.release(); c->queueRank.release(); c->queueHist.release(); c->queueSums.release(); c->queueCount.release();
     c->rinRays.release(); c->rinHits.release(); c->rinObj.release(); c->rinT.release(); c->rinUv.release(); c->rinOcc.release(); c->rinOcc2.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -708,6 +716,102 @@ int rtb_last_frame_ms(rtb_ctx* c, float ms[8]) {
     RTB_CUDA(c, cudaEventSynchronize(c->ev[7]));
     for (int i = 0; i < 7; ++i) RTB_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
     RTB_CUDA(c, cudaEventElapsedTime(&ms[7], c->ev[0], c->ev[7]));
+    return RTB_OK;
+}
+
+// ---- wavefront path tracing: BASELINE.json configs[3] (definition: csrc/rtb_path.cuh) ------------------------------------------
+constexpr uint32_t PATH_MAX_BOUNCES = 15;
+
+int rtb_path_frame(rtb_ctx* c, uint32_t bounces) {
+    if (!c) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (bounces > PATH_MAX_BOUNCES) return fail(c, RTB_ERR_ARG, "rtb_path_frame: at most 15 bounces");
+    { const int rc = checkReady(c); if (rc) return rc; }
+    { const int rc = waitCopy(c, {RTB_TGT_SEED, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
+    const uint32_t slots = c->fm.localSlots, depths = bounces + 1;
+    RTB_CUDA(c, c->pathT.alloc(slots)); RTB_CUDA(c, c->pathL.alloc(slots)); RTB_CUDA(c, c->pathDirect.alloc(slots));
+    for (int k = 0; k < 2; ++k) { RTB_CUDA(c, c->pathRays[k].alloc(slots)); RTB_CUDA(c, c->pathSlots[k].alloc(slots)); }
+    RTB_CUDA(c, c->pathShadowRays.alloc(slots)); RTB_CUDA(c, c->pathShadowSlots.alloc(slots)); RTB_CUDA(c, c->pathOccA.alloc(slots)); RTB_CUDA(c, c->pathOccB.alloc(slots));
+    RTB_CUDA(c, c->pathCounts.alloc(2 * (PATH_MAX_BOUNCES + 2)));
+    if (c->pathEv.empty()) {
+        c->pathEv.resize(4 * (PATH_MAX_BOUNCES + 1) + 2, nullptr);
+        for (auto& ev : c->pathEv) RTB_CUDA(c, cudaEventCreate(&ev));
+    }
+    cudaEvent_t* ev = c->pathEv.data();
+    cudaEvent_t evBegin = ev[4 * (PATH_MAX_BOUNCES + 1)], evEnd = ev[4 * (PATH_MAX_BOUNCES + 1) + 1];
+    const SceneView sv = sceneView(c);
+    TraceCounters* cc = c->countersOn ? c->counters.p : nullptr;
+    const PathBuffers pb{c->pathT.p, c->pathL.p, c->pathDirect.p};
+    auto closestQ = [&](uint32_t d) { RayQueue q{}; q.rays = c->pathRays[d & 1].p; q.slotIds = c->pathSlots[d & 1].p; q.count = c->pathCounts.p + 2 * d; return q; };       // rays traced at depth d (d >= 1)
+    auto shadowQ = [&](uint32_t d) { RayQueue q{}; q.rays = c->pathShadowRays.p; q.slotIds = c->pathShadowSlots.p; q.count = c->pathCounts.p + 2 * d + 1; return q; };     // shadow rays of the vertices at depth d
+    uint32_t launches = 0;
+    RTB_CUDA(c, cudaEventRecord(evBegin, c->stream));
+    RTB_CUDA(c, cudaMemsetAsync(c->pathCounts.p, 0, c->pathCounts.bytes(), c->stream));
+    if (c->countersOn) RTB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(TraceCounters), c->stream));
+    launch_init(c->seed.p, c->stream); ++launches;
+    // depth 0: the reference's G-buffer, by the launches RTB_PASS_FRAME uses
+    RTB_CUDA(c, cudaEventRecord(ev[0], c->stream));
+    { const int rc = passRaygen(c, false); if (rc) return rc; }
+    RTB_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    launches += (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt) ? 1u : 3u;
+    auto shadows = [&](uint32_t d) -> int {   // the shadow rays of depth d's vertices, then their direct terms
+        const RayQueue sq = shadowQ(d);
+        RTB_CUDA(c, cudaEventRecord(ev[4 * d + 2], c->stream));
+        launch_occlusion_others(sv, sq.rays, slots, c->pathOccA.p, c->stream, sq.count);
+        launch_trace_any_bytes(sv, sq.rays, slots, c->pathOccB.p, c->workCounter.p, c->stream, cc ? cc + 1 : nullptr, sq.count);
+        RTB_CUDA(c, cudaEventRecord(ev[4 * d + 3], c->stream));
+        launch_path_shadow_resolve(sq, slots, c->pathOccA.p, c->pathOccB.p, pb, c->stream);
+        launches += 3;
+        return RTB_OK;
+    };
+    launch_path_start(c->fm, sv, &c->camera, c->seed.p, bounces, c->dirT.p, c->uvN.p, pb, shadowQ(0), closestQ(1), c->stream); ++launches;
+    { const int rc = shadows(0); if (rc) return rc; }
+    for (uint32_t d = 1; d < depths; ++d) {
+        const RayQueue in = closestQ(d);
+        RTB_CUDA(c, cudaEventRecord(ev[4 * d], c->stream));
+        launch_trace_closest(sv, in.rays, slots, c->hits.p, c->workCounter.p, cc, PACKETS_OFF, c->stream, in.count);
+        RTB_CUDA(c, cudaEventRecord(ev[4 * d + 1], c->stream));
+        launch_path_vertex(c->fm, sv, &c->camera, c->seed.p, d, bounces, in, c->hits.p, pb, shadowQ(d), closestQ(d + 1), c->stream);
+        launches += 2;
+        const int rc = shadows(d); if (rc) return rc;
+    }
+    launch_path_resolve(c->fm, sv, &c->camera, c->seed.p, pb, c->accum.p, c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, c->stream); ++launches;
+    RTB_CUDA(c, cudaEventRecord(evEnd, c->stream));
+    RTB_CUDA(c, cudaGetLastError());
+    c->pathDepths = depths; c->pathBounces = bounces; c->pathKernelLaunches = launches; c->pathTimed = true;
+    return RTB_OK;
+}
+
+int rtb_path_stats_get(rtb_ctx* c, rtb_path_stats* out) {
+    if (!c || !out) return RTB_ERR_ARG;
+    RTB_BIND(c);
+    if (!c->pathTimed) return fail(c, RTB_ERR_STATE, "no rtb_path_frame has been dispatched yet");
+    std::memset(out, 0, sizeof *out);
+    uint32_t counts[2 * (PATH_MAX_BOUNCES + 2)];
+    RTB_CUDA(c, cudaMemcpyAsync(counts, c->pathCounts.p, sizeof counts, cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEvent_t* ev = c->pathEv.data();
+    out->depths = c->pathDepths; out->kernel_launches = c->pathKernelLaunches;
+    out->closest_launches = c->pathDepths; out->shadow_launches = c->pathDepths;
+    for (uint32_t d = 0; d < c->pathDepths; ++d) {
+        float a = 0.0f, b = 0.0f;
+        RTB_CUDA(c, cudaEventElapsedTime(&a, ev[4 * d], ev[4 * d + 1]));
+        RTB_CUDA(c, cudaEventElapsedTime(&b, ev[4 * d + 2], ev[4 * d + 3]));
+        out->closest_ms_at_depth[d] = a; out->shadow_ms_at_depth[d] = b;
+        out->closest_ms += a; out->shadow_ms += b;
+        out->closest_rays_at_depth[d] = d == 0 ? (uint64_t)c->width * c->height : counts[2 * d];
+        out->shadow_rays_at_depth[d] = counts[2 * d + 1];
+    }
+    if (c->tileCount > 1) {   // this rank's camera rays: its pixels
+        uint64_t px = 0;
+        for (uint32_t k = 0; k < c->fm.localBlocks; ++k) {
+            const uint32_t g = k * c->fm.nranks + c->fm.rank, bx = g % c->fm.blocksX, by = g / c->fm.blocksX;
+            px += (uint64_t)std::min(32u, c->width - bx * 32u) * std::min(32u, c->height - by * 32u);
+        }
+        out->closest_rays_at_depth[0] = px;
+    }
+    for (uint32_t d = 0; d < c->pathDepths; ++d) { out->closest_rays += out->closest_rays_at_depth[d]; out->shadow_rays += out->shadow_rays_at_depth[d]; }
+    RTB_CUDA(c, cudaEventElapsedTime(&out->total_ms, ev[4 * (PATH_MAX_BOUNCES + 1)], ev[4 * (PATH_MAX_BOUNCES + 1) + 1]));
     return RTB_OK;
 }
 

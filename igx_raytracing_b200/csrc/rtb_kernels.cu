@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
     int stack[STACK_SIZE];
+    const uint32_t nRays = a.countPtr ? __ldg(a.countPtr) : a.n;   // a queue's length lives on the device
 
     bool active = false, exhausted = false;
     uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT;
@@ -117,10 +118,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) 
             const int leader = __ffs(need) - 1;
             if ((int)lane == leader) base = atomicAdd(a.workCounter, (uint32_t)__popc(need));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            exhausted = base + (uint32_t)__popc(need) >= a.n;
+            exhausted = base + (uint32_t)__popc(need) >= nRays;
             if (!active) {
                 slot = base + (uint32_t)__popc(need & lanesBelow);
-                if (slot < a.n) {
+                if (slot < nRays) {
                     const float4 o = __ldg(reinterpret_cast<const float4*>(a.rays + slot));
                     const float4 d = __ldg(reinterpret_cast<const float4*>(a.rays + slot) + 1);
                     if (d.w >= 0.0f) {
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) 
                         if (COUNT && bestId != NO_RAY_HIT) cHits++;
                     } else if (MODE == MODE_ANY_BITS) {
                         if (bestId != NO_RAY_HIT) {
-                            const uint32_t sample = slot / a.fm.localSlots, i = slot - sample * a.fm.localSlots;
+                            const uint32_t j = a.slotIds ? __ldg(a.slotIds + slot) : slot;
+                            const uint32_t sample = j / a.fm.localSlots, i = j - sample * a.fm.localSlots;
                             uint32_t x, y;
                             slotToPixel(a.fm, i, x, y);
                             atomicOr(a.bits + indexToLight(x, y, a.fm.w, a.fm.h, sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
@@ -309,10 +311,11 @@ template <int MODE>
 __global__ void __launch_bounds__(BRUTE_THREADS) k_trace_brute(const RayRec* __restrict__ rays, uint32_t n,
                                                                const TriangleRec* __restrict__ tris, uint32_t triCount,
                                                                TriHit* __restrict__ hits, uint32_t* __restrict__ bits, const FrameMap fm,
-                                                               uint8_t* __restrict__ bytes, const bool rejectZeroEdge) {
+                                                               uint8_t* __restrict__ bytes, const bool rejectZeroEdge,
+                                                               const uint32_t* __restrict__ slotIds, const uint32_t* __restrict__ countPtr) {
     __shared__ float4 sTri[BRUTE_CHUNK * 3];
     const uint32_t slot = blockIdx.x * BRUTE_THREADS + threadIdx.x;
-    const bool inRange = slot < n;
+    const bool inRange = slot < (countPtr ? __ldg(countPtr) : n);
     float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, -1.0f);
     if (inRange) { o = __ldg(reinterpret_cast<const float4*>(rays + slot)); d = __ldg(reinterpret_cast<const float4*>(rays + slot) + 1); }
     const bool live = inRange && d.w >= 0.0f;
@@ -343,7 +346,8 @@ __global__ void __launch_bounds__(BRUTE_THREADS) k_trace_brute(const RayRec* __r
         *reinterpret_cast<float4*>(hits + slot) = *reinterpret_cast<float4*>(&h);
     } else if (MODE == MODE_ANY_BITS) {
         if (live && object != NO_RAY_HIT) {
-            const uint32_t sample = slot / fm.localSlots, i = slot - sample * fm.localSlots;
+            const uint32_t j = slotIds ? __ldg(slotIds + slot) : slot;
+            const uint32_t sample = j / fm.localSlots, i = j - sample * fm.localSlots;
             uint32_t x, y;
             slotToPixel(fm, i, x, y);
             atomicOr(bits + indexToLight(x, y, fm.w, fm.h, sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
@@ -382,21 +386,21 @@ void launch_primary_fused(const FrameMap& fm, const SceneView& sv, const CameraR
 }
 
 void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
-                          TraceCounters* counters, int packets, cudaStream_t st) {
+                          TraceCounters* counters, int packets, cudaStream_t st, const uint32_t* countPtr) {
     if (!n) return;
     if (sv.info.triangleCount == 0) { k_fill_miss<<<(n + 255) / 256, 256, 0, st>>>(hits, n); return; }
-    if (sv.useBvh == ACCEL_KIND_CWBVH && packets) {
+    if (sv.useBvh == ACCEL_KIND_CWBVH && packets && !countPtr) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
         a.hits = hits;
         if (packets == PACKETS_FRUSTUM) { if (counters) launchPacket<true, true>(a, st); else launchPacket<false, true>(a, st); }
         else { if (counters) launchPacket<true, false>(a, st); else launchPacket<false, false>(a, st); }
     } else if (sv.useBvh) {
         TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
-        a.hits = hits;
+        a.hits = hits; a.countPtr = countPtr;
         launchTrace<MODE_CLOSEST>(sv, a, counters != nullptr, st);
     } else {
         FrameMap fm{};
-        k_trace_brute<MODE_CLOSEST><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, hits, nullptr, fm, nullptr, !sv.releaseBuild);
+        k_trace_brute<MODE_CLOSEST><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, hits, nullptr, fm, nullptr, !sv.releaseBuild, nullptr, countPtr);
     }
 }
 
@@ -408,20 +412,21 @@ void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec
         a.bits = bits; a.fm = fm; a.slotIds = slotIds; a.countPtr = countPtr;
         launchTrace<MODE_ANY_BITS>(sv, a, counters != nullptr, st);
     } else {
-        k_trace_brute<MODE_ANY_BITS><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, bits, fm, nullptr, !sv.releaseBuild);
+        k_trace_brute<MODE_ANY_BITS><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, bits, fm, nullptr, !sv.releaseBuild, slotIds, countPtr);
     }
 }
 
-void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n, uint8_t* occluded, uint32_t* workCounter, cudaStream_t st) {
+void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n, uint8_t* occluded, uint32_t* workCounter, cudaStream_t st,
+                            TraceCounters* counters, const uint32_t* countPtr) {
     if (!n) return;
     if (sv.info.triangleCount == 0) { cudaMemsetAsync(occluded, 0, n, st); return; }
     if (sv.useBvh) {
-        TraceArgs a = makeArgs(sv, rays, n, workCounter, nullptr);
-        a.bytes = occluded;
-        launchTrace<MODE_ANY_BYTES>(sv, a, false, st);
+        TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
+        a.bytes = occluded; a.countPtr = countPtr;
+        launchTrace<MODE_ANY_BYTES>(sv, a, counters != nullptr, st);
     } else {
         FrameMap fm{};
-        k_trace_brute<MODE_ANY_BYTES><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, nullptr, fm, occluded, !sv.releaseBuild);
+        k_trace_brute<MODE_ANY_BYTES><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, nullptr, fm, occluded, !sv.releaseBuild, nullptr, countPtr);
     }
 }
 
@@ -675,18 +680,19 @@ void launch_clear_hit_strips(const FrameMap& fm, const float4* dirT, uint32_t sa
     k_clear_hit_strips<<<(n + 255) / 256, 256, 0, st>>>(fm, dirT, samples, bits);
 }
 
-__global__ void __launch_bounds__(256) k_occlusion_others(const SceneView sv, RayRec* __restrict__ rays, uint32_t n, uint8_t* __restrict__ occluded) {
+__global__ void __launch_bounds__(256) k_occlusion_others(const SceneView sv, RayRec* __restrict__ rays, uint32_t n, uint8_t* __restrict__ occluded,
+                                                          const uint32_t* __restrict__ countPtr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (countPtr ? __ldg(countPtr) : n)) return;
     const float4 o = *reinterpret_cast<const float4*>(rays + i), d = *(reinterpret_cast<const float4*>(rays + i) + 1);
     Ray ray; ray.pos = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
     const bool occ = occludedByOthers(sv, ray, d.w, fbits(o.w));
     occluded[i] = occ ? 1 : 0;
     if (occ || !(d.w > 0.0f)) rays[i].tmax = -1.0f;   // nothing left for the triangle search
 }
-void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t st) {
+void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t st, const uint32_t* countPtr) {
     if (!n) return;
-    k_occlusion_others<<<(n + 255) / 256, 256, 0, st>>>(sv, rays, n, occluded);
+    k_occlusion_others<<<(n + 255) / 256, 256, 0, st>>>(sv, rays, n, occluded, countPtr);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -833,3 +839,4 @@ void launch_present_host(const FrameMap& fm, const uint32_t* tiled, const uint32
 }
 
 }  // namespace rtb
+#include "rtb_path.cuh"

@@ -49,7 +49,7 @@ void launch_raygen(const FrameMap& fm, const CameraRec* cam, const SeedRec* seed
 // (PACKETS_FRUSTUM, rtb_trace8f.cuh); otherwise one traversal per lane.
 enum { PACKETS_OFF = 0, PACKETS_UNION = 1, PACKETS_FRUSTUM = 3 };
 void launch_trace_closest(const SceneView& sv, const RayRec* rays, uint32_t n, TriHit* hits, uint32_t* workCounter,
-                          TraceCounters* counters, int packets, cudaStream_t s);
+                          TraceCounters* counters, int packets, cudaStream_t s, const uint32_t* countPtr = nullptr);   // countPtr: the rays are a queue of *countPtr (device) entries, n its capacity
 // raygen + nearest hit (frustum packets) + G-buffer finish as ONE launch: no ray / hit records in between
 void launch_primary_fused(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, float4* dirT, float4* uvN,
                           uint32_t* workCounter, cudaStream_t s);
@@ -74,7 +74,7 @@ void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec
 void launch_clear_hit_strips(const FrameMap& fm, const float4* dirT, uint32_t samples, uint32_t* bits, cudaStream_t s);
 // any-hit, one byte per ray (rays-in mode)
 void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n, uint8_t* occluded, uint32_t* workCounter,
-                            cudaStream_t s);
+                            cudaStream_t s, TraceCounters* counters = nullptr, const uint32_t* countPtr = nullptr);
 // lighting.comp + composite.comp
 enum { SHADE_LIGHTING = 1, SHADE_COMPOSITE = 2, SHADE_BOTH = 3 };
 void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
@@ -83,9 +83,19 @@ void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const Camer
 // rays-in helpers
 void launch_finish_rays(const SceneView& sv, const RayRec* rays, const TriHit* hits, uint32_t n, uint32_t* object, float* t,
                         float2* uv, cudaStream_t s);
-void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t s);
+void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t s, const uint32_t* countPtr = nullptr);
 // rank 0: gathered [nranks][slotsPerRank] tiled pixels -> scan-line rgba8
 void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsPerRank, uint32_t* rgba8, cudaStream_t s);
+
+// ---- wavefront path tracing (rtb_path.cuh): the diffuse-bounce workload of BASELINE.json configs[3] ----
+struct PathBuffers { float4* throughput; float4* radiance; float4* direct; };
+void launch_path_start(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t bounces, const float4* dirT, const float4* uvN,
+                       const PathBuffers& pb, const RayQueue& shadowQ, const RayQueue& nextQ, cudaStream_t s);
+void launch_path_vertex(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t depth, uint32_t bounces, const RayQueue& inQ,
+                        const TriHit* hits, const PathBuffers& pb, const RayQueue& shadowQ, const RayQueue& nextQ, cudaStream_t s);
+void launch_path_shadow_resolve(const RayQueue& shadowQ, uint32_t maxRays, const uint8_t* occOthers, const uint8_t* occTris, const PathBuffers& pb, cudaStream_t s);
+void launch_path_resolve(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, const PathBuffers& pb, float4* accum, uint32_t* rgba8,
+                         uint32_t* rgba8Tiled, cudaStream_t s);
 
 // this rank's pixels (from the tiled target when tiled != nullptr, else from the scan-line rgba8 target) into a mapped host frame
 void launch_present_host(const FrameMap& fm, const uint32_t* tiled, const uint32_t* rgba8, uint32_t* hostFrame, cudaStream_t s);

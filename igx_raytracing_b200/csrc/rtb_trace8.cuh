@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_CW_MINBLOCKS) k_trace_cwbvh
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
     uint2 lstack[LOCAL_STACK];
-    const uint32_t nRays = (MODE == MODE_ANY_BITS && a.countPtr) ? __ldg(a.countPtr) : a.n;   // a queue's length lives on the device
+    const uint32_t nRays = a.countPtr ? __ldg(a.countPtr) : a.n;   // a queue's length lives on the device
 
     bool active = false, exhausted = false;
     uint32_t slot = 0, prev = 0, bestId = NO_RAY_HIT, octinv = 0;

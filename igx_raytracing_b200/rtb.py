@@ -27,10 +27,23 @@ NO_HIT = np.float32(3.4028235e38)
 EXPORTS = [
     "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_option", "rtb_set_stream", "rtb_resize", "rtb_upload",
     "rtb_upload_skybox", "rtb_build_accel", "rtb_refit_accel", "rtb_accel_info_get", "rtb_dispatch", "rtb_readback", "rtb_readback_async", "rtb_readback_wait", "rtb_device_ptr", "rtb_sync",
-    "rtb_counters_get", "rtb_probe_l2_read_gbs", "rtb_last_frame_ms", "rtb_trace_rays", "rtb_occlusion_rays", "rtb_untile", "rtb_untile_on", "rtb_present_host", "rtb_pack_triangle",
+    "rtb_counters_get", "rtb_probe_l2_read_gbs", "rtb_last_frame_ms", "rtb_trace_rays", "rtb_occlusion_rays", "rtb_untile", "rtb_untile_on", "rtb_present_host", "rtb_path_frame", "rtb_path_stats_get", "rtb_pack_triangle",
     "rtb_pack_light_directional", "rtb_pack_light_point", "rtb_pack_material", "rtb_pack_camera", "rtb_load_hdr", "rtb_write_png",
     "rtb_gen_soup", "rtb_gen_heightfield",
 ]
+
+
+class PathStats(C.Structure):
+    _fields_ = [("depths", C.c_uint32), ("closest_launches", C.c_uint32), ("shadow_launches", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("closest_rays_at_depth", C.c_uint64 * 16), ("shadow_rays_at_depth", C.c_uint64 * 16),
+                ("closest_ms", C.c_float), ("shadow_ms", C.c_float), ("total_ms", C.c_float), ("closest_ms_at_depth", C.c_float * 16), ("shadow_ms_at_depth", C.c_float * 16)]
+
+    def as_dict(self):
+        d = int(self.depths)
+        return dict(depths=d, kernel_launches=int(self.kernel_launches), closest_rays=int(self.closest_rays), shadow_rays=int(self.shadow_rays),
+                    closest_rays_at_depth=[int(v) for v in self.closest_rays_at_depth[:d]], shadow_rays_at_depth=[int(v) for v in self.shadow_rays_at_depth[:d]],
+                    closest_ms=float(self.closest_ms), shadow_ms=float(self.shadow_ms), total_ms=float(self.total_ms),
+                    closest_ms_at_depth=[float(v) for v in self.closest_ms_at_depth[:d]], shadow_ms_at_depth=[float(v) for v in self.shadow_ms_at_depth[:d]])
 
 
 class Limits(C.Structure):
@@ -87,6 +100,8 @@ def lib() -> C.CDLL:
         L.rtb_untile.argtypes = [vp, vp, u32, u32, vp]
         L.rtb_untile_on.argtypes = [vp, vp, u32, u32, vp, vp]
         L.rtb_present_host.argtypes = [vp, vp, vp, vp]
+        L.rtb_path_frame.argtypes = [vp, u32]
+        L.rtb_path_stats_get.argtypes = [vp, vp]
         L.rtb_pack_triangle.argtypes = [vp, vp, vp]; L.rtb_pack_triangle.restype = None
         L.rtb_pack_light_directional.argtypes = [vp, vp, f, vp]; L.rtb_pack_light_directional.restype = None
         L.rtb_pack_light_point.argtypes = [vp, vp, f, f, f, vp]; L.rtb_pack_light_point.restype = None
@@ -346,6 +361,13 @@ class Context:
         prev = None if prev is None else np.ascontiguousarray(prev, np.uint32)
         self._ck(self.L.rtb_occlusion_rays(self.h, _p(rays), n, _p(md), _p(prev), _p(occ)))
         return occ
+
+    def path_frame(self, bounces): self._ck(self.L.rtb_path_frame(self.h, int(bounces)))
+
+    def path_stats(self) -> PathStats:
+        st = PathStats()
+        self._ck(self.L.rtb_path_stats_get(self.h, C.byref(st)))
+        return st
 
     def untile_on(self, tiled_all_ptr, nranks, slots_per_rank, out_ptr, stream_ptr):
         self._ck(self.L.rtb_untile_on(self.h, C.c_void_p(tiled_all_ptr), nranks, slots_per_rank, C.c_void_p(out_ptr), C.c_void_p(stream_ptr)))

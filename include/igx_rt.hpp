@@ -236,10 +236,13 @@ public:
     enum class Flags : u32 { NONE = 0 };
 
 private:
+    // One pool per object type.  Slot i holds the record at bytes[i * stride]; owner[i] is its handle (0 = free slot).
+    // `device` mirrors what the device buffer holds, so that changed records travel as contiguous runs.
     struct Object {
-        List<u8> cpuData, gpuData;      // working copy / compacted copy that mirrors the device buffer
-        List<bool> markedForUpdate;
-        List<u64> toIndex;
+        List<u8> cpuData, gpuData;      // working copy / what the device holds
+        List<bool> markedForUpdate;     // slot changed since the last upload
+        List<u64> toIndex;              // owner handle per slot
+        u32 holes = 0;                  // free slots below the pool's count (add() only searches when there are any)
     };
     static constexpr usz strides[6] = {sizeof(Light), sizeof(Material), sizeof(Triangle), sizeof(Sphere), sizeof(Cube), sizeof(Plane)};
     static constexpr rtb_buffer bufferIds[6] = {RTB_BUF_LIGHTS, RTB_BUF_MATERIALS, RTB_BUF_TRIANGLES, RTB_BUF_SPHERES, RTB_BUF_CUBES, RTB_BUF_PLANES};
@@ -250,7 +253,6 @@ private:
     u64 counter = 0;
     SceneGraphInfo info{}, limits{};
     List<u32> materialByObject;
-    u32 geometryId = 0;
     bool geometryDirty = true;      // triangles changed since the last acceleration-structure build or refit
     bool topologyDirty = true;      // ... and their number or order changed too: a refit is not enough
     String sceneName;
@@ -288,6 +290,7 @@ public:
             const u8 t = u8(it->second.type);
             objects[t].toIndex[it->second.index] = 0;
             objects[t].markedForUpdate[it->second.index] = false;
+            ++objects[t].holes;
             if (it->second.type == SceneObjectType::TRIANGLE) geometryDirty = topologyDirty = true;
             entries.erase(it);
         }
@@ -329,25 +332,27 @@ public:
         return true;
     }
 
-    // compact every pool and upload what changed (scene_graph.cpp:267-323)
+    // Behaviour of the reference's per-frame update (scene_graph.cpp:267-323, 378-522), restated: every pool is squeezed (holes
+    // out, order kept; lights additionally grouped directional < spot < point, order kept inside a group), records that
+    // changed or moved are uploaded as contiguous runs, and the material-index table lists the geometry in the order the
+    // shaders number it: triangles, spheres, cubes, planes.
     virtual void update(f64) {
-        geometryId = 0;
         lastError = 0;
         for (u8 t = 0; t < 6; ++t) {
-            compact(SceneObjectType(t));
+            squeeze(SceneObjectType(t));
             Object& obj = objects[t];
             const usz stride = strides[t];
             const u32 n = info.objectCount[t];
-            u32 i = 0;
-            while (i < n) {   // one upload per dirty run
+            for (u32 i = 0; i < n;) {   // one upload per dirty run
                 if (!obj.markedForUpdate[i]) { ++i; continue; }
                 u32 j = i;
-                while (j < n && obj.markedForUpdate[j]) { obj.markedForUpdate[j] = false; ++j; }
+                while (j < n && obj.markedForUpdate[j]) obj.markedForUpdate[j++] = false;
                 std::memcpy(obj.gpuData.data() + stride * i, obj.cpuData.data() + stride * i, usz(j - i) * stride);
                 note(rtb_upload(device.get(), bufferIds[t], stride * i, usz(j - i) * stride, obj.gpuData.data() + stride * i));
                 i = j;
             }
         }
+        syncMaterialIndices();
         note(rtb_upload(device.get(), RTB_BUF_SCENE_INFO, 0, sizeof(info), &info));
     }
 
@@ -378,96 +383,92 @@ public:
 private:
     void note(int rc) { if (rc && !lastError) lastError = rc; }
 
-    u64 addInternal(SceneObjectType t, const void* v, usz siz, u32 mat) {   // scene_graph.cpp:343-376
-        do { ++counter; } while (!counter || entries.find(counter) != entries.end());
-        u32& ind = info.objectCount[u8(t)];
-        Object& obj = objects[u8(t)];
-        u32 i = 0;
-        for (; i < ind; ++i) if (!obj.toIndex[i]) break;
-        if (i == ind) {
-            if (ind == limits.objectCount[u8(t)]) return 0;
-            ++ind;
-        }
-        if (obj.cpuData.size() < usz(i + 1) * siz) { const usz want = std::max<usz>(usz(i + 1) * siz, obj.cpuData.size() * 2); obj.cpuData.resize(want); obj.gpuData.resize(want); }
-        entries[counter] = {i, mat, t};
-        obj.markedForUpdate[i] = true;
-        obj.toIndex[i] = counter;
-        std::memcpy(obj.cpuData.data() + siz * i, v, siz);
+    // A new object takes the lowest free slot of its pool, or the next one; 0 when the pool is at capacity.
+    // (behaviour of scene_graph.cpp:343-376)
+    u64 addInternal(SceneObjectType t, const void* v, usz siz, u32 mat) {
+        Object& pool = objects[u8(t)];
+        u32& used = info.objectCount[u8(t)];
+        u32 slot = used;
+        if (pool.holes) slot = u32(std::find(pool.toIndex.begin(), pool.toIndex.begin() + used, u64(0)) - pool.toIndex.begin());
+        if (slot == used) {
+            if (used == limits.objectCount[u8(t)]) return 0;
+            ++used;
+        } else
+            --pool.holes;
+        u64 handle = counter;
+        do { ++handle; } while (!handle || entries.count(handle));
+        counter = handle;
+        const usz end = usz(slot + 1) * siz;
+        if (pool.cpuData.size() < end) { const usz want = std::max(end, pool.cpuData.size() * 2); pool.cpuData.resize(want); pool.gpuData.resize(want); }
+        std::memcpy(pool.cpuData.data() + siz * slot, v, siz);
+        pool.toIndex[slot] = handle;
+        pool.markedForUpdate[slot] = true;
+        entries[handle] = Entry{slot, mat, t};
         if (t == SceneObjectType::TRIANGLE) geometryDirty = topologyDirty = true;
-        return counter;
+        return handle;
     }
 
-    // remove holes; lights additionally ordered directional < spot < point (scene_graph.cpp:378-522)
-    void compact(SceneObjectType type) {
-        Object& obj = objects[u8(type)];
+    static u32 lightGroup(const u8* record) { const u16 ty = u16(reinterpret_cast<const Light*>(record)->type); return ty < 3 ? ty : 2u; }
+
+    // Squeeze one pool: the live slots keep their relative order (lights: grouped by type first), move to the front, and every
+    // record whose slot changed is marked for upload.  One pass builds the new order, one pass moves.
+    void squeeze(SceneObjectType type) {
+        Object& pool = objects[u8(type)];
         const usz stride = strides[u8(type)];
-        u32& count = info.objectCount[u8(type)];
-        if (!count) return;
-        u8* cpuPtr = obj.cpuData.data();
-        u8* gpuPtr = obj.gpuData.data();
-        bool needsRemap = false;
-        u32 j = 0;
+        u32& used = info.objectCount[u8(type)];
+        List<u32> order;   // order[newSlot] = oldSlot
+        order.reserve(used);
+        for (u32 i = 0; i < used; ++i) if (pool.toIndex[i]) order.push_back(i);
         if (type == SceneObjectType::LIGHT) {
-            u32 counters[3]{}, placed[3]{};
-            const Light* lc = reinterpret_cast<const Light*>(cpuPtr);
-            for (u32 i = 0; i < count; ++i) {
-                if (!obj.toIndex[i]) { needsRemap = true; continue; }
-                ++j; ++counters[u16(lc[i].type) < 3 ? u16(lc[i].type) : 2];
-            }
-            for (int k = 0; k < 3; ++k) if (info.lightsCount[k] != counters[k]) { info.lightsCount[k] = counters[k]; needsRemap = true; }
-            if (!needsRemap) return;
-            List<u64> newIndex(obj.toIndex.size(), 0);
-            List<bool> newMarked(obj.markedForUpdate.size(), false);
-            for (u32 i = 0; i < count; ++i) {
-                const u64 id = obj.toIndex[i];
-                if (!id) continue;
-                const u32 lt = u16(lc[i].type) < 3 ? u16(lc[i].type) : 2;
-                u32 globalId = placed[lt]++;
-                for (u32 k = 0; k < lt; ++k) globalId += counters[k];
-                newIndex[globalId] = id;
-                newMarked[globalId] = obj.markedForUpdate[i] || entries[id].index != globalId;
-                entries[id].index = globalId;
-                std::memcpy(gpuPtr + usz(globalId) * stride, cpuPtr + usz(i) * stride, stride);
-            }
-            obj.toIndex.swap(newIndex); obj.markedForUpdate.swap(newMarked);
-        } else {
-            for (u32 i = 0; i < count; ++i) {
-                const u64 id = obj.toIndex[i];
-                if (!id) { needsRemap = true; continue; }
-                if (type != SceneObjectType::MATERIAL) {
-                    u32& dst = materialByObject[geometryId];
-                    const u32 src = entries[id].material;
-                    if (dst != src || !materialUploaded(geometryId)) {
-                        dst = src;
-                        note(rtb_upload(device.get(), RTB_BUF_MATERIAL_INDICES, usz(geometryId) * 4, 4, &dst));
-                        markMaterialUploaded(geometryId);
-                    }
-                    ++geometryId;
-                }
-            }
-            if (!needsRemap) return;
-            for (u32 i = 0; i < count; ++i) {
-                const u64 id = obj.toIndex[i];
-                if (!id) continue;
-                obj.toIndex[j] = id;
-                const bool moved = entries[id].index != j;
-                const bool dirty = obj.markedForUpdate[i] || moved;
-                if (moved) obj.markedForUpdate[i] = false;
-                obj.markedForUpdate[j] = dirty;
-                entries[id].index = j;
-                std::memcpy(gpuPtr + usz(j) * stride, cpuPtr + usz(i) * stride, stride);
-                ++j;
-            }
-            for (u32 i = j; i < count; ++i) { obj.toIndex[i] = 0; obj.markedForUpdate[i] = false; }
-            if (type == SceneObjectType::TRIANGLE) geometryDirty = topologyDirty = true;
+            const u8* rec = pool.cpuData.data();
+            std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return lightGroup(rec + usz(a) * stride) < lightGroup(rec + usz(b) * stride); });
+            u32 groups[3] = {0, 0, 0};
+            for (u32 o : order) ++groups[lightGroup(rec + usz(o) * stride)];
+            for (int k = 0; k < 3; ++k) info.lightsCount[k] = groups[k];
         }
-        count = j;
-        std::memcpy(cpuPtr, gpuPtr, usz(j) * stride);
+        bool identity = order.size() == used;
+        for (u32 p = 0; identity && p < order.size(); ++p) identity = order[p] == p;
+        if (identity) return;
+        // move: the device mirror doubles as scratch (it is rewritten run by run from cpuData afterwards)
+        List<u64> owners(pool.toIndex.size(), 0);
+        List<bool> marks(pool.markedForUpdate.size(), false);
+        u8* scratch = pool.gpuData.data();
+        for (u32 p = 0; p < order.size(); ++p) {
+            const u32 q = order[p];
+            std::memcpy(scratch + usz(p) * stride, pool.cpuData.data() + usz(q) * stride, stride);
+            owners[p] = pool.toIndex[q];
+            marks[p] = pool.markedForUpdate[q] || p != q;
+            entries[owners[p]].index = p;
+        }
+        std::memcpy(pool.cpuData.data(), scratch, order.size() * stride);
+        pool.toIndex.swap(owners);
+        pool.markedForUpdate.swap(marks);
+        pool.holes = 0;
+        used = u32(order.size());
+        if (type == SceneObjectType::TRIANGLE) geometryDirty = topologyDirty = true;
+    }
+
+    // materialIndices[global object id] in the shaders' numbering (triangles, then spheres, cubes, planes); changed entries
+    // travel as runs (behaviour of scene_graph.cpp:464-489)
+    void syncMaterialIndices() {
+        u32 g = 0;
+        if (materialSent.size() < materialByObject.size()) materialSent.resize(materialByObject.size(), false);
+        auto flushRun = [&](u32 first, u32 last) { if (last > first) note(rtb_upload(device.get(), RTB_BUF_MATERIAL_INDICES, usz(first) * 4, usz(last - first) * 4, materialByObject.data() + first)); };
+        u32 runStart = 0;
+        bool inRun = false;
+        for (SceneObjectType t : {SceneObjectType::TRIANGLE, SceneObjectType::SPHERE, SceneObjectType::CUBE, SceneObjectType::PLANE}) {
+            const Object& pool = objects[u8(t)];
+            for (u32 i = 0; i < info.objectCount[u8(t)]; ++i, ++g) {
+                const u32 want = entries[pool.toIndex[i]].material;
+                const bool changed = materialByObject[g] != want || !materialSent[g];
+                if (changed) { materialByObject[g] = want; materialSent[g] = true; if (!inRun) { inRun = true; runStart = g; } }
+                else if (inRun) { flushRun(runStart, g); inRun = false; }
+            }
+        }
+        if (inRun) flushRun(runStart, g);
     }
 
     List<bool> materialSent;
-    bool materialUploaded(u32 g) { if (materialSent.size() <= g) materialSent.resize(usz(g) + 1, false); return materialSent[g]; }
-    void markMaterialUploaded(u32 g) { if (materialSent.size() <= g) materialSent.resize(usz(g) + 1, false); materialSent[g] = true; }
 };
 
 // ---- RenderTask hierarchy (ref: igx/include/helpers/render_task.hpp:21-65) -------------------------------------

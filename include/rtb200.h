@@ -220,6 +220,25 @@ int  rtb_counters_get(rtb_ctx* ctx, rtb_counters* out);
  * nearest-hit traversal, G-buffer finish, shadow-ray set-up, occlusion traversal, lighting+composite, total.  Synchronises. */
 int  rtb_last_frame_ms(rtb_ctx* ctx, float out_ms[8]);
 
+/* ---- diffuse bounces (BASELINE.json configs[3]; NO reference counterpart: the reference traces no secondary rays, its
+ * "reflection" is one skybox tap, ref: res/shaders/light.glsl:205-219) ------------------------------------------------------------
+ * One frame of wavefront path tracing, 1 sample per pixel: init, the reference's G-buffer (primary ray + nearest hit, as
+ * RTB_PASS_RAYGEN), then per path vertex one shadow ray to lights[0] built as shadow.comp builds it, the Cook-Torrance term of
+ * lighting.comp when it is not occluded, and — up to `bounces` times — a cosine-distributed bounce about the shading normal with
+ * throughput *= albedo; the sky on a miss; composite.comp's tail (progressive accumulation under USE_SUPERSAMPLING, exposure,
+ * rgba8).  The full definition is in csrc/rtb_path.cuh (tests hold it against a CPU statement of the same).  bounces = 0 gives the
+ * direct-lighting image.  Targets written: DIR_T, UV_NORMAL, ACCUM (if supersampling), RGBA8, RGBA8_TILED, SEED. */
+int  rtb_path_frame(rtb_ctx* ctx, uint32_t bounces);
+typedef struct rtb_path_stats {
+    uint32_t depths;                      /* bounces + 1 */
+    uint32_t closest_launches, shadow_launches, kernel_launches;   /* per frame */
+    uint64_t closest_rays, shadow_rays;   /* rays of the last frame: camera + bounce rays, shadow rays (this context's tiles) */
+    uint64_t closest_rays_at_depth[16], shadow_rays_at_depth[16];
+    float    closest_ms, shadow_ms, total_ms;   /* CUDA events on the context's stream around the traversal launches / the frame */
+    float    closest_ms_at_depth[16], shadow_ms_at_depth[16];
+} rtb_path_stats;
+int  rtb_path_stats_get(rtb_ctx* ctx, rtb_path_stats* out);   /* synchronises */
+
 /* Measurement aid, not on the hot path: read-only streaming bandwidth (1e9 B/s) over a buffer of `bytes` (choose <= 64 MiB so
  * that it stays L2-resident) with L2-only cached loads — the denominator of the L2 roofline. */
 int  rtb_probe_l2_read_gbs(rtb_ctx* ctx, size_t bytes, double* out_gbs);

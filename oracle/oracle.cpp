@@ -1265,6 +1265,113 @@ void orc_frame(const orc_scene* s, const void* cam144, void* seed24, uint32_t sa
     orc_composite(s, cam144, seed24, dirT, uvN, lighting_f16, accum, rgba8);
 }
 
+// ---- diffuse bounces: BASELINE.json configs[3].  NOT reference behaviour (the reference traces no secondary rays):
+// a restatement of the definition in igx_raytracing_b200/csrc/rtb_path.cuh, built from the reference functions above, so that the
+// CUDA path can be held bit-equal to a CPU statement of the same semantics.  Depth 0 is the reference's own G-buffer. ----
+namespace {
+struct PathOut { bool shadow, bounce; Ray sray; float maxDist; Ray bray; vec3 direct; };
+PathOut pathVertex(const Scene& sc, vec2 uvBase, uint32_t depth, uint32_t bounces, vec3 pos, vec3 v, uint32_t object, vec3 n, vec3& T, vec3& L) {
+    PathOut o;
+    o.shadow = false; o.bounce = false; o.direct = {0, 0, 0}; o.maxDist = -1.0f;
+    const MatU m = unpackMaterial(sc.mat[sc.matIdx[object]]);
+    L = L + T * m.emissive;
+    const uint32_t N = 2u * (bounces + 1u);
+    if (sc.lightCount) {
+        const vec2 random = rand2(uvBase + hammersley(2u * depth, N));
+        const LightRec& light = sc.light[0];
+        const vec3 F0 = mix(vec3{0.04f, 0.04f, 0.04f}, m.albedo, m.metallic);
+        const float NdotV = glsl_max(dot(v, -n), 0.0f);
+        const vec3 c = shadeLight(F0, m.albedo, m.roughness, m.metallic, light, pos, n, v, NdotV, random) * (float)sc.lightCount;
+        const vec3 contribution = T * c;
+        float brightness, dist;
+        const vec3 l = getDirToLight(light, pos, brightness, dist, random);
+        float maxDist = -1.0f;
+        if (dist >= 0.0f) {
+            uint32_t ro; std::memcpy(&ro, &light.rad, 4);
+            const vec2 radOrigin = unpackHalf2x16(ro);
+            if (dist >= radOrigin.y && dist < radOrigin.x) maxDist = dist - radOrigin.y;
+        } else
+            maxDist = noHit;
+        if (maxDist != -1.0f) { o.shadow = true; o.direct = contribution; o.sray = {pos, -l}; o.maxDist = maxDist; }
+        else L = L + contribution;
+    }
+    if (depth < bounces) {
+        const vec2 r = rand2(uvBase + hammersley(2u * depth + 1u, N));
+        const vec3 nn = normalize(n);
+        const vec3 nf = dot(v, nn) > 0.0f ? -nn : nn;
+        const float phi = (2.0f * pi) * r.x;
+        const float cosT = std::sqrt(1.0f - r.y), sinT = std::sqrt(r.y);
+        const float x = cr_cos(phi) * sinT, y = cr_sin(phi) * sinT;
+        const vec3 bitangent = normalize(getPerpendicularVector(nf));
+        const vec3 tangent = cross(bitangent, nf);
+        const vec3 d = normalize(bitangent * x + tangent * y + nf * cosT);
+        T = T * m.albedo;
+        o.bounce = true; o.bray = {pos, d};
+    }
+    return o;
+}
+}  // namespace
+
+void orc_path_frame(const orc_scene* s, const void* cam144, void* seed24, uint32_t bounces, float* dirT, float* uvN, float* accum,
+                    uint32_t* rgba8, float* radiance3, uint64_t* rays_out) {
+    Scene sc = view(s);
+    CameraRec cam; std::memcpy(&cam, cam144, 144);
+    orc_init_pass(seed24);
+    SeedRec seed; std::memcpy(&seed, seed24, 24);
+    const int64_t W = cam.width, H = cam.height;
+    std::vector<float> dT, uN;
+    if (!dirT) { dT.resize((size_t)W * H * 4); dirT = dT.data(); }
+    if (!uvN) { uN.resize((size_t)W * H * 4); uvN = uN.data(); }
+    std::atomic<uint64_t> rays{0};
+    parallelFor(H, 1, [&](int64_t y) {
+        uint64_t nrays = 0;
+        for (int64_t x = 0; x < W; ++x) {
+            const size_t i = (size_t)(y * W + x);
+            float* dt = dirT + 4 * i; float* un = uvN + 4 * i;
+            raygenPixel(sc, cam, seed, (uint32_t)x, (uint32_t)y, dt, un, nullptr, nullptr);
+            ++nrays;
+            const vec3 dxyz = {dt[0], dt[1], dt[2]};
+            uint32_t object = fbits(dt[3]);
+            vec3 T = {1, 1, 1}, L = {0, 0, 0};
+            const vec2 loc = {(float)x, (float)y};
+            const vec2 uvBase = (loc + rand2(loc + vec2{seed.randomX, seed.randomY})) / 128.0f;
+            if (object == noRayHit)
+                L = sampleSkybox(sc, cam, normalize(dxyz));
+            else {
+                vec3 pos = v3(cam.eye) + dxyz, v = normalize(dxyz), n = decodeNormal(fbits(un[2]), fbits(un[3]));
+                for (uint32_t depth = 0;; ++depth) {
+                    PathOut o = pathVertex(sc, uvBase, depth, bounces, pos, v, object, n, T, L);
+                    if (o.shadow) { ++nrays; if (!traceOcclusion(sc, o.sray, o.maxDist, object)) L = L + o.direct; }
+                    if (!o.bounce) break;
+                    ++nrays;
+                    const Hit hit = traceGeometry(sc, o.bray, object);
+                    if (hit.hitT == noHit) { L = L + T * sampleSkybox(sc, cam, o.bray.dir); break; }
+                    uint32_t en[2];
+                    encodeNormalGpu(hit.objectNormal, en);
+                    n = decodeNormal(en[0], en[1]);
+                    pos = o.bray.pos + o.bray.dir * hit.hitT;
+                    v = o.bray.dir;
+                    object = hit.object;
+                }
+            }
+            if (radiance3) { radiance3[3 * i] = L.x; radiance3[3 * i + 1] = L.y; radiance3[3 * i + 2] = L.z; }
+            vec3 color = L;
+            if (g_mode == ORC_MODE_DEBUG && (std::isnan(color.x) || std::isnan(color.y) || std::isnan(color.z))) color = {0.0f, 0.0f, 10000.0f};
+            if (cam.flags & 2u) {
+                float* a = accum + 4 * i;
+                if (seed.sampleCount > 1) color = color + vec3{a[0], a[1], a[2]};
+                a[0] = color.x; a[1] = color.y; a[2] = color.z; a[3] = 0.0f;
+                color = color / (float)seed.sampleCount;
+            }
+            const vec3 e = -color * cam.exposure;
+            color = vmax(vec3{1.0f, 1.0f, 1.0f} - vec3{cr_exp(e.x), cr_exp(e.y), cr_exp(e.z)}, vec3{0, 0, 0});
+            rgba8[i] = unorm8(color.x) | (unorm8(color.y) << 8) | (unorm8(color.z) << 16) | (255u << 24);
+        }
+        rays.fetch_add(nrays, std::memory_order_relaxed);
+    });
+    if (rays_out) *rays_out = rays.load();
+}
+
 uint64_t orc_frame_pixels(const orc_scene* s, const void* cam144, const void* seed24, uint32_t samples, const uint32_t* xy,
                           uint64_t n, uint32_t* rgba8, uint32_t* object, float* t) {
     Scene sc = view(s);

@@ -102,6 +102,12 @@ void orc_composite(const orc_scene* s, const void* cam144, const void* seed24, c
 /* whole frame K0..K4 (seed updated in place). Any output may be NULL except rgba8. */
 void orc_frame(const orc_scene* s, const void* cam144, void* seed24, uint32_t samples,
                float* dirT, float* uvN, uint32_t* bits, uint16_t* lighting_f16, float* accum, uint32_t* rgba8);
+/* Diffuse bounces (BASELINE.json configs[3]).  NOT reference behaviour — the reference traces no secondary rays; this restates the
+   definition in igx_raytracing_b200/csrc/rtb_path.cuh from the reference functions so that the CUDA path has a CPU statement of
+   the same semantics to be compared with.  K0 + one path-traced frame; depth 0 is the reference's G-buffer.  dirT / uvN / accum /
+   radiance3 / rays_out may be NULL (accum must be given under USE_SUPERSAMPLING). */
+void orc_path_frame(const orc_scene* s, const void* cam144, void* seed24, uint32_t bounces, float* dirT, float* uvN, float* accum,
+                    uint32_t* rgba8, float* radiance3, uint64_t* rays_out);
 /* K1..K4 for a list of pixels only (bounded CPU-baseline sample); seed must already be initialised
    by orc_init_pass. Returns the number of rays traced (primary + shadow). */
 uint64_t orc_frame_pixels(const orc_scene* s, const void* cam144, const void* seed24, uint32_t samples,

@@ -326,6 +326,19 @@ class Oracle:
                            _ptr(out["bits"]), _ptr(out["lighting"]), _ptr(accum), _ptr(out["rgba8"]))
         return out
 
+    def path_frame(self, scene, cam, seed, bounces, accum=None):
+        """K0 + one frame with diffuse bounces (our definition, see oracle.h); `seed` is updated in place."""
+        w, h = self._wh(cam)
+        out = dict(dirT=np.zeros((h, w, 4), np.float32), uvN=np.zeros((h, w, 4), np.float32), rgba8=np.zeros((h, w), np.uint32),
+                   radiance=np.zeros((h, w, 3), np.float32))
+        rays = C.c_uint64(0)
+        cs = scene.c()
+        self.lib.orc_path_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 6
+        self.lib.orc_path_frame(C.byref(cs), _ptr(cam), _ptr(seed), int(bounces), _ptr(out["dirT"]), _ptr(out["uvN"]), _ptr(accum),
+                                _ptr(out["rgba8"]), _ptr(out["radiance"]), C.byref(rays))
+        out["rays"] = int(rays.value)
+        return out
+
     def frame_pixels(self, scene, cam, seed, samples, xy):
         xy = np.ascontiguousarray(xy, np.uint32).reshape(-1, 2)
         n = xy.shape[0]
