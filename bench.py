@@ -50,8 +50,8 @@ WORKLOADS = {
                            desc="configs[3] geometry: 10M-triangle displaced height field at 1080p, first hit + 1 shadow ray (no bounces: the reference has none)"),
     # BASELINE.json configs[3] in full: 4 diffuse bounces (SURVEY.md §8d config 4 semantics; the reference has no bounce rays, so
     # this is rtb_path_frame, not RTB_PASS_FRAME), camera above the field looking down so that the mesh fills the frame
-    "heightfield10m_b4": dict(kind="heightfield", grid=2236, width=1920, height=1080, eye=(0.0, 7.5, 0.0), pitch=1.5707964, samples=1, bounces=4,
-                              desc="configs[3]: 10M-triangle displaced height field at 1080p, 1 spp, 4 diffuse bounces + 1 shadow ray per vertex (wavefront path tracing, rtb_path_frame), camera at (0,7.5,0) looking straight down: the mesh fills the frame"),
+    "heightfield10m_b4": dict(kind="heightfield", grid=2236, width=1920, height=1080, eye=(0.0, 7.5, 0.0), pitch=1.5707964, fov=120.0, samples=1, bounces=4,
+                              desc="configs[3]: 10M-triangle displaced height field at 1080p, 1 spp, 4 diffuse bounces + 1 shadow ray per vertex (wavefront path tracing, rtb_path_frame), camera at (0,7.5,0) looking straight down, fov parameter 120 (the reference's convention moves the plane: +-46 x +-30 degrees): the mesh fills the frame"),
     # BASELINE.json configs[4]: 8K, 16 spp progressive accumulation (the reference's export path: the command list replayed
     # per sample with USE_SUPERSAMPLING, raytracing_interface.cpp:196-242), screen tiles across the ranks, one gather per frame
     "niels8k16": dict(kind="niels", width=7680, height=4320, eye=(6.0, 5.0, 12.0), samples=1, spp=16,
@@ -96,7 +96,8 @@ def oracle_scene(orc, wl):
 
 
 def camera_kwargs(wl):
-    return dict(eye=wl["eye"], pitch=wl.get("pitch", 0.0), yaw=wl.get("yaw", 0.0), flags=2 if wl.get("spp", 1) > 1 else 0)
+    return dict(eye=wl["eye"], pitch=wl.get("pitch", 0.0), yaw=wl.get("yaw", 0.0), left_fov=wl.get("fov", 70.0), right_fov=wl.get("fov", 70.0),
+                flags=2 if wl.get("spp", 1) > 1 else 0)
 
 
 class ClockSampler:

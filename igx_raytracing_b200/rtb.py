@@ -315,7 +315,8 @@ class Context:
         w, h, s = self.width, self.height, self.samples
         shape, dt = {TGT_DIR_T: ((h, w, 4), np.float32), TGT_UV_NORMAL: ((h, w, 4), np.float32),
                      TGT_SHADOW_BITS: ((shadow_words(w, h, s),), np.uint32), TGT_LIGHTING: ((h, w, 4), np.uint16),
-                     TGT_ACCUM: ((h, w, 4), np.float32), TGT_RGBA8: ((h, w), np.uint32), TGT_SEED: ((24,), np.uint8)}[target]
+                     TGT_ACCUM: ((h, w, 4), np.float32), TGT_RGBA8: ((h, w), np.uint32), TGT_SEED: ((24,), np.uint8),
+                     TGT_RGBA8_TILED: ((self.device_ptr(TGT_RGBA8_TILED)[1] // 4 if target == TGT_RGBA8_TILED else 0,), np.uint32)}[target]
         out = np.zeros(shape, dt)
         self._ck(self.L.rtb_readback(self.h, target, _p(out), out.nbytes))
         return out

@@ -1374,6 +1374,11 @@ void orc_path_frame(const orc_scene* s, const void* cam144, void* seed24, uint32
 
 uint64_t orc_frame_pixels(const orc_scene* s, const void* cam144, const void* seed24, uint32_t samples, const uint32_t* xy,
                           uint64_t n, uint32_t* rgba8, uint32_t* object, float* t) {
+    return orc_frame_pixels_ex(s, cam144, seed24, samples, xy, n, rgba8, object, t, nullptr, nullptr, nullptr);
+}
+
+uint64_t orc_frame_pixels_ex(const orc_scene* s, const void* cam144, const void* seed24, uint32_t samples, const uint32_t* xy,
+                             uint64_t n, uint32_t* rgba8, uint32_t* object, float* t, float* dirT4, uint8_t* shadowed, uint8_t* flags) {
     Scene sc = view(s);
     CameraRec cam; std::memcpy(&cam, cam144, 144);
     SeedRec seed; std::memcpy(&seed, seed24, 24);
@@ -1382,8 +1387,9 @@ uint64_t orc_frame_pixels(const orc_scene* s, const void* cam144, const void* se
         uint64_t rays = 0;
         const uint32_t x = xy[2 * k], y = xy[2 * k + 1];
         float dirT[4], uvN[4], accum[4] = {0, 0, 0, 0};
-        raygenPixel(sc, cam, seed, x, y, dirT, uvN, nullptr, nullptr);
+        raygenPixel(sc, cam, seed, x, y, dirT, uvN, nullptr, flags ? flags + k : nullptr);
         rays += 1;
+        if (dirT4) std::memcpy(dirT4 + 4 * k, dirT, 16);
         const bool isHit = fbits(dirT[3]) != noRayHit;
         // per-pixel stand-in for the shadow-mask buffer: bit (x&15 | (y&1)<<4) of one word per sample
         std::vector<uint32_t> words(samples, 0u);
@@ -1392,6 +1398,7 @@ uint64_t orc_frame_pixels(const orc_scene* s, const void* cam144, const void* se
                 if (shadowPixel(sc, cam, seed, samples, x, y, i, dirT, nullptr)) words[i] = 0xFFFFFFFFu;
                 rays += 1;
             }
+        if (shadowed) shadowed[k] = (isHit && samples && words[0]) ? 1 : 0;   // sample 0's bit
         vec3 l = {0, 0, 0};
         {
             // lightingPixel indexes the real mask; emulate with a 1-word-per-sample view

@@ -113,6 +113,11 @@ void orc_path_frame(const orc_scene* s, const void* cam144, void* seed24, uint32
 uint64_t orc_frame_pixels(const orc_scene* s, const void* cam144, const void* seed24, uint32_t samples,
                           const uint32_t* xy, uint64_t n, uint32_t* rgba8, uint32_t* object, float* t);
 
+/* the same with more outputs (any may be NULL): the G-buffer texel dirT (4 floats per pixel), sample 0's shadow bit, and the
+   edge / tie / degeneracy flags of the primary ray (ORC_FLAG_*) */
+uint64_t orc_frame_pixels_ex(const orc_scene* s, const void* cam144, const void* seed24, uint32_t samples, const uint32_t* xy,
+                             uint64_t n, uint32_t* rgba8, uint32_t* object, float* t, float* dirT4, uint8_t* shadowed, uint8_t* flags);
+
 #ifdef __cplusplus
 }
 #endif

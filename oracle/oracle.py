@@ -339,6 +339,19 @@ class Oracle:
         out["rays"] = int(rays.value)
         return out
 
+    def frame_pixels_ex(self, scene, cam, seed, samples, xy):
+        """frame_pixels plus the G-buffer texel, sample 0's shadow bit and the primary ray's edge / tie flags"""
+        xy = np.ascontiguousarray(xy, np.uint32).reshape(-1, 2)
+        n = xy.shape[0]
+        out = dict(rgba8=np.zeros(n, np.uint32), object=np.zeros(n, np.uint32), t=np.zeros(n, np.float32), dirT=np.zeros((n, 4), np.float32),
+                   shadowed=np.zeros(n, np.uint8), flags=np.zeros(n, np.uint8))
+        cs = scene.c()
+        self.lib.orc_frame_pixels_ex.restype = C.c_uint64
+        self.lib.orc_frame_pixels_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
+        out["rays"] = int(self.lib.orc_frame_pixels_ex(C.byref(cs), _ptr(cam), _ptr(seed), samples, _ptr(xy), n, _ptr(out["rgba8"]), _ptr(out["object"]),
+                                                       _ptr(out["t"]), _ptr(out["dirT"]), _ptr(out["shadowed"]), _ptr(out["flags"])))
+        return out
+
     def frame_pixels(self, scene, cam, seed, samples, xy):
         xy = np.ascontiguousarray(xy, np.uint32).reshape(-1, 2)
         n = xy.shape[0]

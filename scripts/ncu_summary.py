@@ -50,13 +50,17 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    """src: a .ncu-rep, or the CSV `ncu -i x.ncu-rep --page raw --csv` made of it on the GPU box (reports are too big to bring back)"""
+    if src.endswith(".csv"):
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
     with open(dst, "w") as f:
         f.write(f"# ncu --set full summary of {src}\n\n")
-        f.write("| metric | unit | " + " | ".join(f"`{r[ki].split('(')[0]}`" for r in rows[2:]) + " |\n")
+        f.write("| metric | unit | " + " | ".join(f"`{short_name(r[ki])}`" for r in rows[2:]) + " |\n")
         f.write("|---|---|" + "---:|" * (len(rows) - 2) + "\n")
         for k in KEYS:
             if k in hdr:
@@ -64,5 +68,40 @@ def full(src, dst):
                 f.write(f"| {k} | {units[i]} | " + " | ".join(r[i] for r in rows[2:]) + " |\n")
 
 
+def short_name(full_name):
+    """k_trace_cwbvh<(int)1, (bool)0>(rtb::TraceArgs) -> k_trace_cwbvh<1,0>; k_trace_cwbvh_frustum<...> -> k_trace_cwbvh_frustum"""
+    import re
+    base = full_name.split("(rtb::")[0].split("(const rtb::")[0]
+    base = base[5:] if base.startswith("void ") else base
+    m = re.match(r"(?:rtb::)?(\w+)<(.*)>", base)
+    if not m:
+        return base.replace("rtb::", "")
+    name, args = m.group(1), re.sub(r"\((?:int|bool)\)", "", m.group(2)).replace(" ", "")
+    return name if name.endswith(("frustum", "packet")) else f"{name}<{args}>"
+
+
+def traffic(src_csv, workload, dst_json="profiles/trace_traffic.json"):
+    """src_csv: `ncu -i x.ncu-rep --page raw --csv` of a --set full capture of scripts/profile_frame.py.  Adds, for `workload`,
+    dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches of each kernel) to dst_json."""
+    import json
+    rows = list(csv.reader(open(src_csv)))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = collections.OrderedDict()
+    for r in rows[2:]:
+        v = float(r[ri].replace(",", "")) * scale.get(units[ri], 1.0) + float(r[wi].replace(",", "")) * scale.get(units[wi], 1.0)
+        agg.setdefault(short_name(r[ki]), []).append(v)
+    data = json.load(open(dst_json))
+    data[workload] = {k: int(sum(v) / len(v)) for k, v in agg.items()}
+    data[workload]["_launches_captured"] = {k: len(v) for k, v in agg.items()}
+    data[workload]["_capture"] = src_csv
+    json.dump(data, open(dst_json, "w"), indent=1)
+    print(workload, data[workload])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -100,7 +100,7 @@ def test_path_frame_10m_mesh_bvh_equals_brute_on_a_tile_subsample(rtb):
     scene = dict(triangles=rtb.gen_heightfield(grid, 0xB200), lights=rtb.niels_scene()["lights"][:32],
                  materials=rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0),
                  material_indices=np.zeros(n, np.uint32), info=np.array([1, 1, n, 0, 0, 0, 1, 0, 0], np.uint32))
-    cam_kw = dict(eye=(0.0, 7.5, 0.0), pitch=1.5707964, flags=2)
+    cam_kw = dict(eye=(0.0, 7.5, 0.0), pitch=1.5707964, left_fov=120.0, right_fov=120.0, flags=2)   # bench.py's heightfield10m_b4 camera
     a = gpu_path(rtb, scene, None, w, h, cam_kw, bounces, rtb.ACCEL_BVH, limits=dict(max_triangles=n), tile=(0, 64))
     b = gpu_path(rtb, scene, None, w, h, cam_kw, bounces, rtb.ACCEL_BRUTE, limits=dict(max_triangles=n), tile=(0, 64))
     assert a["stats"]["closest_rays_at_depth"][0] > 30000
