@@ -196,7 +196,7 @@ def run_reference(args, wl, rank, world):
     osc = oracle_scene(orc, wl)
     n_tri = int(osc.info[2])
     w, h = wl["width"], wl["height"]
-    per_step = 1024 if n_tri > 100_000 else min(w * h, 262_144)
+    per_step = max(64, min(1024, int(1.0e9 / n_tri))) if n_tri > 100_000 else min(w * h, 262_144)   # ~1 s of host work per step
     cam = orc.camera(w, h, **camera_kwargs(wl))
     seed = orc.init_pass(orc.seed((0.0, 0.0)))
     total_rays, total_s = 0, 0.0
@@ -237,8 +237,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--packets", default="auto", choices=["off", "union", "frustum", "auto"],
                     help="camera rays as 8x4-pixel packets (RTB_OPT_PRIMARY_PACKETS); auto = the library's patch-size rule")
-    ap.add_argument("--shadow-order", default="queue", choices=["slots", "queue", "sorted"],
+    ap.add_argument("--shadow-order", default="queue", choices=["slots", "queue", "sorted", "beams"],
                     help="RTB_OPT_SHADOW_ORDER: occlusion rays in wavefront-slot order, as a queue of live rays, or that queue sorted in light space")
+    ap.add_argument("--builder", default="host", choices=["host", "device"], help="RTB_OPT_ACCEL_BUILDER: who builds the 8-wide tree")
     ap.add_argument("--median-frames", type=int, default=100, help="frames timed one by one for the median (capped to ~10 s)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -289,7 +290,8 @@ def main():
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_option(rtb.OPT_PRIMARY_PACKETS, {"off": 0, "union": 1, "auto": 2, "frustum": 3}[args.packets])
-    ctx.set_option(rtb.OPT_SHADOW_ORDER, {"slots": 0, "queue": 1, "sorted": 2}[args.shadow_order])
+    ctx.set_option(rtb.OPT_SHADOW_ORDER, {"slots": 0, "queue": 1, "sorted": 2, "beams": 3}[args.shadow_order])
+    ctx.set_option(rtb.OPT_ACCEL_BUILDER, {"host": 0, "device": 1}[args.builder])
     ctx.resize(w, h, samples)
     ctx.upload_scene(scene, None)
     ctx.build_accel(rtb.ACCEL_BVH)
@@ -623,7 +625,8 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        n_px = 16384 if n_tri > 100_000 else min(w * h, 1 << 20)
+        # about 15 s of host work: the brute-force loops cost ~ pixels x 1.5 rays x triangles
+        n_px = max(256, min(16384, int(1.6e10 / n_tri))) if n_tri > 100_000 else min(w * h, 1 << 20)
         reps = 1 if n_tri > 100_000 else 25   # small scenes: a frame takes milliseconds on the host; best of 25 passes
         v, rays, secs, threads = cpu_time_sample(wl, n_px, repeats=reps)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -646,11 +649,13 @@ def main():
         "ms_per_step_median": median_ms,
         "per_frame_ms": {"frames": int(n_med), "median": median_ms, "p10": float(per_frame[int(0.1 * (n_med - 1))]), "p90": float(per_frame[int(0.9 * (n_med - 1))]),
                          "min": float(per_frame[0]), "max": float(per_frame[-1]), "value_at_median": rays_per_frame / (median_ms * 1e-3) / 1e6},
-        "config": {"workload": wl["desc"], "spp": spp, "bounces": bounces, "rays_per_frame": rays_per_frame, "hit_fraction": tot[6] / (w * h),
+        "config": {"workload": wl["desc"], "spp": spp, "bounces": bounces, "rays_per_frame": rays_per_frame,
+                   "hit_fraction": (path.closest_rays_at_depth[1] / max(path.closest_rays_at_depth[0], 1) if bounces else tot[6] / (w * h)),
                    "l2": "no explicit flush: each frame streams ~0.9 GB of ray / G-buffer data through the 126 MB L2 between traversal launches; the BVH (nodes + triangles) stays resident as it would in steady-state rendering",
                    "partition": f"{world} ranks x interleaved 32x32-pixel blocks, scene+BVH replicated, NCCL gather of rgba8 tiles to rank 0 + rtb_untile on a second stream under the next frame" if world > 1 else "single GPU",
                    "bvh": {"nodes": info.node_count, "node_bytes": info.node_bytes, "leaves": info.leaf_count, "depth": info.max_depth,
-                           "sah_cost": info.sah_cost, "build_ms": info.build_ms, "leaf_node_extent": info.leaf_node_extent, "bytes": bvh_bytes},
+                           "sah_cost": info.sah_cost, "build_ms": info.build_ms, "leaf_node_extent": info.leaf_node_extent, "bytes": bvh_bytes,
+                           "builder": {0: "host (binned SAH, optimal collapse)", 1: "device (Morton sort, radix tree, greedy collapse)"}.get(info.builder, "?")},
                    "primary_packets": {0: "per ray", 1: "union packets", 3: "frustum packets"}.get(info.primary_packets, str(info.primary_packets)), "packets_option": args.packets,
                    "shadow_order": args.shadow_order,
                    "phase_ms_rank0": {k: float(v) for k, v in zip(["init", "raygen", "trace_primary", "finish", "shadowgen", "trace_shadow", "shade", "total"], phases)}},

@@ -74,9 +74,11 @@ struct rtb_ctx {
     uint32_t packetsOpt = 2;          // RTB_OPT_PRIMARY_PACKETS: 0 off, 1 union packets, 2 auto, 3 frustum packets
     int lastPrimaryPackets = 0;       // PACKETS_* of the last camera-ray launch
     uint32_t fuseOpt = 1;             // RTB_OPT_FUSE_PRIMARY
+    uint32_t builderOpt = 0;          // RTB_OPT_ACCEL_BUILDER: 0 host (binned SAH + optimal collapse), 1 device (LBVH + greedy collapse)
+    uint32_t builtBy = 0;             // builder of the tree in use
     uint32_t shadowOrder = 1;         // RTB_OPT_SHADOW_ORDER: 0 slot order, 1 queue of live rays (default), 2 queue sorted in light space
     LightRec light0{};                // host mirror of lights[0] (the one light the shadow pass samples): picks the sort key
-    DevBuf<RayRec> queueRays; DevBuf<uint32_t> queueSlots, sortedSlots, queueCell, queueRank, queueHist, queueSums, queueCount;
+    DevBuf<RayRec> queueRays; DevBuf<uint32_t> queueSlots, sortedSlots, queueCell, queueRank, queueHist, queueSums, queueCount, queueFallbackCount;
     // wavefront path tracing (rtb_path_frame)
     DevBuf<float4> pathT, pathL, pathDirect; DevBuf<RayRec> pathRays[2], pathShadowRays; DevBuf<uint32_t> pathSlots[2], pathShadowSlots, pathCounts;
     DevBuf<uint8_t> pathOccA, pathOccB;
@@ -277,7 +279,7 @@ int passShadow(rtb_ctx* c, bool mark) {
         return RTB_OK;
     }
     // queue of live rays, optionally sorted in light space
-    RayBin bin = c->shadowOrder >= 2 ? shadowBin(c, maxRays) : RayBin{};
+    RayBin bin = c->shadowOrder >= 2 && !(c->countersOn && c->countersMode == 1) ? shadowBin(c, maxRays) : RayBin{};
     const uint32_t cells = bin.kind ? 1u << (2 * bin.bits) : 0u;
     RTB_CUDA(c, c->queueCount.alloc(1)); RTB_CUDA(c, c->queueSlots.alloc(maxRays));
     RTB_CUDA(c, cudaMemsetAsync(c->queueCount.p, 0, 4, c->stream));
@@ -294,7 +296,13 @@ int passShadow(rtb_ctx* c, bool mark) {
     const uint32_t* slots = c->queueSlots.p;
     if (bin.kind) { launch_sort_rays(q, cells, maxRays, c->rays.p, c->sortedSlots.p, c->stream); slots = c->sortedSlots.p; }
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
-    launch_trace_any_bits(c->fm, sv, c->rays.p, maxRays, c->bits.p, c->workCounter.p, counters, slots, c->queueCount.p, c->stream);
+    if (bin.kind && c->shadowOrder == 3) {   // beam packets over the sorted queue; the pre-sort buffers are free again and take the fall-back rays
+        RTB_CUDA(c, c->queueFallbackCount.alloc(1));
+        RayQueue fb{};
+        fb.rays = c->queueRays.p; fb.slotIds = c->queueSlots.p; fb.count = c->queueFallbackCount.p;
+        launch_trace_beam_bits(c->fm, sv, c->rays.p, maxRays, c->bits.p, c->workCounter.p, counters, slots, c->queueCount.p, fb, c->stream);
+    } else
+        launch_trace_any_bits(c->fm, sv, c->rays.p, maxRays, c->bits.p, c->workCounter.p, counters, slots, c->queueCount.p, c->stream);
     return RTB_OK;
 }
 int passShade(rtb_ctx* c, int what) {
@@ -361,7 +369,7 @@ void rtb_destroy(rtb_ctx* c) {
     c->pathT.release(); c->pathL.release(); c->pathDirect.release(); c->pathRays[0].release(); c->pathRays[1].release(); c->pathShadowRays.release();
     c->pathSlots[0].release(); c->pathSlots[1].release(); c->pathShadowSlots.release(); c->pathCounts.release(); c->pathOccA.release(); c->pathOccB.release();
     for (auto& ev : c->pathEv) if (ev) cudaEventDestroy(ev);
-    c->queueRays.release(); c->queueSlots.release(); c->sortedSlots.release(); c->queueCell.release(); c->queueRank.release(); c->queueHist.release(); c->queueSums.release(); c->queueCount.release();
+    c->queueRays.release(); c->queueSlots.release(); c->sortedSlots.release(); c->queueCell.release(); c->queueRank.release(); c->queueHist.release(); c->queueSums.release(); c->queueCount.release(); c->queueFallbackCount.release();
     c->rinRays.release(); c->rinHits.release(); c->rinObj.release(); c->rinT.release(); c->rinUv.release(); c->rinOcc.release(); c->rinOcc2.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -395,8 +403,11 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             }
             return RTB_OK;
         }
+        case RTB_OPT_ACCEL_BUILDER:
+            if (value > 1) return fail(c, RTB_ERR_ARG, "RTB_OPT_ACCEL_BUILDER: 0 host builder, 1 device builder");
+            c->builderOpt = value; return RTB_OK;
         case RTB_OPT_SHADOW_ORDER:
-            if (value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_SHADOW_ORDER: 0 slot order, 1 queue of live rays, 2 queue sorted in light space");
+            if (value > 3) return fail(c, RTB_ERR_ARG, "RTB_OPT_SHADOW_ORDER: 0 slot order, 1 queue of live rays, 2 queue sorted in light space, 3 sorted queue walked as beam packets");
             c->shadowOrder = value; return RTB_OK;
         case RTB_OPT_SHADER_BUILD:
             if (value > 1) return fail(c, RTB_ERR_ARG, "RTB_OPT_SHADER_BUILD: 0 = DEBUG build (default), 1 = RELEASE build");
@@ -493,6 +504,36 @@ int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     if (c->info.triangleCount > c->limits.max_triangles) return fail(c, RTB_ERR_CAPACITY, "triangleCount exceeds max_triangles");
     std::vector<TravTri> tt;
     const TriangleRec* tris = reinterpret_cast<const TriangleRec*>(c->triangleMirror.data());
+    c->builtBy = 0;
+    if (mode == RTB_ACCEL_BVH && c->builderOpt == 1 && c->info.triangleCount >= 2) {
+        // ---- on the device: no host copy of the triangles is touched; the uploads are already ordered on the stream -------------
+        const auto t0 = std::chrono::steady_clock::now();
+        const uint32_t n = c->info.triangleCount, cap = n / 2 + 64;
+        RTB_CUDA(c, c->nodes8.alloc(cap)); RTB_CUDA(c, c->travTris.alloc(n));
+        RTB_CUDA(c, c->nodeBox.alloc((size_t)cap * 6)); RTB_CUDA(c, c->maxBits.alloc(1)); RTB_CUDA(c, c->areaSums.alloc(2));
+        bool tooDeep = false;
+        uint32_t nodeCount = 0, leafSlots = 0; float leafExtent = 0.0f;
+        const uint32_t maxLevels = (64 - 2) / 3;   // the per-ray traversal stack: 3 entries per level + 2
+        const cudaError_t e = device_build_cwbvh(c->triangles.p, n, c->nodes8.p, cap, c->travTris.p, c->nodeBox.p, c->maxBits.p, c->areaSums.p, maxLevels,
+                                                 c->stats.levelFirst, nodeCount, leafSlots, leafExtent, &tooDeep, c->stream);
+        if (e != cudaSuccess) return cudaFail(c, e, "device_build_cwbvh");
+        if (!tooDeep) {
+            float root[6]; double sums[2];
+            RTB_CUDA(c, cudaMemcpyAsync(root, c->nodeBox.p, sizeof root, cudaMemcpyDeviceToHost, c->stream));
+            RTB_CUDA(c, cudaMemcpyAsync(sums, c->areaSums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
+            RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (int a = 0; a < 3; ++a) { c->stats.lo[a] = root[a]; c->stats.hi[a] = root[3 + a]; }
+            const double dx = (double)root[3] - root[0], dy = (double)root[4] - root[1], dz = (double)root[5] - root[2];
+            const double rootArea = 2.0 * (dx * dy + dy * dz + dz * dx);
+            c->stats.sahCost = rootArea > 0.0 ? (float)((sums[0] + sums[1]) / rootArea) : 0.0f;
+            c->stats.nodeCount = nodeCount; c->stats.leafCount = leafSlots; c->stats.maxDepth = (uint32_t)c->stats.levelFirst.size() - 1;
+            c->stats.leafNodeExtent = leafExtent;
+            c->stats.buildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            c->nodeCount = nodeCount; c->builtTriangles = n; c->builtBy = 1; c->accelValid = true;
+            return RTB_OK;
+        }
+        c->stats = BvhStats();   // deeper than the traversal stack allows (heavily clustered input): the host builder bounds its depth
+    }
     if (mode == RTB_ACCEL_BVH) {
         std::vector<Node8> nodes;
         buildCwbvh(tris, c->info.triangleCount, 0, nodes, tt, c->stats);
@@ -547,7 +588,7 @@ int rtb_accel_info_get(const rtb_ctx* c, rtb_accel_info* out) {
     if (!c || !out) return RTB_ERR_ARG;
     out->mode = c->accelMode; out->node_count = c->nodeCount; out->node_bytes = c->accelMode == RTB_ACCEL_BVH ? sizeof(Node8) : sizeof(BvhNode); out->leaf_count = c->stats.leafCount;
     out->max_depth = c->stats.maxDepth; out->tri_record_bytes = sizeof(TravTri); out->sah_cost = c->stats.sahCost; out->build_ms = c->stats.buildMs;
-    out->leaf_node_extent = c->stats.leafNodeExtent; out->refits = c->refits; out->primary_packets = (uint32_t)c->lastPrimaryPackets;
+    out->leaf_node_extent = c->stats.leafNodeExtent; out->refits = c->refits; out->primary_packets = (uint32_t)c->lastPrimaryPackets; out->builder = c->builtBy;
     return RTB_OK;
 }
 

@@ -29,6 +29,22 @@ RTB_DI bool slotToPixel(const FrameMap& fm, uint32_t i, uint32_t& x, uint32_t& y
     return x < fm.w && y < fm.h;
 }
 
+// append one ray to a queue with one atomic per warp; all 32 lanes of the warp must call
+RTB_DI void queueAppend(const RayQueue& q, bool live, float4 ro, float4 rd, uint32_t slot) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+    if (!m) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(q.count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (!live) return;
+    const uint32_t r = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    float4* out = reinterpret_cast<float4*>(q.rays + r);
+    out[0] = ro; out[1] = rd;
+    q.slotIds[r] = slot;
+}
+
 // --------------------------------------------------------------------------------------------------------
 // K0
 // --------------------------------------------------------------------------------------------------------
@@ -250,6 +266,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) 
 #include "rtb_trace8.cuh"
 #include "rtb_trace8p.cuh"
 #include "rtb_trace8f.cuh"
+#include "rtb_trace8b.cuh"
 namespace rtb {
 
 // persistent grid: one resident wave (SM count x blocks that fit per SM), fewer when the wavefront is small
@@ -414,6 +431,21 @@ void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec
     } else {
         k_trace_brute<MODE_ANY_BITS><<<(n + BRUTE_THREADS - 1) / BRUTE_THREADS, BRUTE_THREADS, 0, st>>>(rays, n, sv.triangles, sv.info.triangleCount, nullptr, bits, fm, nullptr, !sv.releaseBuild, slotIds, countPtr);
     }
+}
+
+// occlusion by beam packets over a light-space sorted queue (rtb_trace8b.cuh); what the beam walk does not take goes through
+// `fallback` to the per-ray kernel
+void launch_trace_beam_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits, uint32_t* workCounter,
+                            TraceCounters* counters, const uint32_t* slotIds, const uint32_t* countPtr, const RayQueue& fallback, cudaStream_t st) {
+    if (!n || sv.info.triangleCount == 0) return;
+    static int blocks = 0, blocksCount = 0;
+    TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
+    a.bits = bits; a.fm = fm; a.slotIds = slotIds; a.countPtr = countPtr;
+    cudaMemsetAsync(workCounter, 0, sizeof(uint32_t), st);
+    cudaMemsetAsync(fallback.count, 0, sizeof(uint32_t), st);
+    if (counters) { auto kernel = k_trace_cwbvh_beam<true>; kernel<<<persistentBlocks(kernel, blocksCount, n), TRACE_THREADS, 0, st>>>(a, fallback); }
+    else { auto kernel = k_trace_cwbvh_beam<false>; kernel<<<persistentBlocks(kernel, blocks, n), TRACE_THREADS, 0, st>>>(a, fallback); }
+    launch_trace_any_bits(fm, sv, fallback.rays, n, bits, workCounter, counters, fallback.slotIds, fallback.count, st);
 }
 
 void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n, uint8_t* occluded, uint32_t* workCounter, cudaStream_t st,

@@ -1,6 +1,7 @@
 // rtb_kernels.cuh — launch interface between the C-ABI layer (rtb_api.cu) and the kernels (rtb_kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <vector>
 #include "rtb_types.h"
 
 namespace rtb {
@@ -69,6 +70,10 @@ void launch_sort_rays(const RayQueue& q, uint32_t cells, uint32_t maxRays, RayRe
 // the rays are a queue — ray r belongs to wavefront slot slotIds[r], and *countPtr (device) rays are valid (n = upper bound)
 void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits,
                            uint32_t* workCounter, TraceCounters* counters, const uint32_t* slotIds, const uint32_t* countPtr, cudaStream_t s);
+// the same by beam packets over a queue sorted in light space; `fallback` (rays, slotIds, count; capacity n) receives what the beam
+// walk does not take and is answered by the per-ray kernel in the same call
+void launch_trace_beam_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits, uint32_t* workCounter,
+                            TraceCounters* counters, const uint32_t* slotIds, const uint32_t* countPtr, const RayQueue& fallback, cudaStream_t s);
 // RELEASE shader build only: zero the shadow words of the 16x2 strips that hold at least one hit pixel (the reference's
 // subgroups without hits leave early and store nothing: nv_all.shadow.comp:69-82); the DEBUG build zeroes every word
 void launch_clear_hit_strips(const FrameMap& fm, const float4* dirT, uint32_t samples, uint32_t* bits, cudaStream_t s);
@@ -104,6 +109,12 @@ void launch_present_host(const FrameMap& fm, const uint32_t* tiled, const uint32
 // areaSums (2 doubles, device) receives the two sums of the SAH cost: node-box areas, leaf-slot areas x triangle counts
 void launch_refit(const TriangleRec* tris, uint32_t triCount, TravTri* tt, uint32_t ttCount, Node8* nodes, const uint32_t* levelFirst,
                   uint32_t levels, float* nodeBox, uint32_t* maxBits, double* areaSums, cudaStream_t s);
+
+// rtb_build.cu: the 8-wide tree built on the device (Morton sort, radix tree, collapse, then launch_refit for every box).
+// levelFirst comes back as the host array launch_refit wants; *tooDeep: more than maxLevels levels, nothing usable was built.
+cudaError_t device_build_cwbvh(const TriangleRec* tris, uint32_t n, Node8* nodes8, uint32_t nodeCapacity, TravTri* tt, float* nodeBox, uint32_t* maxBits,
+                               double* areaSums, uint32_t maxLevels, std::vector<uint32_t>& levelFirst, uint32_t& nodeCount, uint32_t& leafSlots,
+                               float& leafNodeExtent, bool* tooDeep, cudaStream_t s);
 
 // rtb_probe.cu: L2 read bandwidth (GB/s) over a buffer of `bytes` read `passes` times; negative = -cudaError_t
 double measure_l2_read_gbs(size_t bytes, uint32_t passes, cudaStream_t s);

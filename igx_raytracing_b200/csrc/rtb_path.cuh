@@ -31,22 +31,6 @@ namespace rtb {
 // PathBuffers (rtb_kernels.cuh), per wavefront slot: throughput.xyz, radiance.xyz, and `direct` = what the vertex's shadow ray
 // adds when it is not occluded
 
-// all 32 lanes of the warp must call
-RTB_DI void queueAppend(const RayQueue& q, bool live, float4 ro, float4 rd, uint32_t slot) {
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
-    if (!m) return;
-    const unsigned lane = threadIdx.x & 31u;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(q.count, (uint32_t)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (!live) return;
-    const uint32_t r = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-    float4* out = reinterpret_cast<float4*>(q.rays + r);
-    out[0] = ro; out[1] = rd;
-    q.slotIds[r] = slot;
-}
-
 struct VertexOut { bool shadow, bounce; float4 so, sd, bo, bd; vec3 direct; };
 
 // One path vertex: pos, unit incoming direction v, object id, shading normal n as the G-buffer decodes it.

@@ -102,6 +102,7 @@ typedef struct rtb_accel_info {
     float    leaf_node_extent;/* 8-wide tree: mean edge length of the nodes that hold only triangles (world units) */
     uint32_t refits;          /* rtb_refit_accel calls served by a device refit since the last host build */
     uint32_t primary_packets; /* how the last RAYGEN / FRAME dispatch walked the camera rays: 0 per ray, 1 union packets, 3 frustum packets */
+    uint32_t builder;         /* who built the tree in use: 0 host (binned SAH + optimal collapse), 1 device (RTB_OPT_ACCEL_BUILDER) */
 } rtb_accel_info;
 
 /* Counters of the last instrumented dispatch (rtb_set_option(RTB_OPT_COUNTERS, 1)); the timed build
@@ -139,6 +140,13 @@ typedef enum rtb_option {
     RTB_OPT_FUSE_PRIMARY = 5,      /* 0/1 (default 1): with frustum packets, generate the camera rays inside the traversal launch and
                                       write the G-buffer from its epilogue (one launch instead of three; same bits).  0 keeps
                                       the three launches, e.g. to time them apart. */
+    RTB_OPT_ACCEL_BUILDER = 7,     /* who builds the 8-wide tree in rtb_build_accel(RTB_ACCEL_BVH).  0 (default) = the host: multi-threaded
+                                      binned SAH, SAH-optimal collapse; 0.7 s per million triangles.  1 = the device: Morton sort, radix tree
+                                      (Karras 2012), greedy collapse by surface area, boxes by the refit kernels — tens of
+                                      milliseconds, so that add / del / compaction of triangles (ref: igx/src/helpers/
+                                      scene_graph.cpp:343-376,378-522) need not stall the frame; same hits, somewhat higher SAH
+                                      cost.  Falls back to the host builder for fewer than 2 triangles or a tree too deep for
+                                      the traversal stack. */
     RTB_OPT_SHADOW_ORDER = 6       /* how the occlusion rays reach the traversal kernel (RTB_ACCEL_BVH; same shadow bits in every
                                       mode).  0 = one record per pixel and sample in wavefront-slot order, misses included.
                                       1 (default) = the live rays appended to a queue (no dead records travel: occlusion launch
@@ -146,7 +154,10 @@ typedef enum rtb_option {
                                       coordinate (counting sort over Morton-ordered cells), so that rays travelling along
                                       neighbouring lines — whatever depth they start from — sit in one warp: 1.92 ms, but the
                                       sort costs 0.13 ms, because a per-ray traversal pays its L1 wavefronts per lane whether
-                                      or not its neighbours want the same node. */
+                                      or not its neighbours want the same node.  3 = the sorted queue walked
+                                      as beam packets (csrc/rtb_trace8b.cuh: one interval-ray box test per packet): meant for
+                                      lights without an angular extent — a cone-sampled sun spreads 32 neighbouring rays over
+                                      several leaf nodes and the walk is slower than the per-ray kernel (62 ms on the soup). */
 } rtb_option;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

@@ -70,7 +70,7 @@ def test_headline_frame_against_the_oracle_on_4096_pixels(rtb, oracle, soup, hea
     got_shadow = shadow_bit(headline_frame["bits"], x, y, W, H)
     sb = (got_shadow != want["shadowed"]) & same
     assert int(sb.sum()) <= 1, f"{int(sb.sum())} shadow bits differ from the oracle"   # 1-ulp binary64 sin/cos budget (DESIGN.md numerics)
-    assert want["shadowed"][hit].mean() > 0.5
+    assert 0.1 < want["shadowed"][hit].mean() < 0.9   # both outcomes are well represented (29 % of the shadow rays are occluded)
     d = np.abs(headline_frame["rgba8"][y, x].view(np.uint8).reshape(-1, 4).astype(int) - want["rgba8"].view(np.uint8).reshape(-1, 4).astype(int)).max(-1)
     assert int((d[same & ~sb] > 1).sum()) == 0
 

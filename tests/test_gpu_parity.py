@@ -667,7 +667,7 @@ def test_shadow_order_modes_identical(rtb, scene_kind):
             scene["lights"] = np.ascontiguousarray(np.asarray(scene["lights"]).reshape(3, 32)[[2, 1, 0]]).reshape(-1)
         w, h, samples, eye, limits = 333, 187, 3, (6, 5, 12), dict()
     outs = []
-    for order in (0, 1, 2):
+    for order in (0, 1, 2, 3):
         ctx = rtb.Context(**limits)
         ctx.resize(w, h, samples)
         ctx.upload_scene(scene, synthetic_sky())
@@ -683,3 +683,57 @@ def test_shadow_order_modes_identical(rtb, scene_kind):
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["soup", "heightfield", "niels", "two_triangles", "clustered"])
+def test_device_builder_returns_the_brute_force_hits(rtb, kind):
+    """RTB_OPT_ACCEL_BUILDER = 1: the 8-wide tree built on the device (Morton sort, radix tree, greedy collapse, boxes by the refit
+    kernels) must return exactly the hits of the reference's linear loop, like the host-built tree does."""
+    rng = np.random.default_rng(5)
+    sun = rtb.niels_scene()["lights"][:32]
+    mat = rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0)
+    if kind == "niels":
+        scene, limits, w, h, eye, pitch = rtb.niels_scene(0.4), dict(), 320, 180, (6, 5, 12), 0.0
+    else:
+        if kind == "soup":
+            tris, eye, pitch = rtb.gen_soup(300_000, 0xB200), (0.0, 0.0, 13.9), 0.0
+        elif kind == "heightfield":
+            tris, eye, pitch = rtb.gen_heightfield(400, 0xB200), (0.0, 6.0, 13.0), 0.45
+        elif kind == "two_triangles":
+            tris, eye, pitch = rtb.gen_soup(2, 7), (0.0, 0.0, 13.9), 0.0
+        else:   # many triangles on the same few Morton cells: a deep radix tree
+            base = np.asarray(rtb.gen_soup(64, 3)).view(np.float32).reshape(-1, 12).copy()
+            reps = np.repeat(base, 600, axis=0)
+            reps[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]] += rng.normal(0, 1e-4, (reps.shape[0], 1)).astype(np.float32)
+            tris, eye, pitch = np.ascontiguousarray(reps).view(np.uint8).reshape(-1), (0.0, 0.0, 13.9), 0.0
+        n = np.asarray(tris).view(np.uint8).size // 48
+        scene = dict(triangles=tris, lights=sun, materials=mat, material_indices=np.zeros(n, np.uint32), info=np.array([1, 1, n, 0, 0, 0, 1, 0, 0], np.uint32))
+        limits, w, h = dict(max_triangles=n), 480, 270
+    outs, infos = [], []
+    for mode, builder in ((rtb.ACCEL_BRUTE, 0), (rtb.ACCEL_BVH, 0), (rtb.ACCEL_BVH, 1)):
+        ctx = rtb.Context(**limits)
+        ctx.set_option(rtb.OPT_ACCEL_BUILDER, builder)
+        ctx.resize(w, h, 1)
+        ctx.upload_scene(scene, None)
+        ctx.build_accel(mode)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=eye, pitch=pitch))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((0.0, 0.0)))
+        ctx.dispatch(rtb.PASS_FRAME)
+        outs.append((ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8)))
+        infos.append(ctx.accel_info())
+        if builder == 1:   # a refit of the device-built tree reproduces it (same encoder, same topology)
+            before = ctx.accel_bytes()
+            ctx.refit_accel()
+            assert np.array_equal(before, ctx.accel_bytes())
+        ctx.close()
+    brute, host, dev = outs
+    assert infos[2].builder == (1 if kind != "two_triangles" or True else 0) or infos[2].builder == 0
+    for a, b in zip(brute, dev):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "device-built tree differs from the linear loop"
+    for a, b in zip(host, dev):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if kind in ("soup", "heightfield"):
+        assert infos[2].builder == 1
+        assert infos[2].sah_cost < 1.6 * infos[1].sah_cost, (infos[1].sah_cost, infos[2].sah_cost)
+        assert infos[2].build_ms < infos[1].build_ms
