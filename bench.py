@@ -239,7 +239,7 @@ def main():
                     help="camera rays as 8x4-pixel packets (RTB_OPT_PRIMARY_PACKETS); auto = the library's patch-size rule")
     ap.add_argument("--shadow-order", default="queue", choices=["slots", "queue", "sorted", "beams"],
                     help="RTB_OPT_SHADOW_ORDER: occlusion rays in wavefront-slot order, as a queue of live rays, or that queue sorted in light space")
-    ap.add_argument("--builder", default="host", choices=["host", "device"], help="RTB_OPT_ACCEL_BUILDER: who builds the 8-wide tree")
+    ap.add_argument("--builder", default="host", choices=["host", "device", "device3"], help="RTB_OPT_ACCEL_BUILDER: who builds the 8-wide tree")
     ap.add_argument("--median-frames", type=int, default=100, help="frames timed one by one for the median (capped to ~10 s)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -291,7 +291,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     ctx.set_option(rtb.OPT_PRIMARY_PACKETS, {"off": 0, "union": 1, "auto": 2, "frustum": 3}[args.packets])
     ctx.set_option(rtb.OPT_SHADOW_ORDER, {"slots": 0, "queue": 1, "sorted": 2, "beams": 3}[args.shadow_order])
-    ctx.set_option(rtb.OPT_ACCEL_BUILDER, {"host": 0, "device": 1}[args.builder])
+    ctx.set_option(rtb.OPT_ACCEL_BUILDER, {"host": 0, "device": 1, "device3": 2}[args.builder])
     ctx.resize(w, h, samples)
     ctx.upload_scene(scene, None)
     ctx.build_accel(rtb.ACCEL_BVH)

@@ -404,7 +404,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             return RTB_OK;
         }
         case RTB_OPT_ACCEL_BUILDER:
-            if (value > 1) return fail(c, RTB_ERR_ARG, "RTB_OPT_ACCEL_BUILDER: 0 host builder, 1 device builder");
+            if (value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_ACCEL_BUILDER: 0 host builder, 1 device builder, 2 device builder with up to 3 triangles per leaf slot");
             c->builderOpt = value; return RTB_OK;
         case RTB_OPT_SHADOW_ORDER:
             if (value > 3) return fail(c, RTB_ERR_ARG, "RTB_OPT_SHADOW_ORDER: 0 slot order, 1 queue of live rays, 2 queue sorted in light space, 3 sorted queue walked as beam packets");
@@ -505,16 +505,16 @@ int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     std::vector<TravTri> tt;
     const TriangleRec* tris = reinterpret_cast<const TriangleRec*>(c->triangleMirror.data());
     c->builtBy = 0;
-    if (mode == RTB_ACCEL_BVH && c->builderOpt == 1 && c->info.triangleCount >= 2) {
+    if (mode == RTB_ACCEL_BVH && c->builderOpt >= 1 && c->info.triangleCount >= 2) {
         // ---- on the device: no host copy of the triangles is touched; the uploads are already ordered on the stream -------------
         const auto t0 = std::chrono::steady_clock::now();
-        const uint32_t n = c->info.triangleCount, cap = n / 2 + 64;
+        const uint32_t n = c->info.triangleCount, cap = n + 64;   // every node but the root holds at least two children
         RTB_CUDA(c, c->nodes8.alloc(cap)); RTB_CUDA(c, c->travTris.alloc(n));
         RTB_CUDA(c, c->nodeBox.alloc((size_t)cap * 6)); RTB_CUDA(c, c->maxBits.alloc(1)); RTB_CUDA(c, c->areaSums.alloc(2));
         bool tooDeep = false;
         uint32_t nodeCount = 0, leafSlots = 0; float leafExtent = 0.0f;
         const uint32_t maxLevels = (64 - 2) / 3;   // the per-ray traversal stack: 3 entries per level + 2
-        const cudaError_t e = device_build_cwbvh(c->triangles.p, n, c->nodes8.p, cap, c->travTris.p, c->nodeBox.p, c->maxBits.p, c->areaSums.p, maxLevels,
+        const cudaError_t e = device_build_cwbvh(c->triangles.p, n, c->nodes8.p, cap, c->travTris.p, c->nodeBox.p, c->maxBits.p, c->areaSums.p, maxLevels, c->builderOpt == 1 ? 1u : 3u,
                                                  c->stats.levelFirst, nodeCount, leafSlots, leafExtent, &tooDeep, c->stream);
         if (e != cudaSuccess) return cudaFail(c, e, "device_build_cwbvh");
         if (!tooDeep) {

@@ -9,7 +9,7 @@
 //   k_lbvh_fit          boxes bottom-up: the second thread to arrive at a node merges its children
 //   k_collapse_level    one launch per level of the 8-wide tree: a node starts from a binary node's two children and keeps opening
 //                       the child with the largest surface area until it has eight (or nothing is left to open); children whose
-//                       subtree holds at most three triangles become leaf slots, the others nodes of the next level (allocated
+//                       subtree holds at most leafMax (1 .. 3) triangles become leaf slots, the others nodes of the next level (allocated
 //                       consecutively, so the tree is breadth-first and a level is an index range); child slots are assigned by
 //                       octant like the host builder's
 //   launch_refit        (rtb_refit.cu) fills every box, grid and plane with the builder's own encoder and sums the SAH cost —
@@ -143,7 +143,7 @@ __device__ __forceinline__ float areaOf(const TriBox& b) {
 __global__ void __launch_bounds__(128) k_collapse_level(const unsigned long long* __restrict__ keys, const TriangleRec* __restrict__ tris, const LbvhNode* __restrict__ bn,
                                                         const TriBox* __restrict__ boxes, const int* __restrict__ rootOf, uint32_t first, uint32_t count,
                                                         uint32_t nextFirst, uint32_t capacity, Node8* __restrict__ nodes8, int* __restrict__ rootOfNext, TravTri* __restrict__ tt,
-                                                        uint32_t* __restrict__ counters) {
+                                                        uint32_t* __restrict__ counters, const uint32_t leafMax) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= count) return;
     const int root = rootOf[w];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) k_collapse_level(const unsigned long long
         const int k = childAt[s];
         if (k < 0) continue;
         const uint32_t cnt = trisOf(ref[k]);
-        if (cnt > 3u) { imask |= 1u << s; ++inner; }
+        if (cnt > leafMax) { imask |= 1u << s; ++inner; }
         else { presence |= ((1u << cnt) - 1u) << (3 * s); triTotal += cnt; ++leafSlots; }
     }
     const uint32_t childBase = inner ? nextFirst + atomicAdd(counters, inner) : 0u;
@@ -225,7 +225,7 @@ template <class T> cudaError_t devAlloc(T*& p, size_t n) { return cudaMalloc(rei
 // Builds the 8-wide tree over tris[0, n) into nodes8 (capacity nodeCapacity) and tt (capacity n).  Returns cudaSuccess and fills
 // the out parameters, or an error; *tooDeep is set when the tree has more levels than maxLevels (the caller falls back).
 cudaError_t device_build_cwbvh(const TriangleRec* tris, uint32_t n, Node8* nodes8, uint32_t nodeCapacity, TravTri* tt, float* nodeBox, uint32_t* maxBits,
-                               double* areaSums, uint32_t maxLevels, std::vector<uint32_t>& levelFirst, uint32_t& nodeCount, uint32_t& leafSlots,
+                               double* areaSums, uint32_t maxLevels, uint32_t leafMax, std::vector<uint32_t>& levelFirst, uint32_t& nodeCount, uint32_t& leafSlots,
                                float& leafNodeExtent, bool* tooDeep, cudaStream_t st) {
     *tooDeep = false;
     levelFirst.clear();
@@ -264,7 +264,7 @@ cudaError_t device_build_cwbvh(const TriangleRec* tris, uint32_t n, Node8* nodes
         const uint32_t nextFirst = first + count;
         if (nextFirst > nodeCapacity) { cleanup(); return cudaErrorMemoryAllocation; }
         RTB_B(cudaMemsetAsync(counters, 0, 4, st));
-        k_collapse_level<<<(count + 127u) / 128u, 128, 0, st>>>(keysSorted, tris, bn, boxes, cur, first, count, nextFirst, nodeCapacity, nodes8, nxt, tt, counters);
+        k_collapse_level<<<(count + 127u) / 128u, 128, 0, st>>>(keysSorted, tris, bn, boxes, cur, first, count, nextFirst, nodeCapacity, nodes8, nxt, tt, counters, leafMax);
         uint32_t next = 0;
         RTB_B(cudaMemcpyAsync(&next, counters, 4, cudaMemcpyDeviceToHost, st));
         RTB_B(cudaStreamSynchronize(st));

@@ -113,7 +113,7 @@ void launch_refit(const TriangleRec* tris, uint32_t triCount, TravTri* tt, uint3
 // rtb_build.cu: the 8-wide tree built on the device (Morton sort, radix tree, collapse, then launch_refit for every box).
 // levelFirst comes back as the host array launch_refit wants; *tooDeep: more than maxLevels levels, nothing usable was built.
 cudaError_t device_build_cwbvh(const TriangleRec* tris, uint32_t n, Node8* nodes8, uint32_t nodeCapacity, TravTri* tt, float* nodeBox, uint32_t* maxBits,
-                               double* areaSums, uint32_t maxLevels, std::vector<uint32_t>& levelFirst, uint32_t& nodeCount, uint32_t& leafSlots,
+                               double* areaSums, uint32_t maxLevels, uint32_t leafMax, std::vector<uint32_t>& levelFirst, uint32_t& nodeCount, uint32_t& leafSlots,
                                float& leafNodeExtent, bool* tooDeep, cudaStream_t s);
 
 // rtb_probe.cu: L2 read bandwidth (GB/s) over a buffer of `bytes` read `passes` times; negative = -cudaError_t

@@ -255,6 +255,7 @@ private:
     List<u32> materialByObject;
     bool geometryDirty = true;      // triangles changed since the last acceleration-structure build or refit
     bool topologyDirty = true;      // ... and their number or order changed too: a refit is not enough
+    bool builtOnce = false;
     String sceneName;
     List<u16> skyboxPixels; u32 skyW = 0, skyH = 0; bool skyboxDirty = false;
     int lastError = 0;
@@ -363,8 +364,16 @@ public:
         cl->add([this](rtb_ctx* c) {
             if (skyboxDirty) { skyboxDirty = false; const int rc = rtb_upload_skybox(c, skyW, skyH, skyboxPixels.empty() ? nullptr : skyboxPixels.data()); if (rc) return rc; }
             if (geometryDirty) {
-                const int rc = topologyDirty ? rtb_build_accel(c, accelMode) : rtb_refit_accel(c);
+                int rc;
+                if (topologyDirty) {
+                    // the first tree is built by the host builder (best SAH cost); a scene whose triangles come and go afterwards
+                    // (add / del / compaction, scene_graph.cpp:343-376,378-522) rebuilds on the device: milliseconds, not a stall
+                    rtb_set_option(c, RTB_OPT_ACCEL_BUILDER, (builtOnce && rebuildOnDevice) ? 1u : 0u);
+                    rc = rtb_build_accel(c, accelMode);
+                } else
+                    rc = rtb_refit_accel(c);
                 if (rc) return rc;   // stays dirty: the next frame tries again
+                builtOnce = true;
                 geometryDirty = topologyDirty = false;
             }
             return 0;
@@ -379,6 +388,7 @@ public:
     Device& getDevice() const { return device; }
     int error() const { return lastError; }
     rtb_accel_mode accelMode = RTB_ACCEL_BVH;
+    bool rebuildOnDevice = true;    // RTB_OPT_ACCEL_BUILDER = 1 for every build after the first
 
 private:
     void note(int rc) { if (rc && !lastError) lastError = rc; }
