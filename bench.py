@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--shadow-order", default="queue", choices=["slots", "queue", "sorted", "beams"],
                     help="RTB_OPT_SHADOW_ORDER: occlusion rays in wavefront-slot order, as a queue of live rays, or that queue sorted in light space")
     ap.add_argument("--builder", default="host", choices=["host", "device", "device3"], help="RTB_OPT_ACCEL_BUILDER: who builds the 8-wide tree")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2], help="RTB_OPT_FRAME_LANES: a frame as one lane or as two half-frame lanes on two streams")
     ap.add_argument("--median-frames", type=int, default=100, help="frames timed one by one for the median (capped to ~10 s)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -292,6 +293,7 @@ def main():
     ctx.set_option(rtb.OPT_PRIMARY_PACKETS, {"off": 0, "union": 1, "auto": 2, "frustum": 3}[args.packets])
     ctx.set_option(rtb.OPT_SHADOW_ORDER, {"slots": 0, "queue": 1, "sorted": 2, "beams": 3}[args.shadow_order])
     ctx.set_option(rtb.OPT_ACCEL_BUILDER, {"host": 0, "device": 1, "device3": 2}[args.builder])
+    ctx.set_option(rtb.OPT_FRAME_LANES, args.lanes)
     ctx.resize(w, h, samples)
     ctx.upload_scene(scene, None)
     ctx.build_accel(rtb.ACCEL_BVH)
@@ -523,11 +525,13 @@ def main():
     phases = np.zeros(8)
     t_primary = t_shadow = 0.0
     if not bounces:
+        ctx.set_option(rtb.OPT_FRAME_LANES, 1)   # one lane: the launches run one after the other and can be timed alone
         n_ph = min(args.steps, 10)
         for _ in range(n_ph):
             ctx.dispatch(rtb.PASS_FRAME)
             phases += np.array(ctx.last_frame_ms())
         phases /= n_ph
+        ctx.set_option(rtb.OPT_FRAME_LANES, args.lanes)
         t_primary, t_shadow = float(phases[2]) * 1e-3, float(phases[5]) * 1e-3
     else:
         for _ in range(3):
@@ -657,7 +661,8 @@ def main():
                            "sah_cost": info.sah_cost, "build_ms": info.build_ms, "leaf_node_extent": info.leaf_node_extent, "bytes": bvh_bytes,
                            "builder": {0: "host (binned SAH, optimal collapse)", 1: "device (Morton sort, radix tree, greedy collapse)"}.get(info.builder, "?")},
                    "primary_packets": {0: "per ray", 1: "union packets", 3: "frustum packets"}.get(info.primary_packets, str(info.primary_packets)), "packets_option": args.packets,
-                   "shadow_order": args.shadow_order,
+                   "shadow_order": args.shadow_order, "frame_lanes": args.lanes,
+                   "phase_note": "phase_ms_rank0 is measured with ONE lane (launches back to back); the timed frames run %d lane(s)" % args.lanes,
                    "phase_ms_rank0": {k: float(v) for k, v in zip(["init", "raygen", "trace_primary", "finish", "shadowgen", "trace_shadow", "shade", "total"], phases)}},
         "clocks": clocks,
         "checksum": checksum,

@@ -66,8 +66,17 @@ struct rtb_ctx {
     FrameMap fm{};
     uint32_t tileRank = 0, tileCount = 1;
     DevBuf<float4> dirT, uvN, accum; DevBuf<uint2> lighting; DevBuf<uint32_t> bits, rgba8, rgba8Tiled;
-    DevBuf<RayRec> rays; DevBuf<TriHit> hits;
-    DevBuf<uint32_t> workCounter;
+    // per-lane wavefront buffers.  Lane 0 serves the whole frame (per-pass dispatch, rays-in, path frames) or, when a frame runs as
+    // two half-frame lanes on two streams (RTB_OPT_FRAME_LANES), the even local blocks; lane 1 the odd ones.
+    struct LaneBufs {
+        DevBuf<RayRec> rays; DevBuf<TriHit> hits; DevBuf<uint32_t> workCounter;
+        DevBuf<RayRec> queueRays; DevBuf<uint32_t> queueSlots, sortedSlots, queueCell, queueRank, queueHist, queueSums, queueCount, queueFallbackCount;
+        void release() { rays.release(); hits.release(); workCounter.release(); queueRays.release(); queueSlots.release(); sortedSlots.release(); queueCell.release();
+                         queueRank.release(); queueHist.release(); queueSums.release(); queueCount.release(); queueFallbackCount.release(); }
+    } lane[2];
+    FrameMap laneFm[2]{};             // the two half-frame maps: lane h of rank r is virtual rank h * n + r of 2 n
+    cudaStream_t laneStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    uint32_t lanesOpt = 2;            // RTB_OPT_FRAME_LANES
     DevBuf<TraceCounters> counters;   // [0] primary, [1] shadow
     bool countersOn = false;
     uint32_t countersMode = 0;        // 1: per-ray algorithmic counts (per-lane kernel); 2: what the kernels in use fetch
@@ -78,7 +87,6 @@ struct rtb_ctx {
     uint32_t builtBy = 0;             // builder of the tree in use
     uint32_t shadowOrder = 1;         // RTB_OPT_SHADOW_ORDER: 0 slot order, 1 queue of live rays (default), 2 queue sorted in light space
     LightRec light0{};                // host mirror of lights[0] (the one light the shadow pass samples): picks the sort key
-    DevBuf<RayRec> queueRays; DevBuf<uint32_t> queueSlots, sortedSlots, queueCell, queueRank, queueHist, queueSums, queueCount, queueFallbackCount;
     // wavefront path tracing (rtb_path_frame)
     DevBuf<float4> pathT, pathL, pathDirect; DevBuf<RayRec> pathRays[2], pathShadowRays; DevBuf<uint32_t> pathSlots[2], pathShadowSlots, pathCounts;
     DevBuf<uint8_t> pathOccA, pathOccB;
@@ -117,14 +125,19 @@ SceneView sceneView(const rtb_ctx* c) {
     return v;
 }
 
-void makeFrameMap(rtb_ctx* c) {
-    FrameMap& fm = c->fm;
-    fm.w = c->width; fm.h = c->height;
-    fm.blocksX = (c->width + 31) / 32; fm.blocksY = (c->height + 31) / 32;
-    fm.rank = c->tileRank; fm.nranks = c->tileCount;
+void fillFrameMap(FrameMap& fm, uint32_t w, uint32_t h, uint32_t rank, uint32_t nranks, uint32_t tiledMul, uint32_t tiledAdd) {
+    fm.w = w; fm.h = h;
+    fm.blocksX = (w + 31) / 32; fm.blocksY = (h + 31) / 32;
+    fm.rank = rank; fm.nranks = nranks;
     const uint32_t total = fm.blocksX * fm.blocksY;
     fm.localBlocks = total > fm.rank ? (total - fm.rank + fm.nranks - 1) / fm.nranks : 0;
     fm.localSlots = fm.localBlocks * 1024u;
+    fm.tiledMul = tiledMul; fm.tiledAdd = tiledAdd;
+}
+void makeFrameMap(rtb_ctx* c) {
+    fillFrameMap(c->fm, c->width, c->height, c->tileRank, c->tileCount, 1, 0);
+    // lane h takes the rank's local blocks 2 k + h: global blocks g = (2 k + h) n + r = k (2 n) + (h n + r)
+    for (uint32_t h = 0; h < 2; ++h) fillFrameMap(c->laneFm[h], c->width, c->height, h * c->tileCount + c->tileRank, 2 * c->tileCount, 2, h);
 }
 
 uint32_t shadowWords(uint32_t w, uint32_t h, uint32_t samples) { return ((w + 15) / 16) * ((h + 1) / 2) * samples; }
@@ -136,8 +149,11 @@ int allocFrame(rtb_ctx* c) {
     RTB_CUDA(c, c->lighting.alloc(px)); RTB_CUDA(c, c->rgba8.alloc(px));
     RTB_CUDA(c, c->bits.alloc(shadowWords(c->width, c->height, c->samples)));
     RTB_CUDA(c, c->rgba8Tiled.alloc((size_t)((c->fm.blocksX * c->fm.blocksY + c->fm.nranks - 1) / c->fm.nranks) * 1024u));
-    RTB_CUDA(c, c->rays.alloc((size_t)c->fm.localSlots * (c->samples ? c->samples : 1)));
-    RTB_CUDA(c, c->hits.alloc(c->fm.localSlots));
+    RTB_CUDA(c, c->lane[0].rays.alloc((size_t)c->fm.localSlots * (c->samples ? c->samples : 1)));
+    RTB_CUDA(c, c->lane[0].hits.alloc(c->fm.localSlots));
+    RTB_CUDA(c, c->lane[1].rays.alloc((size_t)c->laneFm[1].localSlots * (c->samples ? c->samples : 1)));
+    RTB_CUDA(c, c->lane[1].hits.alloc(c->laneFm[1].localSlots));
+    RTB_CUDA(c, c->lane[1].workCounter.alloc(1));
     // pixels owned by other ranks are never written: keep them defined
     RTB_CUDA(c, cudaMemsetAsync(c->dirT.p, 0, c->dirT.bytes(), c->stream));
     RTB_CUDA(c, cudaMemsetAsync(c->uvN.p, 0, c->uvN.bytes(), c->stream));
@@ -206,26 +222,35 @@ int primaryPackets(const rtb_ctx* c) {
     return patch < PACKET_RATIO * c->stats.leafNodeExtent ? PACKETS_FRUSTUM : PACKETS_OFF;
 }
 
-// `mark` (frame dispatch only) records an event after each phase so the traversal launches can be timed alone
-int passRaygen(rtb_ctx* c, bool mark) {
-    { const int rc = waitCopy(c, {RTB_TGT_DIR_T, RTB_TGT_UV_NORMAL}); if (rc) return rc; }
+// `mark` (single-lane frame dispatch only) records an event after each phase so the traversal launches can be timed alone.
+// lane < 0: the whole frame on the context's stream; lane 0 / 1: that half-frame lane (lane 1 on its own stream).
+struct LaneRef { const FrameMap& fm; rtb_ctx::LaneBufs& b; cudaStream_t st; };
+LaneRef laneOf(rtb_ctx* c, int lane) {
+    if (lane < 0) return LaneRef{c->fm, c->lane[0], c->stream};
+    return LaneRef{c->laneFm[lane], c->lane[lane], lane == 1 ? c->laneStream : c->stream};
+}
+
+int passRaygen(rtb_ctx* c, bool mark, int lane = -1) {
+    if (lane < 0) { const int rc = waitCopy(c, {RTB_TGT_DIR_T, RTB_TGT_UV_NORMAL}); if (rc) return rc; }
+    const LaneRef L = laneOf(c, lane);
     const SceneView sv = sceneView(c);
-    c->lastPrimaryPackets = primaryPackets(c);
+    if (lane <= 0) c->lastPrimaryPackets = primaryPackets(c);
     if (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt) {
         // one launch: rays generated in registers, traced, G-buffer written (the phase events collapse onto the trace phase)
-        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-        launch_primary_fused(c->fm, sv, &c->camera, c->seed.p, c->dirT.p, c->uvN.p, c->workCounter.p, c->stream);
-        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], L.st));
+        launch_primary_fused(L.fm, sv, &c->camera, c->seed.p, c->dirT.p, c->uvN.p, L.b.workCounter.p, L.st);
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], L.st));
         return RTB_OK;
     }
-    launch_raygen(c->fm, &c->camera, c->seed.p, c->rays.p, c->stream);
-    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    launch_trace_closest(sv, c->rays.p, c->fm.localSlots, c->hits.p, c->workCounter.p, c->countersOn ? c->counters.p : nullptr, c->lastPrimaryPackets, c->stream);
-    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
-    launch_finish_primary(c->fm, sv, c->rays.p, c->hits.p, c->dirT.p, c->uvN.p, c->stream);
-    if (c->countersOn) launch_count_hits(c->fm, c->dirT.p, c->counters.p, c->stream);
+    launch_raygen(L.fm, &c->camera, c->seed.p, L.b.rays.p, L.st);
+    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], L.st));
+    launch_trace_closest(sv, L.b.rays.p, L.fm.localSlots, L.b.hits.p, L.b.workCounter.p, c->countersOn ? c->counters.p : nullptr, c->lastPrimaryPackets, L.st);
+    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], L.st));
+    launch_finish_primary(L.fm, sv, L.b.rays.p, L.b.hits.p, c->dirT.p, c->uvN.p, L.st);
+    if (c->countersOn) launch_count_hits(L.fm, c->dirT.p, c->counters.p, L.st);
     return RTB_OK;
 }
+
 // Light-space binning of the occlusion rays (rtb_sort.cu): a sun gets two axes perpendicular to its direction, a point light
 // the octahedral map of the direction from the light; the cell grid covers the scene bounds seen from the light.
 RayBin shadowBin(const rtb_ctx* c, uint32_t maxRays) {
@@ -264,52 +289,96 @@ RayBin shadowBin(const rtb_ctx* c, uint32_t maxRays) {
     return b;
 }
 
-int passShadow(rtb_ctx* c, bool mark) {
+// the shadow words start from zero (DEBUG build) or keep what they held where no subgroup has a hit (RELEASE): once per frame,
+// before any lane's rays are traced
+int clearShadowBits(rtb_ctx* c) {
     { const int rc = waitCopy(c, {RTB_TGT_SHADOW_BITS}); if (rc) return rc; }
-    const SceneView sv = sceneView(c);
     if (c->releaseBuild) launch_clear_hit_strips(c->fm, c->dirT.p, c->samples, c->bits.p, c->stream);
     else RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, c->samples) * 4, c->stream));
-    const uint32_t maxRays = c->fm.localSlots * c->samples;
+    return RTB_OK;
+}
+
+int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
+    // (the RELEASE build's clear reads the G-buffer, so with lanes it runs after both lanes' nearest-hit launches: see the frame dispatch)
+    if (lane < 0) { const int rc = clearShadowBits(c); if (rc) return rc; }
+    const LaneRef L = laneOf(c, lane);
+    rtb_ctx::LaneBufs& B = L.b;
+    const SceneView sv = sceneView(c);
+    const uint32_t maxRays = L.fm.localSlots * c->samples;
     TraceCounters* counters = c->countersOn ? c->counters.p + 1 : nullptr;
     if (!c->shadowOrder || sv.useBvh != ACCEL_KIND_CWBVH || !sv.info.triangleCount || !maxRays) {
         // slot order: one record per (sample, slot), what the first-generation kernels and the reference loop consume
-        launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, nullptr, nullptr, c->stream);
-        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
-        launch_trace_any_bits(c->fm, sv, c->rays.p, maxRays, c->bits.p, c->workCounter.p, counters, nullptr, nullptr, c->stream);
+        launch_shadowgen(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, B.rays.p, c->bits.p, nullptr, nullptr, L.st);
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], L.st));
+        launch_trace_any_bits(L.fm, sv, B.rays.p, maxRays, c->bits.p, B.workCounter.p, counters, nullptr, nullptr, L.st);
         return RTB_OK;
     }
     // queue of live rays, optionally sorted in light space
     RayBin bin = c->shadowOrder >= 2 && !(c->countersOn && c->countersMode == 1) ? shadowBin(c, maxRays) : RayBin{};
     const uint32_t cells = bin.kind ? 1u << (2 * bin.bits) : 0u;
-    RTB_CUDA(c, c->queueCount.alloc(1)); RTB_CUDA(c, c->queueSlots.alloc(maxRays));
-    RTB_CUDA(c, cudaMemsetAsync(c->queueCount.p, 0, 4, c->stream));
+    RTB_CUDA(c, B.queueCount.alloc(1)); RTB_CUDA(c, B.queueSlots.alloc(maxRays));
+    RTB_CUDA(c, cudaMemsetAsync(B.queueCount.p, 0, 4, L.st));
     RayQueue q{};
-    q.count = c->queueCount.p; q.slotIds = c->queueSlots.p;
+    q.count = B.queueCount.p; q.slotIds = B.queueSlots.p;
     if (bin.kind) {
-        RTB_CUDA(c, c->queueRays.alloc(maxRays)); RTB_CUDA(c, c->sortedSlots.alloc(maxRays)); RTB_CUDA(c, c->queueCell.alloc(maxRays)); RTB_CUDA(c, c->queueRank.alloc(maxRays));
-        RTB_CUDA(c, c->queueHist.alloc(cells)); RTB_CUDA(c, c->queueSums.alloc(1024));
-        RTB_CUDA(c, cudaMemsetAsync(c->queueHist.p, 0, (size_t)cells * 4, c->stream));
-        q.rays = c->queueRays.p; q.cell = c->queueCell.p; q.rank = c->queueRank.p; q.hist = c->queueHist.p; q.blockSums = c->queueSums.p;
+        RTB_CUDA(c, B.queueRays.alloc(maxRays)); RTB_CUDA(c, B.sortedSlots.alloc(maxRays)); RTB_CUDA(c, B.queueCell.alloc(maxRays)); RTB_CUDA(c, B.queueRank.alloc(maxRays));
+        RTB_CUDA(c, B.queueHist.alloc(cells)); RTB_CUDA(c, B.queueSums.alloc(1024));
+        RTB_CUDA(c, cudaMemsetAsync(B.queueHist.p, 0, (size_t)cells * 4, L.st));
+        q.rays = B.queueRays.p; q.cell = B.queueCell.p; q.rank = B.queueRank.p; q.hist = B.queueHist.p; q.blockSums = B.queueSums.p;
     } else
-        q.rays = c->rays.p;
-    launch_shadowgen(c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->rays.p, c->bits.p, &q, &bin, c->stream);
-    const uint32_t* slots = c->queueSlots.p;
-    if (bin.kind) { launch_sort_rays(q, cells, maxRays, c->rays.p, c->sortedSlots.p, c->stream); slots = c->sortedSlots.p; }
-    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        q.rays = B.rays.p;
+    launch_shadowgen(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, B.rays.p, c->bits.p, &q, &bin, L.st);
+    const uint32_t* slots = B.queueSlots.p;
+    if (bin.kind) { launch_sort_rays(q, cells, maxRays, B.rays.p, B.sortedSlots.p, L.st); slots = B.sortedSlots.p; }
+    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], L.st));
     if (bin.kind && c->shadowOrder == 3) {   // beam packets over the sorted queue; the pre-sort buffers are free again and take the fall-back rays
-        RTB_CUDA(c, c->queueFallbackCount.alloc(1));
+        RTB_CUDA(c, B.queueFallbackCount.alloc(1));
         RayQueue fb{};
-        fb.rays = c->queueRays.p; fb.slotIds = c->queueSlots.p; fb.count = c->queueFallbackCount.p;
-        launch_trace_beam_bits(c->fm, sv, c->rays.p, maxRays, c->bits.p, c->workCounter.p, counters, slots, c->queueCount.p, fb, c->stream);
+        fb.rays = B.queueRays.p; fb.slotIds = B.queueSlots.p; fb.count = B.queueFallbackCount.p;
+        launch_trace_beam_bits(L.fm, sv, B.rays.p, maxRays, c->bits.p, B.workCounter.p, counters, slots, B.queueCount.p, fb, L.st);
     } else
-        launch_trace_any_bits(c->fm, sv, c->rays.p, maxRays, c->bits.p, c->workCounter.p, counters, slots, c->queueCount.p, c->stream);
+        launch_trace_any_bits(L.fm, sv, B.rays.p, maxRays, c->bits.p, B.workCounter.p, counters, slots, B.queueCount.p, L.st);
     return RTB_OK;
 }
-int passShade(rtb_ctx* c, int what) {
-    { const int rc = waitCopy(c, {RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
+int passShade(rtb_ctx* c, int what, int lane = -1) {
+    if (lane < 0) { const int rc = waitCopy(c, {RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
+    const LaneRef L = laneOf(c, lane);
     const SceneView sv = sceneView(c);
-    launch_shade(what, c->fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->uvN.p, c->bits.p, c->lighting.p, c->accum.p,
-                 c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, c->stream);
+    launch_shade(what, L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->uvN.p, c->bits.p, c->lighting.p, c->accum.p,
+                 c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, L.st);
+    return RTB_OK;
+}
+
+// a frame as two half-frame lanes on two streams: while a persistent launch of one lane drains (its last rays are the longest),
+// the other lane's launch takes the freed SM slots.  Same kernels, same pixels; only the launches' slot ranges differ.
+bool useLanes(const rtb_ctx* c) {
+    return c->lanesOpt == 2 && !c->countersOn && c->laneFm[1].localSlots >= 64u * 1024u;   // >= 64 blocks per lane: smaller frames are launch-bound
+}
+int frameInLanes(rtb_ctx* c) {
+    if (!c->laneStream) {
+        RTB_CUDA(c, cudaStreamCreateWithFlags(&c->laneStream, cudaStreamNonBlocking));
+        RTB_CUDA(c, cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+        RTB_CUDA(c, cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+    }
+    { const int rc = waitCopy(c, {RTB_TGT_DIR_T, RTB_TGT_UV_NORMAL, RTB_TGT_SHADOW_BITS, RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
+    int rc;
+    if (!c->releaseBuild) { if ((rc = clearShadowBits(c))) return rc; }
+    RTB_CUDA(c, cudaEventRecord(c->evFork, c->stream));
+    RTB_CUDA(c, cudaStreamWaitEvent(c->laneStream, c->evFork, 0));
+    for (int lane = 0; lane < 2; ++lane) if ((rc = passRaygen(c, false, lane))) return rc;
+    if (c->releaseBuild) {   // the RELEASE clear reads the whole G-buffer: join, clear, fork again
+        RTB_CUDA(c, cudaEventRecord(c->evJoin, c->laneStream));
+        RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evJoin, 0));
+        if ((rc = clearShadowBits(c))) return rc;
+        RTB_CUDA(c, cudaEventRecord(c->evFork, c->stream));
+        RTB_CUDA(c, cudaStreamWaitEvent(c->laneStream, c->evFork, 0));
+    }
+    for (int lane = 0; lane < 2; ++lane) {
+        if ((rc = passShadow(c, false, lane))) return rc;
+        if ((rc = passShade(c, SHADE_BOTH, lane))) return rc;
+    }
+    RTB_CUDA(c, cudaEventRecord(c->evJoin, c->laneStream));
+    RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evJoin, 0));
     return RTB_OK;
 }
 
@@ -343,7 +412,7 @@ int rtb_create(rtb_ctx** out, int cudaDevice, const rtb_limits* limits) {
     const size_t objects = (size_t)limits->max_triangles + limits->max_spheres + limits->max_cubes + limits->max_planes;
     if ((e = c->materialIndices.alloc(objects)) != cudaSuccess) return bail(e, "alloc materialIndices");
     if ((e = c->seed.alloc(1)) != cudaSuccess) return bail(e, "alloc seed");
-    if ((e = c->workCounter.alloc(1)) != cudaSuccess) return bail(e, "alloc workCounter");
+    if ((e = c->lane[0].workCounter.alloc(1)) != cudaSuccess) return bail(e, "alloc workCounter");
     if ((e = c->counters.alloc(2)) != cudaSuccess) return bail(e, "alloc counters");
     if ((e = cudaMemsetAsync(c->lights.p, 0, c->lights.bytes(), c->stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(c->materials.p, 0, c->materials.bytes(), c->stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
@@ -365,11 +434,13 @@ void rtb_destroy(rtb_ctx* c) {
     c->triangles.release(); c->spheres.release(); c->cubes.release(); c->planes.release(); c->lights.release(); c->materials.release();
     c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release(); c->nodeBox.release(); c->maxBits.release(); c->areaSums.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
-    c->rays.release(); c->hits.release(); c->workCounter.release(); c->counters.release();
+    c->lane[0].release(); c->lane[1].release(); c->counters.release();
+    if (c->laneStream) cudaStreamDestroy(c->laneStream);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
     c->pathT.release(); c->pathL.release(); c->pathDirect.release(); c->pathRays[0].release(); c->pathRays[1].release(); c->pathShadowRays.release();
     c->pathSlots[0].release(); c->pathSlots[1].release(); c->pathShadowSlots.release(); c->pathCounts.release(); c->pathOccA.release(); c->pathOccB.release();
     for (auto& ev : c->pathEv) if (ev) cudaEventDestroy(ev);
-    c->queueRays.release(); c->queueSlots.release(); c->sortedSlots.release(); c->queueCell.release(); c->queueRank.release(); c->queueHist.release(); c->queueSums.release(); c->queueCount.release(); c->queueFallbackCount.release();
     c->rinRays.release(); c->rinHits.release(); c->rinObj.release(); c->rinT.release(); c->rinUv.release(); c->rinOcc.release(); c->rinOcc2.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -403,6 +474,9 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             }
             return RTB_OK;
         }
+        case RTB_OPT_FRAME_LANES:
+            if (value < 1 || value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_FRAME_LANES: 1 or 2");
+            c->lanesOpt = value; return RTB_OK;
         case RTB_OPT_ACCEL_BUILDER:
             if (value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_ACCEL_BUILDER: 0 host builder, 1 device builder, 2 device builder with up to 3 triangles per leaf slot");
             c->builderOpt = value; return RTB_OK;
@@ -609,6 +683,13 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
             if ((rc = waitCopy(c, {RTB_TGT_SEED}))) return rc;
             launch_init(c->seed.p, c->stream);
             RTB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+            if (useLanes(c)) {
+                if ((rc = frameInLanes(c))) return rc;
+                for (int k = 2; k < 7; ++k) RTB_CUDA(c, cudaEventRecord(c->ev[k], c->stream));   // phases overlap: only the total means something
+                RTB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
+                c->frameTimed = true;
+                break;
+            }
             if ((rc = passRaygen(c, true))) return rc;
             RTB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
             if ((rc = passShadow(c, true))) return rc;
@@ -734,7 +815,7 @@ int rtb_probe_l2_read_gbs(rtb_ctx* c, size_t bytes, double* outGbs) {
 int rtb_sync(rtb_ctx* c) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
-    RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RTB_CUDA(c, cudaStreamSynchronize(c->stream));   // (a frame in lanes has joined the lane stream back into this one)
     if (c->copyStream) RTB_CUDA(c, cudaStreamSynchronize(c->copyStream));
     return RTB_OK;
 }
@@ -799,7 +880,7 @@ int rtb_path_frame(rtb_ctx* c, uint32_t bounces) {
         const RayQueue sq = shadowQ(d);
         RTB_CUDA(c, cudaEventRecord(ev[4 * d + 2], c->stream));
         launch_occlusion_others(sv, sq.rays, slots, c->pathOccA.p, c->stream, sq.count);
-        launch_trace_any_bytes(sv, sq.rays, slots, c->pathOccB.p, c->workCounter.p, c->stream, cc ? cc + 1 : nullptr, sq.count);
+        launch_trace_any_bytes(sv, sq.rays, slots, c->pathOccB.p, c->lane[0].workCounter.p, c->stream, cc ? cc + 1 : nullptr, sq.count);
         RTB_CUDA(c, cudaEventRecord(ev[4 * d + 3], c->stream));
         launch_path_shadow_resolve(sq, slots, c->pathOccA.p, c->pathOccB.p, pb, c->stream);
         launches += 3;
@@ -810,9 +891,9 @@ int rtb_path_frame(rtb_ctx* c, uint32_t bounces) {
     for (uint32_t d = 1; d < depths; ++d) {
         const RayQueue in = closestQ(d);
         RTB_CUDA(c, cudaEventRecord(ev[4 * d], c->stream));
-        launch_trace_closest(sv, in.rays, slots, c->hits.p, c->workCounter.p, cc, PACKETS_OFF, c->stream, in.count);
+        launch_trace_closest(sv, in.rays, slots, c->lane[0].hits.p, c->lane[0].workCounter.p, cc, PACKETS_OFF, c->stream, in.count);
         RTB_CUDA(c, cudaEventRecord(ev[4 * d + 1], c->stream));
-        launch_path_vertex(c->fm, sv, &c->camera, c->seed.p, d, bounces, in, c->hits.p, pb, shadowQ(d), closestQ(d + 1), c->stream);
+        launch_path_vertex(c->fm, sv, &c->camera, c->seed.p, d, bounces, in, c->lane[0].hits.p, pb, shadowQ(d), closestQ(d + 1), c->stream);
         launches += 2;
         const int rc = shadows(d); if (rc) return rc;
     }
@@ -880,7 +961,7 @@ int rtb_trace_rays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* pr
     if (rc) return rc;
     RTB_CUDA(c, c->rinHits.alloc((size_t)n)); RTB_CUDA(c, c->rinObj.alloc((size_t)n)); RTB_CUDA(c, c->rinT.alloc((size_t)n)); RTB_CUDA(c, c->rinUv.alloc((size_t)n));
     const SceneView sv = sceneView(c);
-    launch_trace_closest(sv, c->rinRays.p, (uint32_t)n, c->rinHits.p, c->workCounter.p, nullptr, c->packetsOpt == 2 ? PACKETS_OFF : (int)c->packetsOpt, c->stream);
+    launch_trace_closest(sv, c->rinRays.p, (uint32_t)n, c->rinHits.p, c->lane[0].workCounter.p, nullptr, c->packetsOpt == 2 ? PACKETS_OFF : (int)c->packetsOpt, c->stream);
     launch_finish_rays(sv, c->rinRays.p, c->rinHits.p, (uint32_t)n, c->rinObj.p, c->rinT.p, c->rinUv.p, c->stream);
     RTB_CUDA(c, cudaGetLastError());
     if (object) RTB_CUDA(c, cudaMemcpyAsync(object, c->rinObj.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -901,7 +982,7 @@ int rtb_occlusion_rays(rtb_ctx* c, const float* rays, uint64_t n, const float* m
     RTB_CUDA(c, c->rinOcc.alloc((size_t)n)); RTB_CUDA(c, c->rinOcc2.alloc((size_t)n));
     const SceneView sv = sceneView(c);
     launch_occlusion_others(sv, c->rinRays.p, (uint32_t)n, c->rinOcc.p, c->stream);
-    launch_trace_any_bytes(sv, c->rinRays.p, (uint32_t)n, c->rinOcc2.p, c->workCounter.p, c->stream);
+    launch_trace_any_bytes(sv, c->rinRays.p, (uint32_t)n, c->rinOcc2.p, c->lane[0].workCounter.p, c->stream);
     RTB_CUDA(c, cudaGetLastError());
     std::vector<uint8_t> a((size_t)n), b((size_t)n);
     RTB_CUDA(c, cudaMemcpyAsync(a.data(), c->rinOcc.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));

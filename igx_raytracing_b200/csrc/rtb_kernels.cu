@@ -28,6 +28,7 @@ RTB_DI bool slotToPixel(const FrameMap& fm, uint32_t i, uint32_t& x, uint32_t& y
     y = by * 32u + (s >> 2) * 4u + (lane >> 3);
     return x < fm.w && y < fm.h;
 }
+RTB_DI uint32_t tiledSlot(const FrameMap& fm, uint32_t i) { return (((i >> 10) * fm.tiledMul + fm.tiledAdd) << 10) | (i & 1023u); }
 
 // append one ray to a queue with one atomic per warp; all 32 lanes of the warp must call
 RTB_DI void queueAppend(const RayQueue& q, bool live, float4 ro, float4 rd, uint32_t slot) {
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
     }
     if (i >= fm.localSlots) return;
     uint32_t x, y;
-    if (!slotToPixel(fm, i, x, y)) { if (DO_COMP && rgba8Tiled) rgba8Tiled[i] = 0u; return; }
+    if (!slotToPixel(fm, i, x, y)) { if (DO_COMP && rgba8Tiled) rgba8Tiled[tiledSlot(fm, i)] = 0u; return; }
     const size_t px = (size_t)y * fm.w + x;
     const float4 dt = __ldg(dirT + px), un = __ldg(uvN + px);
     const uint32_t object = fbits(dt.w);
@@ -814,7 +815,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
     color = vmax(mk3(1.0f, 1.0f, 1.0f) - mk3(cr_exp(e.x), cr_exp(e.y), cr_exp(e.z)), mk3(0.0f, 0.0f, 0.0f));
     const uint32_t out = unorm8(color.x) | (unorm8(color.y) << 8) | (unorm8(color.z) << 16) | (255u << 24);
     if (rgba8) rgba8[px] = out;
-    if (rgba8Tiled) rgba8Tiled[i] = out;
+    if (rgba8Tiled) rgba8Tiled[tiledSlot(fm, i)] = out;
 }
 void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
                   const float4* dirT, const float4* uvN, const uint32_t* bits, uint2* lighting, float4* accum,

@@ -14,6 +14,9 @@ namespace rtb {
 // sectors on every scan-line-order store.
 struct FrameMap {
     uint32_t w, h, blocksX, blocksY, rank, nranks, localBlocks, localSlots;
+    // where local slot i lives in the rank's RTB_TGT_RGBA8_TILED buffer: block (i >> 10) * tiledMul + tiledAdd.  (1, 0) for a rank's
+    // own map; (2, h) for half-frame lane h, which is virtual rank h * n + r of 2 n and owns the rank's local blocks 2 k + h.
+    uint32_t tiledMul, tiledAdd;
 };
 
 struct SceneView {

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) k_path_resolve(const FrameMap fm, const S
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= fm.localSlots) return;
     uint32_t x, y;
-    if (!slotToPixel(fm, i, x, y)) { if (rgba8Tiled) rgba8Tiled[i] = 0u; return; }
+    if (!slotToPixel(fm, i, x, y)) { if (rgba8Tiled) rgba8Tiled[tiledSlot(fm, i)] = 0u; return; }
     const size_t px = (size_t)y * fm.w + x;
     const float4 l4 = pb.radiance[i];
     vec3 color = mk3(l4.x, l4.y, l4.z);
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) k_path_resolve(const FrameMap fm, const S
     color = vmax(mk3(1.0f, 1.0f, 1.0f) - mk3(cr_exp(e.x), cr_exp(e.y), cr_exp(e.z)), mk3(0.0f, 0.0f, 0.0f));
     const uint32_t out = unorm8(color.x) | (unorm8(color.y) << 8) | (unorm8(color.z) << 16) | (255u << 24);
     rgba8[px] = out;
-    if (rgba8Tiled) rgba8Tiled[i] = out;
+    if (rgba8Tiled) rgba8Tiled[tiledSlot(fm, i)] = out;
 }
 
 void launch_path_start(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t bounces, const float4* dirT, const float4* uvN,

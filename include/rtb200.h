@@ -147,6 +147,11 @@ typedef enum rtb_option {
                                       scene_graph.cpp:343-376,378-522) need not stall the frame; same hits, somewhat higher SAH
                                       cost.  Falls back to the host builder for fewer than 2 triangles or a tree too deep for
                                       the traversal stack. */
+    RTB_OPT_FRAME_LANES = 8,       /* 2 (default): RTB_PASS_FRAME runs as two half-frame lanes (the rank's even / odd 32x32 blocks) on two
+                                      streams, so that while one lane's persistent traversal launch drains its last, longest rays
+                                      the other lane's launch takes the freed SM slots; frames of fewer than 128 blocks and
+                                      instrumented frames run as one lane.  1: one lane (rtb_last_frame_ms then reports the phases;
+                                      with lanes only the total).  Same pixels either way. */
     RTB_OPT_SHADOW_ORDER = 6       /* how the occlusion rays reach the traversal kernel (RTB_ACCEL_BVH; same shadow bits in every
                                       mode).  0 = one record per pixel and sample in wavefront-slot order, misses included.
                                       1 (default) = the live rays appended to a queue (no dead records travel: occlusion launch

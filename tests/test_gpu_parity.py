@@ -737,3 +737,51 @@ def test_device_builder_returns_the_brute_force_hits(rtb, kind):
         assert infos[2].builder == 1
         assert infos[2].sah_cost < 1.6 * infos[1].sah_cost, (infos[1].sah_cost, infos[2].sah_cost)
         assert infos[2].build_ms < infos[1].build_ms
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("release", [0, 1])
+@pytest.mark.parametrize("scene_kind", ["niels", "soup"])
+def test_frame_lanes_identical(rtb, scene_kind, release):
+    """RTB_OPT_FRAME_LANES: a frame as one lane or as two half-frame lanes on two streams must be the same bits in every target
+    (also tiled, also with the RELEASE shader build, whose shadow-word clear needs both lanes' G-buffer)."""
+    if scene_kind == "soup":
+        n = 150_000
+        scene = dict(triangles=rtb.gen_soup(n, 0xB200), lights=rtb.niels_scene()["lights"][:32],
+                     materials=rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0),
+                     material_indices=np.zeros(n, np.uint32), info=np.array([1, 1, n, 0, 0, 0, 1, 0, 0], np.uint32))
+        w, h, samples, eye, limits = 1000, 600, 2, (0.0, 0.0, 13.9), dict(max_triangles=n)
+    else:
+        scene, w, h, samples, eye, limits = rtb.niels_scene(0.2), 1111, 555, 3, (6, 5, 12), dict()
+    outs = []
+    for lanes, tile in ((1, None), (2, None), (2, (1, 3))):
+        ctx = rtb.Context(**limits)
+        if tile:
+            ctx.set_option(rtb.OPT_TILE_COUNT, tile[1])
+            ctx.set_option(rtb.OPT_TILE_RANK, tile[0])
+        ctx.set_option(rtb.OPT_FRAME_LANES, lanes)
+        ctx.set_option(rtb.OPT_SHADER_BUILD, release)
+        ctx.resize(w, h, samples)
+        ctx.upload_scene(scene, synthetic_sky())
+        ctx.build_accel(rtb.ACCEL_BVH)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=eye, flags=2))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((2.0, 5.0)))
+        for _ in range(3):
+            ctx.dispatch(rtb.PASS_FRAME)
+        o = {k: ctx.readback(t) for k, t in (("dirT", rtb.TGT_DIR_T), ("uvN", rtb.TGT_UV_NORMAL), ("bits", rtb.TGT_SHADOW_BITS), ("lighting", rtb.TGT_LIGHTING),
+                                                 ("accum", rtb.TGT_ACCUM), ("rgba8", rtb.TGT_RGBA8))}
+        if tile:
+            o["tiled"] = ctx.readback(rtb.TGT_RGBA8_TILED)
+        outs.append(o)
+        ctx.close()
+    one, two, tiled = outs
+    for k in ("dirT", "uvN", "bits", "lighting", "accum", "rgba8"):
+        assert np.array_equal(one[k].view(np.uint8), two[k].view(np.uint8)), k
+    # the tiled rank's own pixels equal the full frame's, and its tiled buffer holds them in the rank's slot order
+    bx, by = (w + 31) // 32, (h + 31) // 32
+    own = (np.arange(bx * by) % 3 == 1).reshape(by, bx)
+    px = np.kron(own, np.ones((32, 32), bool))[:h, :w]
+    assert np.array_equal(one["rgba8"][px], tiled["rgba8"][px])
+    from igx_raytracing_b200 import tiles
+    x, y, valid = tiles.slot_pixels(w, h, 1, 3)
+    assert np.array_equal(tiled["tiled"][: valid.size][valid], one["rgba8"][y[valid], x[valid]])
