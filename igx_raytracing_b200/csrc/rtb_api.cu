@@ -76,7 +76,12 @@ struct rtb_ctx {
     } lane[2];
     FrameMap laneFm[2]{};             // the two half-frame maps: lane h of rank r is virtual rank h * n + r of 2 n
     cudaStream_t laneStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
-    uint32_t lanesOpt = 2;            // RTB_OPT_FRAME_LANES
+    uint32_t lanesOpt = 1;            // RTB_OPT_FRAME_LANES
+    // RTB_PASS_FRAME as two CUDA graphs (everything before the shade launch / the shade launch), replayed while nothing the
+    // recorded launches hold by value has changed: `stamp` counts those changes
+    uint32_t graphOpt = 1;            // RTB_OPT_FRAME_GRAPH
+    uint64_t stamp = 1, lastFrameStamp = 0, graphStamp = 0;
+    cudaGraphExec_t graphA = nullptr, graphB = nullptr;
     DevBuf<TraceCounters> counters;   // [0] primary, [1] shadow
     bool countersOn = false;
     uint32_t countersMode = 0;        // 1: per-ray algorithmic counts (per-lane kernel); 2: what the kernels in use fetch
@@ -354,31 +359,74 @@ int passShade(rtb_ctx* c, int what, int lane = -1) {
 bool useLanes(const rtb_ctx* c) {
     return c->lanesOpt == 2 && !c->countersOn && c->laneFm[1].localSlots >= 64u * 1024u;   // >= 64 blocks per lane: smaller frames are launch-bound
 }
-int frameInLanes(rtb_ctx* c) {
-    if (!c->laneStream) {
-        RTB_CUDA(c, cudaStreamCreateWithFlags(&c->laneStream, cudaStreamNonBlocking));
-        RTB_CUDA(c, cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
-        RTB_CUDA(c, cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
-    }
-    { const int rc = waitCopy(c, {RTB_TGT_DIR_T, RTB_TGT_UV_NORMAL, RTB_TGT_SHADOW_BITS, RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
-    int rc;
-    if (!c->releaseBuild) { if ((rc = clearShadowBits(c))) return rc; }
+int prepareLanes(rtb_ctx* c) {
+    if (c->laneStream) return RTB_OK;
+    RTB_CUDA(c, cudaStreamCreateWithFlags(&c->laneStream, cudaStreamNonBlocking));
+    RTB_CUDA(c, cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    RTB_CUDA(c, cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+    return RTB_OK;
+}
+int forkLanes(rtb_ctx* c) {
     RTB_CUDA(c, cudaEventRecord(c->evFork, c->stream));
     RTB_CUDA(c, cudaStreamWaitEvent(c->laneStream, c->evFork, 0));
-    for (int lane = 0; lane < 2; ++lane) if ((rc = passRaygen(c, false, lane))) return rc;
-    if (c->releaseBuild) {   // the RELEASE clear reads the whole G-buffer: join, clear, fork again
-        RTB_CUDA(c, cudaEventRecord(c->evJoin, c->laneStream));
-        RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evJoin, 0));
-        if ((rc = clearShadowBits(c))) return rc;
-        RTB_CUDA(c, cudaEventRecord(c->evFork, c->stream));
-        RTB_CUDA(c, cudaStreamWaitEvent(c->laneStream, c->evFork, 0));
-    }
-    for (int lane = 0; lane < 2; ++lane) {
-        if ((rc = passShadow(c, false, lane))) return rc;
-        if ((rc = passShade(c, SHADE_BOTH, lane))) return rc;
-    }
+    return RTB_OK;
+}
+int joinLanes(rtb_ctx* c) {
     RTB_CUDA(c, cudaEventRecord(c->evJoin, c->laneStream));
     RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evJoin, 0));
+    return RTB_OK;
+}
+
+// RTB_PASS_FRAME, part A: init .. occlusion.  Everything here is stream-ordered work without host synchronisation or waits on
+// outside events (the caller has done those), so that it can be captured into a CUDA graph.  `mark`: phase events (one lane only).
+int framePartA(rtb_ctx* c, bool mark) {
+    int rc;
+    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    launch_init(c->seed.p, c->stream);
+    if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (!useLanes(c)) {
+        if ((rc = passRaygen(c, mark))) return rc;
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+        if ((rc = passShadow(c, mark))) return rc;
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+        return RTB_OK;
+    }
+    // two half-frame lanes on two streams: while a persistent launch of one lane drains, the other lane's launch takes the freed SM slots
+    if (!c->releaseBuild) { if ((rc = clearShadowBits(c))) return rc; }
+    if ((rc = forkLanes(c))) return rc;
+    for (int lane = 0; lane < 2; ++lane) if ((rc = passRaygen(c, false, lane))) return rc;
+    if (c->releaseBuild) {   // the RELEASE clear reads the whole G-buffer: join, clear, fork again
+        if ((rc = joinLanes(c))) return rc;
+        if ((rc = clearShadowBits(c))) return rc;
+        if ((rc = forkLanes(c))) return rc;
+    }
+    for (int lane = 0; lane < 2; ++lane) if ((rc = passShadow(c, false, lane))) return rc;
+    return joinLanes(c);
+}
+// part B: lighting + composite
+int framePartB(rtb_ctx* c, bool mark) {
+    int rc;
+    if (!useLanes(c)) {
+        if ((rc = passShade(c, SHADE_BOTH))) return rc;
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
+        return RTB_OK;
+    }
+    if ((rc = forkLanes(c))) return rc;
+    for (int lane = 0; lane < 2; ++lane) if ((rc = passShade(c, SHADE_BOTH, lane))) return rc;
+    return joinLanes(c);
+}
+
+int captureFrame(rtb_ctx* c, int (*part)(rtb_ctx*, bool), cudaGraphExec_t* out) {
+    if (*out) { cudaGraphExecDestroy(*out); *out = nullptr; }
+    RTB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    const int rc = part(c, false);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return cudaFail(c, e, "cudaStreamEndCapture");
+    const cudaError_t e2 = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { *out = nullptr; return cudaFail(c, e2, "cudaGraphInstantiate"); }
     return RTB_OK;
 }
 
@@ -435,6 +483,8 @@ void rtb_destroy(rtb_ctx* c) {
     c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release(); c->nodeBox.release(); c->maxBits.release(); c->areaSums.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->lane[0].release(); c->lane[1].release(); c->counters.release();
+    if (c->graphA) cudaGraphExecDestroy(c->graphA);
+    if (c->graphB) cudaGraphExecDestroy(c->graphB);
     if (c->laneStream) cudaStreamDestroy(c->laneStream);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
@@ -451,6 +501,7 @@ const char* rtb_last_error(const rtb_ctx* c) { return c ? c->error.c_str() : g_c
 
 int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
     if (!c) return RTB_ERR_ARG;
+    ++c->stamp;   // recorded frames hold the options' effects
     switch (opt) {
         case RTB_OPT_COUNTERS: c->countersOn = value != 0; c->countersMode = value; return RTB_OK;
         case RTB_OPT_FUSE_PRIMARY: c->fuseOpt = value ? 1u : 0u; return RTB_OK;
@@ -474,6 +525,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             }
             return RTB_OK;
         }
+        case RTB_OPT_FRAME_GRAPH: c->graphOpt = value ? 1u : 0u; return RTB_OK;
         case RTB_OPT_FRAME_LANES:
             if (value < 1 || value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_FRAME_LANES: 1 or 2");
             c->lanesOpt = value; return RTB_OK;
@@ -495,6 +547,7 @@ int rtb_set_stream(rtb_ctx* c, void* s) {
     RTB_BIND(c);
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = s ? static_cast<cudaStream_t>(s) : c->ownStream;
+    ++c->stamp;
     return RTB_OK;
 }
 
@@ -507,6 +560,7 @@ int rtb_resize(rtb_ctx* c, uint32_t w, uint32_t h, uint32_t shadowSamples) {
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     { const int rc = drainCopy(c); if (rc) return rc; }
     c->width = w; c->height = h; c->samples = shadowSamples; c->shadowSamplesProp = shadowSamples;
+    ++c->stamp;
     const int rc = allocFrame(c);
     if (rc) { c->width = c->height = 0; c->samples = 0; makeFrameMap(c); }   // a failed allocation leaves NO frame: dispatch reports "before rtb_resize"
     return rc;
@@ -519,11 +573,13 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
     switch (id) {
         case RTB_BUF_CAMERA:
             if (off > sizeof(CameraRec) || bytes > sizeof(CameraRec) - off) return fail(c, RTB_ERR_CAPACITY, "camera upload past 144 bytes");
+            if (!c->cameraSet || std::memcmp(reinterpret_cast<uint8_t*>(&c->camera) + off, src, bytes)) ++c->stamp;   // kernels take the camera by value
             std::memcpy(reinterpret_cast<uint8_t*>(&c->camera) + off, src, bytes); c->cameraSet = true;
             return RTB_OK;
         case RTB_BUF_SCENE_INFO: {
             if (off > sizeof(SceneInfoRec) || bytes > sizeof(SceneInfoRec) - off) return fail(c, RTB_ERR_CAPACITY, "scene info upload past 36 bytes");
             const uint32_t before = c->info.triangleCount;
+            if (std::memcmp(reinterpret_cast<uint8_t*>(&c->info) + off, src, bytes)) ++c->stamp;
             std::memcpy(reinterpret_cast<uint8_t*>(&c->info) + off, src, bytes);
             if (c->info.triangleCount != before) c->accelValid = false;
             return RTB_OK;
@@ -531,6 +587,7 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
         case RTB_BUF_SHADOW_PROPS:
             if (off > 4 || bytes > 4 - off) return fail(c, RTB_ERR_CAPACITY, "shadow properties upload past 4 bytes");
             std::memcpy(reinterpret_cast<uint8_t*>(&c->shadowSamplesProp) + off, src, bytes);
+            ++c->stamp;
             if (c->width && c->shadowSamplesProp != c->samples) return rtb_resize(c, c->width, c->height, c->shadowSamplesProp);
             return RTB_OK;
         case RTB_BUF_SEED: dst = c->seed.p; cap = sizeof(SeedRec); break;
@@ -548,7 +605,8 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
     }
     if (off > cap || bytes > cap - off) return fail(c, RTB_ERR_CAPACITY, "rtb_upload: range exceeds the capacity given to rtb_create");
     if (!bytes) return RTB_OK;
-    if (id == RTB_BUF_TRIANGLES) { std::memcpy(c->triangleMirror.data() + off, src, bytes); c->accelValid = false; }
+    if (id == RTB_BUF_TRIANGLES) { std::memcpy(c->triangleMirror.data() + off, src, bytes); c->accelValid = false; ++c->stamp; }
+    if (id == RTB_BUF_LIGHTS && off < sizeof(LightRec)) ++c->stamp;   // lights[0] picks the occlusion rays' sort key
     if (id == RTB_BUF_LIGHTS && off < sizeof(LightRec)) std::memcpy(reinterpret_cast<uint8_t*>(&c->light0) + off, src, std::min(bytes, sizeof(LightRec) - off));
     // pageable source: cudaMemcpyAsync stages it before returning, so the caller may reuse src at once (like GPUBuffer::flush)
     RTB_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, src, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -558,6 +616,7 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
 int rtb_upload_skybox(rtb_ctx* c, uint32_t w, uint32_t h, const uint16_t* px) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
+    ++c->stamp;
     if (!w || !h || !px) { c->skyW = c->skyH = 0; return RTB_OK; }
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     RTB_CUDA(c, c->skybox.alloc((size_t)w * h));
@@ -572,6 +631,7 @@ int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     if (mode != RTB_ACCEL_BRUTE && mode != RTB_ACCEL_BVH && mode != RTB_ACCEL_BVH2) return fail(c, RTB_ERR_ARG, "rtb_build_accel: unknown mode");
     c->accelMode = mode;
     c->accelValid = false;   // until this build has succeeded
+    ++c->stamp;
     c->stats = BvhStats();
     c->nodeCount = 0; c->builtTriangles = 0; c->refits = 0;
     if (mode == RTB_ACCEL_BRUTE) { c->accelValid = true; return RTB_OK; }
@@ -655,6 +715,7 @@ int rtb_refit_accel(rtb_ctx* c) {
     }
     ++c->refits;
     c->accelValid = true;
+    ++c->stamp;   // the scene bounds feed the packet rule
     return RTB_OK;
 }
 
@@ -677,27 +738,30 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
         case RTB_PASS_SHADOW: rc = passShadow(c, false); break;
         case RTB_PASS_LIGHTING: rc = passShade(c, SHADE_LIGHTING); break;
         case RTB_PASS_COMPOSITE: rc = passShade(c, SHADE_COMPOSITE); break;
-        case RTB_PASS_FRAME:
+        case RTB_PASS_FRAME: {
             if (c->countersOn) RTB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(TraceCounters), c->stream));
-            RTB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-            if ((rc = waitCopy(c, {RTB_TGT_SEED}))) return rc;
-            launch_init(c->seed.p, c->stream);
-            RTB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-            if (useLanes(c)) {
-                if ((rc = frameInLanes(c))) return rc;
-                for (int k = 2; k < 7; ++k) RTB_CUDA(c, cudaEventRecord(c->ev[k], c->stream));   // phases overlap: only the total means something
-                RTB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
-                c->frameTimed = true;
-                break;
+            if (useLanes(c)) { if ((rc = prepareLanes(c))) return rc; }
+            // copies still in flight (rtb_readback_async) are waited for outside the recorded work: before part A those of its
+            // targets, before part B those of the shade targets — so a frame's read-back overlaps the next frame's traversal
+            if ((rc = waitCopy(c, {RTB_TGT_SEED, RTB_TGT_DIR_T, RTB_TGT_UV_NORMAL, RTB_TGT_SHADOW_BITS}))) return rc;
+            const bool canGraph = c->graphOpt && !c->countersOn;
+            const bool replay = canGraph && c->graphA && c->graphB && c->graphStamp == c->stamp;
+            const bool capture = canGraph && !replay && c->lastFrameStamp == c->stamp;   // the second frame with nothing changed
+            c->lastFrameStamp = c->stamp;
+            if (capture) {
+                if ((rc = captureFrame(c, framePartA, &c->graphA))) return rc;
+                if ((rc = captureFrame(c, framePartB, &c->graphB))) return rc;
+                c->graphStamp = c->stamp;
             }
-            if ((rc = passRaygen(c, true))) return rc;
-            RTB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-            if ((rc = passShadow(c, true))) return rc;
-            RTB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-            if ((rc = passShade(c, SHADE_BOTH))) return rc;
-            RTB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
-            c->frameTimed = true;
+            const bool graph = replay || capture;
+            if (graph) RTB_CUDA(c, cudaGraphLaunch(c->graphA, c->stream));
+            else if ((rc = framePartA(c, !useLanes(c)))) return rc;
+            if ((rc = waitCopy(c, {RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}))) return rc;
+            if (graph) RTB_CUDA(c, cudaGraphLaunch(c->graphB, c->stream));
+            else if ((rc = framePartB(c, !useLanes(c)))) return rc;
+            c->frameTimed = !graph && !useLanes(c);
             break;
+        }
         default: return fail(c, RTB_ERR_ARG, "rtb_dispatch: unknown pass");
     }
     if (rc) return rc;
@@ -834,7 +898,7 @@ int rtb_counters_get(rtb_ctx* c, rtb_counters* out) {
 int rtb_last_frame_ms(rtb_ctx* c, float ms[8]) {
     if (!c || !ms) return RTB_ERR_ARG;
     RTB_BIND(c);
-    if (!c->frameTimed) return fail(c, RTB_ERR_STATE, "no RTB_PASS_FRAME has been dispatched yet");
+    if (!c->frameTimed) return fail(c, RTB_ERR_STATE, "the last RTB_PASS_FRAME recorded no phase events: none dispatched yet, or it ran as a CUDA graph / in two lanes (set RTB_OPT_FRAME_GRAPH = 0 and RTB_OPT_FRAME_LANES = 1 to time the phases)");
     RTB_CUDA(c, cudaEventSynchronize(c->ev[7]));
     for (int i = 0; i < 7; ++i) RTB_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
     RTB_CUDA(c, cudaEventElapsedTime(&ms[7], c->ev[0], c->ev[7]));

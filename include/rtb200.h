@@ -147,11 +147,18 @@ typedef enum rtb_option {
                                       scene_graph.cpp:343-376,378-522) need not stall the frame; same hits, somewhat higher SAH
                                       cost.  Falls back to the host builder for fewer than 2 triangles or a tree too deep for
                                       the traversal stack. */
-    RTB_OPT_FRAME_LANES = 8,       /* 2 (default): RTB_PASS_FRAME runs as two half-frame lanes (the rank's even / odd 32x32 blocks) on two
+    RTB_OPT_FRAME_GRAPH = 9,       /* 1 (default): RTB_PASS_FRAME is recorded into two CUDA graphs (everything before the shade launch /
+                                      the shade launch) the second time it is dispatched with nothing changed, and replayed from
+                                      then on — what the reference does with its CommandList (recorded once, replayed per frame
+                                      and N times for an export: ref: src/rt/raytracing_interface.cpp:144-179,222-226).  Anything
+                                      the launches hold by value (camera, scene info, options, size, acceleration structure)
+                                      re-records; uploads into device buffers (seed, geometry, materials) do not.  0: every frame
+                                      is launched directly (rtb_last_frame_ms needs this). */
+    RTB_OPT_FRAME_LANES = 8,       /* 2: RTB_PASS_FRAME runs as two half-frame lanes (the rank's even / odd 32x32 blocks) on two
                                       streams, so that while one lane's persistent traversal launch drains its last, longest rays
                                       the other lane's launch takes the freed SM slots; frames of fewer than 128 blocks and
-                                      instrumented frames run as one lane.  1: one lane (rtb_last_frame_ms then reports the phases;
-                                      with lanes only the total).  Same pixels either way. */
+                                      instrumented frames run as one lane.  1 (default): one lane.  Same pixels either way; measured
+                                      on B200 the halved launches cost more than the filled tails give back. */
     RTB_OPT_SHADOW_ORDER = 6       /* how the occlusion rays reach the traversal kernel (RTB_ACCEL_BVH; same shadow bits in every
                                       mode).  0 = one record per pixel and sample in wavefront-slot order, misses included.
                                       1 (default) = the live rays appended to a queue (no dead records travel: occlusion launch

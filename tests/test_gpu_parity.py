@@ -785,3 +785,61 @@ def test_frame_lanes_identical(rtb, scene_kind, release):
     from igx_raytracing_b200 import tiles
     x, y, valid = tiles.slot_pixels(w, h, 1, 3)
     assert np.array_equal(tiled["tiled"][: valid.size][valid], one["rgba8"][y[valid], x[valid]])
+
+
+@pytest.mark.gpu
+def test_frame_graph_replay_identical_and_rerecorded_on_change(rtb, oracle):
+    """RTB_OPT_FRAME_GRAPH: from the third unchanged frame on RTB_PASS_FRAME replays two CUDA graphs.  Six accumulated frames
+    equal the oracle's (and the directly launched ones); a camera change, a moved triangle (refit) and a new shadow-sample count
+    re-record instead of replaying stale launches."""
+    w, h = 320, 180
+    sky = synthetic_sky()
+    cam_kw = dict(eye=(6, 5, 12), flags=2)
+
+    def run(graph):
+        ctx = rtb.Context()
+        ctx.set_option(rtb.OPT_FRAME_GRAPH, graph)
+        ctx.resize(w, h, 2)
+        scene = rtb.niels_scene(0.0)
+        ctx.upload_scene(scene, sky)
+        ctx.build_accel(rtb.ACCEL_BVH)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, **cam_kw))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((3.0, 9.0)))
+        outs = []
+        for _ in range(6):
+            ctx.dispatch(rtb.PASS_FRAME)
+        outs.append((ctx.readback(rtb.TGT_ACCUM), ctx.readback(rtb.TGT_RGBA8), ctx.readback(rtb.TGT_SEED)))
+        # a new camera: the recorded launches hold the old one by value
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(5, 4, 11), flags=0))
+        for _ in range(4):
+            ctx.dispatch(rtb.PASS_FRAME)
+        outs.append((ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_RGBA8)))
+        # a moved triangle + refit, then a different shadow-sample count
+        tris = np.asarray(scene["triangles"]).view(np.float32).reshape(-1, 12).copy()
+        tris[0, [1, 5, 9]] += 0.75
+        ctx.upload(rtb.BUF_TRIANGLES, tris.view(np.uint8).reshape(-1))
+        ctx.refit_accel()
+        for _ in range(3):
+            ctx.dispatch(rtb.PASS_FRAME)
+        outs.append((ctx.readback(rtb.TGT_DIR_T), ctx.readback(rtb.TGT_RGBA8)))
+        ctx.resize(w, h, 3)
+        for _ in range(3):
+            ctx.dispatch(rtb.PASS_FRAME)
+        outs.append((ctx.readback(rtb.TGT_SHADOW_BITS), ctx.readback(rtb.TGT_RGBA8)))
+        ctx.close()
+        return outs
+
+    direct, replayed = run(0), run(1)
+    for a, b in zip(direct, replayed):
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x).view(np.uint8), np.asarray(y).view(np.uint8))
+    # and the six accumulated frames are the oracle's
+    seed = oracle.seed((3.0, 9.0))
+    acc = np.zeros((h, w, 4), np.float32)
+    osc = oracle.niels_scene(0.0, sky)
+    for _ in range(6):
+        want = oracle.frame(osc, oracle.camera(w, h, **cam_kw), seed, 2, accum=acc)
+    assert np.array_equal(replayed[0][2], seed)
+    bad = int((replayed[0][0].view(np.uint32) != acc.view(np.uint32)).any(-1).sum())
+    assert bad <= 4
+    assert int((replayed[0][1] != want["rgba8"]).sum()) <= 4
