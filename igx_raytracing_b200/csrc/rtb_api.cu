@@ -82,6 +82,7 @@ struct rtb_ctx {
     uint32_t graphOpt = 1;            // RTB_OPT_FRAME_GRAPH
     uint64_t stamp = 1, lastFrameStamp = 0, graphStamp = 0;
     cudaGraphExec_t graphA = nullptr, graphB = nullptr;
+    bool capturing = false;
     DevBuf<TraceCounters> counters;   // [0] primary, [1] shadow
     bool countersOn = false;
     uint32_t countersMode = 0;        // 1: per-ray algorithmic counts (per-lane kernel); 2: what the kernels in use fetch
@@ -171,7 +172,7 @@ int allocFrame(rtb_ctx* c) {
 
 // before a pass overwrites `target`: let a read-back of it that is still in flight finish first (device-side wait)
 int waitCopy(rtb_ctx* c, std::initializer_list<int> targets) {
-    if (c->copyTarget < 0) return RTB_OK;
+    if (c->copyTarget < 0 || c->capturing) return RTB_OK;   // (while a frame is being recorded the dispatcher does the waits, outside the graph)
     for (int t : targets)
         if (t == c->copyTarget) { RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evCopied, 0)); c->copyTarget = -1; break; }
     return RTB_OK;
@@ -419,7 +420,9 @@ int framePartB(rtb_ctx* c, bool mark) {
 int captureFrame(rtb_ctx* c, int (*part)(rtb_ctx*, bool), cudaGraphExec_t* out) {
     if (*out) { cudaGraphExecDestroy(*out); *out = nullptr; }
     RTB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
     const int rc = part(c, false);
+    c->capturing = false;
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }

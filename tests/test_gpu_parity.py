@@ -726,9 +726,10 @@ def test_device_builder_returns_the_brute_force_hits(rtb, kind):
             before = ctx.accel_bytes()
             ctx.refit_accel()
             assert np.array_equal(before, ctx.accel_bytes())
+            ctx.build_accel(mode)   # a second build: the first one in a process also pays for loading the sort's kernels
+            infos[-1] = ctx.accel_info()
         ctx.close()
     brute, host, dev = outs
-    assert infos[2].builder == (1 if kind != "two_triangles" or True else 0) or infos[2].builder == 0
     for a, b in zip(brute, dev):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "device-built tree differs from the linear loop"
     for a, b in zip(host, dev):
