@@ -368,27 +368,27 @@ def main():
 
     def present(k, mode):
         """N > 1: presentation of frame k on the side stream (double-buffered), under the rendering of frame k + 1.
-        'device' / 'e2e_gather': NCCL gather + rtb_untile on rank 0 (+ one device-to-host copy); 'e2e': every rank writes its own
-        tiles into the shared host frame."""
+        'device' / 'e2e': NCCL gather + rtb_untile on rank 0 (+ one device-to-host copy by the copy engine); 'e2e_host': every rank
+        writes its own tiles into the shared host frame (rtb_present_host)."""
         i = k & 1
         stream.wait_event(done[i])                      # buffers i are free again (frame k - 2 has been presented)
         staging[i].copy_(tiled, non_blocking=True)
         ready[i].record(stream)
         with torch.cuda.stream(side):
             side.wait_event(ready[i])
-            if mode == "e2e":
+            if mode == "e2e_host":
                 ctx.present_host(shared_ptr, staging[i].data_ptr(), side.cuda_stream)
             else:
                 dist.gather(staging[i], list(gathered[i].split(slots)) if rank == 0 else None, dst=0)
                 if rank == 0:
                     ctx.untile_on(gathered[i].data_ptr(), world, slots, untiled[i].data_ptr(), side.cuda_stream)
-                    if mode == "e2e_gather":
+                    if mode == "e2e":
                         frame_pins[i].copy_(untiled[i], non_blocking=True)
             done[i].record(side)
 
     def frame(k, mode):
-        """mode: 'device' (inputs resident), 'e2e' (host buffers in, frame in host memory out), 'e2e_gather' (N > 1: through the
-        NCCL gather and rank 0's PCIe link instead of rtb_present_host)"""
+        """mode: 'device' (inputs resident), 'e2e' (host buffers in, frame in host memory out), 'e2e_host' (N > 1: the frame reaches
+        the host through rtb_present_host on every rank instead of the NCCL gather and rank 0's PCIe link)"""
         if mode != "device":   # what the host does per frame in the reference: camera + seed upload (raytracing_interface.cpp:327, composite_task.cpp:243)
             ctx.upload_raw(rtb.BUF_CAMERA, cam_pin.data_ptr(), 144)
             ctx.upload_raw(rtb.BUF_SEED, seed_pin.data_ptr(), 24)
@@ -461,7 +461,7 @@ def main():
     if world > 1:
         checksum_frame()
         present(0, "device")
-        present(1, "e2e")
+        present(1, "e2e_host")
         drain()
         barrier()
         if rank == 0:
@@ -547,9 +547,9 @@ def main():
 
     e2e_ms, _ = timed("e2e", args.steps, args.warmup, False)
     e2e_value = rays_per_frame / (e2e_ms / args.steps * 1e-3) / 1e6
-    e2e_gather_ms = None
+    e2e_host_ms = None
     if world > 1:
-        e2e_gather_ms, _ = timed("e2e_gather", args.steps, args.warmup, False)
+        e2e_host_ms, _ = timed("e2e_host", args.steps, args.warmup, False)
 
     if world > 1:
         torch.cuda.cudart().cudaHostUnregister(shared_ptr)
@@ -646,11 +646,11 @@ def main():
     else:   # init, fused camera-ray launch (or raygen, nearest hit, finish), shadow-ray set-up, occlusion, lighting + composite
         kernels_per_frame = (5 if info.primary_packets == 3 else 7) * spp
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 168 * world, "d2h_bytes_per_step": w * h * 4, "ms_per_step": e2e_ms / args.steps,
-           "path": ("every rank writes its tiles of the frame into ONE page-locked host frame in shared memory (rtb_present_host: %d PCIe links instead of rank 0's)" % world) if world > 1
+           "path": "NCCL gather to rank 0 + rtb_untile + one device-to-host copy (copy engine) over rank 0's PCIe link, all on a second stream under the next frame" if world > 1
                    else "rtb_readback_async of the rgba8 frame into pinned memory (copy engine, overlaps the next frame)"}
-    if e2e_gather_ms is not None:
-        e2e["via_nccl_gather"] = {"value": rays_per_frame / (e2e_gather_ms / args.steps * 1e-3) / 1e6, "ms_per_step": e2e_gather_ms / args.steps,
-                                  "path": "NCCL gather to rank 0 + rtb_untile + one device-to-host copy over rank 0's PCIe link, all under the next frame"}
+    if e2e_host_ms is not None:
+        e2e["via_present_host"] = {"value": rays_per_frame / (e2e_host_ms / args.steps * 1e-3) / 1e6, "ms_per_step": e2e_host_ms / args.steps,
+                                   "path": "no gather: every rank's rtb_present_host kernel writes its tiles into ONE page-locked host frame in shared memory (%d PCIe links); the kernel waits for SM slots behind the next frame's persistent launches" % world}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
