@@ -43,6 +43,9 @@ CASES = {
     "niels_degenerate_tri_96x54": dict(time=0.0, w=96, h=54, samples=1, cam=dict(eye=(2, 5, 6), pitch=-0.25), off=(0.0, 0.0), frames=1, sky=True,
                                        degenerate=True),
     "niels_release_96x54": dict(time=0.0, w=96, h=54, samples=2, cam=dict(eye=(6, 5, 12)), off=(0.0, 0.0), frames=1, sky=True, release=True),
+    # diffuse bounces (rtb_path_frame): NO reference semantics beyond depth 0 (the reference traces no secondary rays), so this fixture
+    # is the ORACLE's statement of our definition (oracle.h orc_path_frame); its depth 0 is checked against the reference's raygen.comp
+    "niels_path4_64x36": dict(time=0.0, w=64, h=36, samples=1, cam=dict(eye=(6, 5, 12), flags=2), off=(3.0, 9.0), frames=2, sky=True, path_bounces=4),
     "niels_release_degenerate_80x45": dict(time=0.0, w=80, h=45, samples=1, cam=dict(eye=(2, 5, 6), pitch=-0.25), off=(0.0, 0.0), frames=1,
                                            sky=True, degenerate=True, release=True),
 }
@@ -73,6 +76,23 @@ def render(engine, oracle, case):
                 dirT=ref["dirT"], uvN=ref["uvN"], bits=ref["bits"], lighting=ref["lighting"], rgba8=ref["rgba8"], accum=accum)
 
 
+def render_path(oracle, ref, case):
+    """rtb_path_frame's definition as the oracle states it; depth 0 (the G-buffer) must be the reference's raygen.comp output"""
+    from conftest import case_scene
+    scene = case_scene(oracle, case)
+    w, h = case["w"], case["h"]
+    cam = oracle.camera(w, h, **case["cam"])
+    seed = oracle.seed(tuple(case["off"]))
+    accum = np.zeros((h, w, 4), np.float32)
+    for _ in range(case["frames"]):
+        out = oracle.path_frame(scene, cam, seed, case["path_bounces"], accum=accum)
+        ref_dirT, _ = ref.raygen(scene, cam, seed)   # seed is the state after this frame's init pass
+        if not np.array_equal(ref_dirT.view(np.uint32), out["dirT"].view(np.uint32)):
+            sys.exit("path fixture: depth 0 differs from the reference's raygen.comp")
+    return dict(camera=np.frombuffer(bytes(cam), np.uint8).copy(), seed_after=np.frombuffer(bytes(seed), np.uint8).copy(),
+                dirT=out["dirT"], rgba8=out["rgba8"], accum=accum)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -87,13 +107,16 @@ def main():
     bad = 0
     for name, case in CASES.items():
         release = bool(case.get("release"))
-        out = render(refs[release], orc, case)
-        orc.set_mode(1 if release else 0)
-        mine = render(orc, orc, case)
-        orc.set_mode(0)
-        for k, v in out.items():
-            if not np.array_equal(np.asarray(v).view(np.uint8), np.asarray(mine[k]).view(np.uint8)):
-                sys.exit(f"{name}: the oracle's {k} differs from the reference shaders — fix the oracle before writing fixtures")
+        if case.get("path_bounces") is not None:
+            out = render_path(orc, refs[False], case)
+        else:
+            out = render(refs[release], orc, case)
+            orc.set_mode(1 if release else 0)
+            mine = render(orc, orc, case)
+            orc.set_mode(0)
+            for k, v in out.items():
+                if not np.array_equal(np.asarray(v).view(np.uint8), np.asarray(mine[k]).view(np.uint8)):
+                    sys.exit(f"{name}: the oracle's {k} differs from the reference shaders — fix the oracle before writing fixtures")
         path = os.path.join(GOLDEN, name + ".npz")
         if args.check:
             have = np.load(path)
