@@ -77,6 +77,12 @@ struct rtb_ctx {
     FrameMap laneFm[2]{};             // the two half-frame maps: lane h of rank r is virtual rank h * n + r of 2 n
     cudaStream_t laneStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
     uint32_t lanesOpt = 1;            // RTB_OPT_FRAME_LANES
+    // beyond the reference: every light evaluated, tile light lists, History blend (LightsView in rtb_kernels.cuh)
+    uint32_t lightsOpt = 0;           // RTB_OPT_LIGHTS: 0 reference (light 0 x lightCount), 1 all lights, 2 all lights through tile lists
+    float historyAlpha = 0.0f;        // RTB_OPT_HISTORY_ALPHA (float bits): 0 = off
+    bool historyValid = false;        // false: the next lighting pass starts the History texture (alpha 1)
+    DevBuf<uint32_t> lightTileCount, lightTileList; DevBuf<uint2> history;
+    uint32_t bitsLayers = 0;          // layers the shadow-word buffer currently holds
     // RTB_PASS_FRAME as two CUDA graphs (everything before the shade launch / the shade launch), replayed while nothing the
     // recorded launches hold by value has changed: `stamp` counts those changes
     uint32_t graphOpt = 1;            // RTB_OPT_FRAME_GRAPH
@@ -295,12 +301,44 @@ RayBin shadowBin(const rtb_ctx* c, uint32_t maxRays) {
     return b;
 }
 
+uint32_t shadowLayers(const rtb_ctx* c) { return c->samples * (c->lightsOpt ? std::max(c->info.lightCount, 1u) : 1u); }
+
+// the shadow-word buffer holds `layers` layers (samples, or lights x samples with RTB_OPT_LIGHTS); grown when a scene gains lights
+int ensureShadowWords(rtb_ctx* c) {
+    const uint32_t layers = shadowLayers(c);
+    if (layers == c->bitsLayers && c->bits.p) return RTB_OK;
+    const size_t words = shadowWords(c->width, c->height, layers);
+    if (words > c->bits.count) {
+        RTB_CUDA(c, cudaStreamSynchronize(c->stream));
+        RTB_CUDA(c, c->bits.alloc(words));
+    }
+    RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, c->bits.bytes(), c->stream));
+    c->bitsLayers = layers;
+    return RTB_OK;
+}
+
+int lightsView(rtb_ctx* c, LightsView& lv, bool forLighting) {
+    lv = LightsView{};
+    lv.mode = c->lightsOpt && c->info.lightCount ? c->lightsOpt : 0u;
+    lv.tilesX = (c->width + 15u) / 16u;
+    lv.lightBegin = 0; lv.lightEnd = c->info.lightCount;
+    if (lv.mode == 2u) { lv.tileCount = c->lightTileCount.p; lv.tileList = c->lightTileList.p; }
+    if (forLighting && c->historyAlpha > 0.0f) {
+        const size_t px = (size_t)c->width * c->height;
+        if (c->history.count < px) { RTB_CUDA(c, cudaStreamSynchronize(c->stream)); RTB_CUDA(c, c->history.alloc(px)); c->historyValid = false; }
+        lv.history = c->history.p;
+        lv.historyAlpha = c->historyValid ? c->historyAlpha : 1.0f;   // the first frame of a sequence starts the history
+    }
+    return RTB_OK;
+}
+
 // the shadow words start from zero (DEBUG build) or keep what they held where no subgroup has a hit (RELEASE): once per frame,
 // before any lane's rays are traced
 int clearShadowBits(rtb_ctx* c) {
     { const int rc = waitCopy(c, {RTB_TGT_SHADOW_BITS}); if (rc) return rc; }
-    if (c->releaseBuild) launch_clear_hit_strips(c->fm, c->dirT.p, c->samples, c->bits.p, c->stream);
-    else RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, c->samples) * 4, c->stream));
+    { const int rc = ensureShadowWords(c); if (rc) return rc; }
+    if (c->releaseBuild) launch_clear_hit_strips(c->fm, c->dirT.p, shadowLayers(c), c->bits.p, c->stream);
+    else RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, (size_t)shadowWords(c->width, c->height, shadowLayers(c)) * 4, c->stream));
     return RTB_OK;
 }
 
@@ -310,8 +348,34 @@ int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
     const LaneRef L = laneOf(c, lane);
     rtb_ctx::LaneBufs& B = L.b;
     const SceneView sv = sceneView(c);
-    const uint32_t maxRays = L.fm.localSlots * c->samples;
     TraceCounters* counters = c->countersOn ? c->counters.p + 1 : nullptr;
+    if (c->lightsOpt && sv.info.lightCount) {
+        // ---- every light (beyond the reference): the queue is filled and traced in chunks of lights so that it stays bounded ----
+        LightsView lv;
+        { const int rc = lightsView(c, lv, false); if (rc) return rc; }
+        if (lv.mode == 2u) {
+            const uint32_t tiles = lv.tilesX * ((c->height + 15u) / 16u);
+            RTB_CUDA(c, c->lightTileCount.alloc(tiles)); RTB_CUDA(c, c->lightTileList.alloc((size_t)tiles * LIGHTS_PER_TILE));
+            lv.tileCount = c->lightTileCount.p; lv.tileList = c->lightTileList.p;
+            launch_light_tiles(L.fm, sv, &c->camera, c->dirT.p, c->lightTileCount.p, c->lightTileList.p, L.st);
+        }
+        const uint32_t perLight = L.fm.localSlots * c->samples;
+        if (!perLight) return RTB_OK;
+        const uint32_t lightsPerChunk = std::max(1u, std::min(sv.info.lightCount, (64u << 20) / perLight));
+        const uint32_t capacity = lightsPerChunk * perLight;
+        RTB_CUDA(c, B.queueCount.alloc(1)); RTB_CUDA(c, B.queueSlots.alloc(capacity)); RTB_CUDA(c, B.queueRays.alloc(capacity));
+        RayQueue q{};
+        q.rays = B.queueRays.p; q.slotIds = B.queueSlots.p; q.count = B.queueCount.p;
+        if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], L.st));
+        for (uint32_t first = 0; first < sv.info.lightCount; first += lightsPerChunk) {
+            lv.lightBegin = first; lv.lightEnd = std::min(sv.info.lightCount, first + lightsPerChunk);
+            RTB_CUDA(c, cudaMemsetAsync(B.queueCount.p, 0, 4, L.st));
+            launch_shadowgen_lights(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->bits.p, q, lv, L.st);
+            launch_trace_any_bits(L.fm, sv, q.rays, capacity, c->bits.p, B.workCounter.p, counters, q.slotIds, q.count, L.st);
+        }
+        return RTB_OK;
+    }
+    const uint32_t maxRays = L.fm.localSlots * c->samples;
     if (!c->shadowOrder || sv.useBvh != ACCEL_KIND_CWBVH || !sv.info.triangleCount || !maxRays) {
         // slot order: one record per (sample, slot), what the first-generation kernels and the reference loop consume
         launch_shadowgen(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, B.rays.p, c->bits.p, nullptr, nullptr, L.st);
@@ -350,15 +414,18 @@ int passShade(rtb_ctx* c, int what, int lane = -1) {
     if (lane < 0) { const int rc = waitCopy(c, {RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
     const LaneRef L = laneOf(c, lane);
     const SceneView sv = sceneView(c);
+    LightsView lv;
+    { const int rc = lightsView(c, lv, what != SHADE_COMPOSITE); if (rc) return rc; }
     launch_shade(what, L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->uvN.p, c->bits.p, c->lighting.p, c->accum.p,
-                 c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, L.st);
+                 c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, L.st, &lv);
+    if (lv.history && !c->historyValid) { c->historyValid = true; ++c->stamp; }   // the recorded launches hold alpha by value
     return RTB_OK;
 }
 
 // a frame as two half-frame lanes on two streams: while a persistent launch of one lane drains (its last rays are the longest),
 // the other lane's launch takes the freed SM slots.  Same kernels, same pixels; only the launches' slot ranges differ.
 bool useLanes(const rtb_ctx* c) {
-    return c->lanesOpt == 2 && !c->countersOn && c->laneFm[1].localSlots >= 64u * 1024u;   // >= 64 blocks per lane: smaller frames are launch-bound
+    return c->lanesOpt == 2 && !c->countersOn && !c->lightsOpt && !(c->historyAlpha > 0.0f) && c->laneFm[1].localSlots >= 64u * 1024u;   // >= 64 blocks per lane: smaller frames are launch-bound
 }
 int prepareLanes(rtb_ctx* c) {
     if (c->laneStream) return RTB_OK;
@@ -486,6 +553,7 @@ void rtb_destroy(rtb_ctx* c) {
     c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release(); c->nodeBox.release(); c->maxBits.release(); c->areaSums.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->lane[0].release(); c->lane[1].release(); c->counters.release();
+    c->lightTileCount.release(); c->lightTileList.release(); c->history.release();
     if (c->graphA) cudaGraphExecDestroy(c->graphA);
     if (c->graphB) cudaGraphExecDestroy(c->graphB);
     if (c->laneStream) cudaStreamDestroy(c->laneStream);
@@ -528,6 +596,14 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             }
             return RTB_OK;
         }
+        case RTB_OPT_LIGHTS:
+            if (value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_LIGHTS: 0 reference (light 0 x lightCount), 1 all lights, 2 all lights through tile lists");
+            c->lightsOpt = value; c->historyValid = false; return RTB_OK;
+        case RTB_OPT_HISTORY_ALPHA: {
+            float a; std::memcpy(&a, &value, 4);
+            if (!(a >= 0.0f && a <= 1.0f)) return fail(c, RTB_ERR_ARG, "RTB_OPT_HISTORY_ALPHA: the bits of a float in [0, 1]; 0 switches the History blend off");
+            c->historyAlpha = a; c->historyValid = false; return RTB_OK;
+        }
         case RTB_OPT_FRAME_GRAPH: c->graphOpt = value ? 1u : 0u; return RTB_OK;
         case RTB_OPT_FRAME_LANES:
             if (value < 1 || value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_FRAME_LANES: 1 or 2");
@@ -564,6 +640,7 @@ int rtb_resize(rtb_ctx* c, uint32_t w, uint32_t h, uint32_t shadowSamples) {
     { const int rc = drainCopy(c); if (rc) return rc; }
     c->width = w; c->height = h; c->samples = shadowSamples; c->shadowSamplesProp = shadowSamples;
     ++c->stamp;
+    c->historyValid = false; c->bitsLayers = 0;
     const int rc = allocFrame(c);
     if (rc) { c->width = c->height = 0; c->samples = 0; makeFrameMap(c); }   // a failed allocation leaves NO frame: dispatch reports "before rtb_resize"
     return rc;
@@ -779,7 +856,7 @@ int rtb_device_ptr(rtb_ctx* c, rtb_target t, void** out, size_t* bytes) {
     switch (t) {
         case RTB_TGT_DIR_T: p = c->dirT.p; n = px * 16; break;
         case RTB_TGT_UV_NORMAL: p = c->uvN.p; n = px * 16; break;
-        case RTB_TGT_SHADOW_BITS: p = c->bits.p; n = (size_t)shadowWords(c->width, c->height, c->samples) * 4; break;
+        case RTB_TGT_SHADOW_BITS: p = c->bits.p; n = (size_t)shadowWords(c->width, c->height, shadowLayers(c)) * 4; break;
         case RTB_TGT_LIGHTING: p = c->lighting.p; n = px * 8; break;
         case RTB_TGT_ACCUM: p = c->accum.p; n = px * 16; break;
         case RTB_TGT_RGBA8: p = c->rgba8.p; n = px * 4; break;

@@ -736,11 +736,11 @@ void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint
 #ifndef RTB_SHADE_MINBLOCKS
 #define RTB_SHADE_MINBLOCKS 6
 #endif
-template <bool DO_LIGHT, bool DO_COMP>
+template <bool DO_LIGHT, bool DO_COMP, bool EXT>
 __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
                                                uint32_t samples, const float4* __restrict__ dirT, const float4* __restrict__ uvN,
                                                const uint32_t* __restrict__ bits, uint2* __restrict__ lighting, float4* __restrict__ accum,
-                                               uint32_t* __restrict__ rgba8, uint32_t* __restrict__ rgba8Tiled) {
+                                               uint32_t* __restrict__ rgba8, uint32_t* __restrict__ rgba8Tiled, const LightsView lv) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     {
         uint32_t x0, y0;
@@ -772,18 +772,48 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
             const float NdotV = fmaxf(dot(v, -n), 0.0f);
             const vec2 loc = mk2((float)x, (float)y);
             const vec2 uv = (loc + rand2(loc + mk2(0.0f, 0.0f))) / 128.0f;   // Seed is unbound in lighting.comp: reads as zero (decree D8)
-            const LightRec l0 = sv.lights[0];
             const uint32_t bit = 1u << ((x & 15u) | ((y & 1u) << 4));
-            for (uint32_t s = 0; s < samples; ++s) {
-                const vec2 random = rand2(uv + hammersley(s, samples));
-                const uint32_t word = __ldg(bits + indexToLight(x, y, fm.w, fm.h, s));
-                if (!(word & bit)) light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, l0, hitPos, n, v, NdotV, random);
+            if (!EXT || lv.mode == 0u) {
+                const LightRec l0 = sv.lights[0];
+                for (uint32_t s = 0; s < samples; ++s) {
+                    const vec2 random = rand2(uv + hammersley(s, samples));
+                    const uint32_t word = __ldg(bits + indexToLight(x, y, fm.w, fm.h, s));
+                    if (!(word & bit)) light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, l0, hitPos, n, v, NdotV, random);
+                }
+                light = light / (float)samples * (float)sv.info.lightCount;
+            } else {
+                // every light, in ascending order (the order of the sum is part of the result); the tile list leaves out only lights
+                // whose term is exactly zero for every pixel of the tile
+                uint32_t cnt = sv.info.lightCount;
+                const uint32_t* list = nullptr;
+                if (lv.mode == 2u) {
+                    const uint32_t tile = (y >> 4) * lv.tilesX + (x >> 4), c = __ldg(lv.tileCount + tile);
+                    if (c != LIGHT_TILE_ALL) { cnt = c; list = lv.tileList + (size_t)tile * LIGHTS_PER_TILE; }
+                }
+                for (uint32_t e = 0; e < cnt; ++e) {
+                    const uint32_t L = list ? __ldg(list + e) : e;
+                    const LightRec ll = sv.lights[L];
+                    for (uint32_t s = 0; s < samples; ++s) {
+                        const vec2 random = rand2(uv + hammersley(s, samples));
+                        const uint32_t word = __ldg(bits + indexToLight(x, y, fm.w, fm.h, L * samples + s));
+                        if (!(word & bit)) light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, ll, hitPos, n, v, NdotV, random);
+                    }
+                }
+                light = light / (float)samples;
             }
-            light = light / (float)samples * (float)sv.info.lightCount;
         }
         // imageStore to rgba16f (alpha 1 on a hit; the shipped DEBUG shader stores vec4(0) on a miss)
         lx = f2h_rn(light.x); ly = f2h_rn(light.y); lz = f2h_rn(light.z);
-        if (lighting && (isHit || !sv.releaseBuild)) lighting[px] = make_uint2(lx | (ly << 16), lz | ((isHit ? 0x3C00u : 0u) << 16));
+        uint32_t la = isHit ? 0x3C00u : 0u;
+        if (EXT && lv.historyAlpha > 0.0f) {   // temporal blend through the History texture (rgba16f), evaluated in binary32, stored in both
+            const uint2 hv = lv.history[px];
+            const float a = lv.historyAlpha, b = 1.0f - a;
+            lx = f2h_rn(h2f(hv.x & 0xFFFFu) * b + h2f(lx) * a); ly = f2h_rn(h2f(hv.x >> 16) * b + h2f(ly) * a);
+            lz = f2h_rn(h2f(hv.y & 0xFFFFu) * b + h2f(lz) * a); la = f2h_rn(h2f(hv.y >> 16) * b + h2f(la) * a);
+            lv.history[px] = make_uint2(lx | (ly << 16), lz | (la << 16));
+            if (lighting) lighting[px] = make_uint2(lx | (ly << 16), lz | (la << 16));
+        } else
+        if (lighting && (isHit || !sv.releaseBuild)) lighting[px] = make_uint2(lx | (ly << 16), lz | (la << 16));
         if (!DO_COMP) return;
     } else {
         const uint2 lv = __ldg(lighting + px);
@@ -819,12 +849,165 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
 }
 void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
                   const float4* dirT, const float4* uvN, const uint32_t* bits, uint2* lighting, float4* accum,
-                  uint32_t* rgba8, uint32_t* rgba8Tiled, cudaStream_t st) {
+                  uint32_t* rgba8, uint32_t* rgba8Tiled, cudaStream_t st, const LightsView* lights) {
     if (!fm.localSlots) return;
     const uint32_t g = (fm.localSlots + 255) / 256;
-    if (what == SHADE_LIGHTING) k_shade<true, false><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled);
-    else if (what == SHADE_COMPOSITE) k_shade<false, true><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled);
-    else k_shade<true, true><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled);
+    const bool ext = lights && (lights->mode != 0u || lights->historyAlpha > 0.0f);
+    const LightsView lv = lights ? *lights : LightsView{};
+    if (ext) {   // separate instantiations: the reference path keeps its registers
+        if (what == SHADE_LIGHTING) k_shade<true, false, true><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled, lv);
+        else if (what == SHADE_COMPOSITE) k_shade<false, true, false><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled, lv);
+        else k_shade<true, true, true><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled, lv);
+        return;
+    }
+    if (what == SHADE_LIGHTING) k_shade<true, false, false><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled, lv);
+    else if (what == SHADE_COMPOSITE) k_shade<false, true, false><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled, lv);
+    else k_shade<true, true, false><<<g, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, uvN, bits, lighting, accum, rgba8, rgba8Tiled, lv);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// every light (LightsView.mode != 0): tile light lists and shadow-ray generation.  No reference counterpart beyond the sketch in
+// "Raytracing optimization.md":1-14 and LIGHTS_PER_TILE (res/shaders/defines.glsl:6).
+// --------------------------------------------------------------------------------------------------------
+// Can light `l` add anything to a hit point at distance >= its radius?  getDirToLight (SH/light.glsl:107-126): brightness =
+// pow(smoothstep(r, 0, d), specularity) with r = rad - origin, d = max(dist - origin, 0); for dist >= rad the Hermite value is 0 and
+// 0^specularity = 0 when specularity > 0 — so a point light with rad > origin >= 0 and specularity > 0 is bounded by its radius.
+// Everything else (directional lights, specularity <= 0, degenerate radii) reaches every pixel.
+RTB_DI bool lightIsBounded(const LightRec& l, float& rad) {
+    if ((l.colorBType >> 16) != LIGHT_POINT) return false;
+    vec2 ro = unpackHalf2x16(l.radOrigin);
+    ro = mk2(fmaxf(ro.x, 0.0f), fmaxf(ro.y, 0.0f));
+    ro.y = fminf(ro.y, ro.x);
+    const float spec = ubits(l.dir[0]);
+    rad = ro.x;
+    return ro.x > ro.y && spec > 0.0f && isfinite(ro.x);
+}
+
+// one block per 16x16-pixel tile: the box of its hit points, then every light against it, in index order
+__global__ void __launch_bounds__(256) k_light_tiles(const FrameMap fm, const SceneView sv, const CameraRec cam, const float4* __restrict__ dirT,
+                                                     uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileList) {
+    __shared__ float sLo[3][8], sHi[3][8];
+    __shared__ uint32_t sWarpCount[8], sBase;
+    const uint32_t tilesX = (fm.w + 15u) >> 4;
+    const uint32_t tile = blockIdx.x, tx = tile % tilesX, ty = tile / tilesX;
+    const uint32_t x = tx * 16u + (threadIdx.x & 15u), y = ty * 16u + (threadIdx.x >> 4);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (x < fm.w && y < fm.h) {
+        const float4 dt = __ldg(dirT + (size_t)y * fm.w + x);
+        if (fbits(dt.w) != NO_RAY_HIT) {
+            const vec3 p = mk3(cam.eye) + mk3(dt.x, dt.y, dt.z);
+            lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z;
+        }
+    }
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o)); }
+        if (lane == 0) { sLo[a][warp] = lo[a]; sHi[a][warp] = hi[a]; }
+    }
+    if (threadIdx.x == 0) sBase = 0u;
+    __syncthreads();
+    for (int a = 0; a < 3; ++a) for (int w = 0; w < 8; ++w) { lo[a] = fminf(lo[a], sLo[a][w]); hi[a] = fmaxf(hi[a], sHi[a][w]); }
+    const bool anyHit = lo[0] <= hi[0];
+    if (!anyHit) { if (threadIdx.x == 0) tileCount[tile] = 0u; return; }   // (uniform: every thread holds the same box)
+    bool overflow = false;
+    for (uint32_t first = 0; first < sv.info.lightCount && !overflow; first += 256u) {
+        const uint32_t L = first + threadIdx.x;
+        bool reaches = false;
+        if (L < sv.info.lightCount) {
+            const LightRec l = sv.lights[L];
+            float rad;
+            if (!lightIsBounded(l, rad)) reaches = true;
+            else {   // squared distance from the light to the box against the radius, with slack for the rounding of both
+                float d2 = 0.0f;
+                for (int a = 0; a < 3; ++a) { const float c = l.pos[a], d = fmaxf(fmaxf(lo[a] - c, c - hi[a]), 0.0f); d2 += d * d; }
+                const float r = rad * 1.0001f + 1e-6f;
+                reaches = !(d2 > r * r);   // a NaN position stays in the list
+            }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, reaches);
+        if (lane == 0) sWarpCount[warp] = (uint32_t)__popc(m);
+        __syncthreads();
+        uint32_t before = sBase, total = sBase;
+        for (uint32_t w = 0; w < 8u; ++w) { if (w < warp) before += sWarpCount[w]; total += sWarpCount[w]; }
+        if (total > LIGHTS_PER_TILE) overflow = true;   // uniform
+        else if (reaches) tileList[(size_t)tile * LIGHTS_PER_TILE + before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = L;
+        __syncthreads();
+        if (threadIdx.x == 0) sBase = total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tileCount[tile] = overflow ? LIGHT_TILE_ALL : sBase;
+}
+void launch_light_tiles(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const float4* dirT, uint32_t* tileCount, uint32_t* tileList, cudaStream_t st) {
+    const uint32_t tiles = ((fm.w + 15u) >> 4) * ((fm.h + 15u) >> 4);
+    if (!tiles) return;
+    k_light_tiles<<<tiles, 256, 0, st>>>(fm, sv, *cam, dirT, tileCount, tileList);
+}
+
+// one thread per (sample, slot): the sample's random pair once (shadow.comp:84-95 — it does not depend on the light), then one
+// shadow ray per light of the launch's range, built as shadow.comp builds the one for light 0
+__global__ void __launch_bounds__(256) k_shadowgen_lights(const FrameMap fm, const SceneView sv, const CameraRec cam, const SeedRec* __restrict__ seed,
+                                                          uint32_t samples, const float4* __restrict__ dirT, uint32_t* __restrict__ bits,
+                                                          const RayQueue q, const LightsView lv) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t sample = j / fm.localSlots, i = j - sample * fm.localSlots;
+    uint32_t x = 0, y = 0, object = NO_RAY_HIT;
+    vec3 hitPos = mk3(0.0f, 0.0f, 0.0f);
+    vec2 random = mk2(0.0f, 0.0f);
+    if (sample < samples && slotToPixel(fm, i, x, y)) {
+        const float4 dt = __ldg(dirT + (size_t)y * fm.w + x);
+        object = fbits(dt.w);
+        if (object != NO_RAY_HIT) {
+            hitPos = mk3(cam.eye) + mk3(dt.x, dt.y, dt.z);
+            const vec2 loc = mk2((float)x, (float)y);
+            vec2 uv = (loc + rand2(loc + mk2(__ldg(&seed->randomX), __ldg(&seed->randomY)))) / 128.0f;
+            uv = uv + hammersley(sample, samples);
+            random = rand2(uv);
+        }
+    }
+    const bool isHit = object != NO_RAY_HIT;
+    // the lights this lane walks: the tile's list or every light, restricted to the launch's range
+    uint32_t cnt = isHit ? sv.info.lightCount : 0u;
+    const uint32_t* list = nullptr;
+    if (isHit && lv.mode == 2u) {
+        const uint32_t tile = (y >> 4) * lv.tilesX + (x >> 4), c = __ldg(lv.tileCount + tile);
+        if (c != LIGHT_TILE_ALL) { cnt = c; list = lv.tileList + (size_t)tile * LIGHTS_PER_TILE; }
+    }
+    for (uint32_t e = 0; __any_sync(0xFFFFFFFFu, e < cnt); ++e) {
+        float4 ro = make_float4(0.f, 0.f, 0.f, ubits(NO_RAY_HIT)), rd = make_float4(0.f, 0.f, 1.f, -1.0f);
+        uint32_t L = 0;
+        bool live = false;
+        if (e < cnt) {
+            L = list ? __ldg(list + e) : e;
+            if (L >= lv.lightBegin && L < lv.lightEnd) {
+                const LightRec light = sv.lights[L];
+                float brightness, dist;
+                const vec3 l = getDirToLight(light, hitPos, brightness, dist, random);
+                Ray ray; ray.pos = hitPos; ray.dir = -l;
+                float maxDist = -1.0f;
+                if (dist >= 0.0f) {
+                    const vec2 radOrigin = unpackHalf2x16(light.radOrigin);
+                    if (dist >= radOrigin.y && dist < radOrigin.x) maxDist = dist - radOrigin.y;
+                } else
+                    maxDist = NO_HIT;
+                if (maxDist != -1.0f) {
+                    if (occludedByOthers(sv, ray, maxDist, object))
+                        atomicOr(bits + indexToLight(x, y, fm.w, fm.h, L * samples + sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
+                    else if (maxDist > 0.0f) {
+                        ro = make_float4(ray.pos.x, ray.pos.y, ray.pos.z, ubits(object));
+                        rd = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, maxDist);
+                        live = true;
+                    }
+                }
+            }
+        }
+        queueAppend(q, live, ro, rd, (L * samples + sample) * fm.localSlots + i);
+    }
+}
+void launch_shadowgen_lights(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples, const float4* dirT,
+                             uint32_t* bits, const RayQueue& queue, const LightsView& lv, cudaStream_t st) {
+    const uint32_t n = fm.localSlots * samples;
+    if (!n) return;
+    k_shadowgen_lights<<<(n + 255) / 256, 256, 0, st>>>(fm, sv, *cam, seed, samples, dirT, bits, queue, lv);
 }
 
 // --------------------------------------------------------------------------------------------------------

@@ -83,11 +83,34 @@ void launch_clear_hit_strips(const FrameMap& fm, const float4* dirT, uint32_t sa
 // any-hit, one byte per ray (rays-in mode)
 void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n, uint8_t* occluded, uint32_t* workCounter,
                             cudaStream_t s, TraceCounters* counters = nullptr, const uint32_t* countPtr = nullptr);
+// ---- beyond the reference: every light evaluated, screen-tile light lists, temporal History blend ----
+// The reference samples lights[0] only and scales by lightCount (nv_all.shadow.comp:97, nv_all.lighting.comp:88,98).  With
+// LightsView.mode != 0 every light gets its own shadow ray per sample and its own Cook-Torrance term; the shadow mask then has
+// lightCount * samples layers, layer = light * samples + sample.  mode 2 walks, per 16x16-pixel screen tile, a list of the lights
+// that can reach a hit point of the tile (at most LIGHTS_PER_TILE = 32 entries, ascending; a tile with more keeps the full loop):
+// a light left out contributes exactly zero to every pixel of the tile, so the result is mode 1's bit for bit.
+constexpr uint32_t LIGHTS_PER_TILE = 32;          // ref: res/shaders/defines.glsl:6
+constexpr uint32_t LIGHT_TILE_ALL = 0xFFFFFFFFu;  // tile count value: walk every light
+struct LightsView {
+    uint32_t mode;                 // 0 reference (light 0 x lightCount), 1 all lights, 2 all lights through the tile lists
+    uint32_t tilesX;               // 16x16-pixel tiles per row
+    const uint32_t* tileCount;     // per tile: entries in its list, or LIGHT_TILE_ALL
+    const uint32_t* tileList;      // per tile: LIGHTS_PER_TILE light indices, ascending
+    uint32_t lightBegin, lightEnd; // shadow-ray generation only: the lights of this launch (the queue is filled in chunks of lights)
+    float historyAlpha;            // > 0: lighting = history * (1 - a) + lighting * a through `history` (rgba16f), stored in both
+    uint2* history;
+};
+void launch_light_tiles(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const float4* dirT, uint32_t* tileCount, uint32_t* tileList, cudaStream_t s);
+// shadow rays of every light in [lv.lightBegin, lv.lightEnd) for every hit pixel and sample, appended to `queue`
+// (slot id = layer * localSlots + slot); occluders other than triangles are answered here
+void launch_shadowgen_lights(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples, const float4* dirT,
+                             uint32_t* bits, const RayQueue& queue, const LightsView& lv, cudaStream_t s);
+
 // lighting.comp + composite.comp
 enum { SHADE_LIGHTING = 1, SHADE_COMPOSITE = 2, SHADE_BOTH = 3 };
 void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
                   const float4* dirT, const float4* uvN, const uint32_t* bits, uint2* lighting, float4* accum,
-                  uint32_t* rgba8, uint32_t* rgba8Tiled, cudaStream_t s);
+                  uint32_t* rgba8, uint32_t* rgba8Tiled, cudaStream_t s, const LightsView* lights = nullptr);
 // rays-in helpers
 void launch_finish_rays(const SceneView& sv, const RayRec* rays, const TriHit* hits, uint32_t n, uint32_t* object, float* t,
                         float2* uv, cudaStream_t s);

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("RTB_LIB", os.path.join(HERE, "librtb200.so"))   # RTB
 PASS_INIT, PASS_RAYGEN, PASS_SHADOW, PASS_LIGHTING, PASS_COMPOSITE, PASS_FRAME = range(6)
 TGT_DIR_T, TGT_UV_NORMAL, TGT_SHADOW_BITS, TGT_LIGHTING, TGT_ACCUM, TGT_RGBA8, TGT_SEED, TGT_RGBA8_TILED, TGT_ACCEL_NODES, TGT_ACCEL_TRIANGLES = range(10)
 ACCEL_BRUTE, ACCEL_BVH, ACCEL_BVH2 = 0, 1, 2
-OPT_COUNTERS, OPT_TILE_RANK, OPT_TILE_COUNT, OPT_SHADER_BUILD, OPT_PRIMARY_PACKETS, OPT_FUSE_PRIMARY, OPT_SHADOW_ORDER, OPT_ACCEL_BUILDER, OPT_FRAME_LANES, OPT_FRAME_GRAPH = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+OPT_COUNTERS, OPT_TILE_RANK, OPT_TILE_COUNT, OPT_SHADER_BUILD, OPT_PRIMARY_PACKETS, OPT_FUSE_PRIMARY, OPT_SHADOW_ORDER, OPT_ACCEL_BUILDER, OPT_FRAME_LANES, OPT_FRAME_GRAPH, OPT_LIGHTS, OPT_HISTORY_ALPHA = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 BUILDER_HOST, BUILDER_DEVICE = 0, 1
 SHADER_DEBUG, SHADER_RELEASE = 0, 1
 NO_RAY_HIT = 0xFFFFFFFF
@@ -262,6 +262,9 @@ class Context:
             raise RtbError(f"rtb error {rc}: {self.L.rtb_last_error(self.h).decode()}")
 
     def set_option(self, opt, value): self._ck(self.L.rtb_set_option(self.h, opt, value))
+    def set_history_alpha(self, alpha):
+        self.set_option(OPT_HISTORY_ALPHA, int(np.array([alpha], np.float32).view(np.uint32)[0]))
+
     def set_stream(self, stream_ptr): self._ck(self.L.rtb_set_stream(self.h, C.c_void_p(stream_ptr)))
 
     def resize(self, w, h, samples=1):
@@ -315,7 +318,7 @@ class Context:
     def readback(self, target):
         w, h, s = self.width, self.height, self.samples
         shape, dt = {TGT_DIR_T: ((h, w, 4), np.float32), TGT_UV_NORMAL: ((h, w, 4), np.float32),
-                     TGT_SHADOW_BITS: ((shadow_words(w, h, s),), np.uint32), TGT_LIGHTING: ((h, w, 4), np.uint16),
+                     TGT_SHADOW_BITS: ((self.device_ptr(TGT_SHADOW_BITS)[1] // 4 if target == TGT_SHADOW_BITS else 0,), np.uint32), TGT_LIGHTING: ((h, w, 4), np.uint16),
                      TGT_ACCUM: ((h, w, 4), np.float32), TGT_RGBA8: ((h, w), np.uint32), TGT_SEED: ((24,), np.uint8),
                      TGT_RGBA8_TILED: ((self.device_ptr(TGT_RGBA8_TILED)[1] // 4 if target == TGT_RGBA8_TILED else 0,), np.uint32)}[target]
         out = np.zeros(shape, dt)

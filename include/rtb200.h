@@ -71,7 +71,7 @@ typedef enum rtb_pass {
 typedef enum rtb_target {
     RTB_TGT_DIR_T = 0,        /* rgba32f  w*h*16 B   ref: src/rt/task/raygen_task.cpp:18-20 */
     RTB_TGT_UV_NORMAL = 1,    /* rgba32f  w*h*16 B */
-    RTB_TGT_SHADOW_BITS = 2,  /* u32[ceil(w/16)*ceil(h/2)*samples]  ref: src/rt/task/shadow_task.cpp:146-165 */
+    RTB_TGT_SHADOW_BITS = 2,  /* u32[ceil(w/16)*ceil(h/2)*samples]  ref: src/rt/task/shadow_task.cpp:146-165 (x lightCount with RTB_OPT_LIGHTS) */
     RTB_TGT_LIGHTING = 3,     /* rgba16f  w*h*8 B    ref: src/rt/task/shadow_task.cpp:20-22 */
     RTB_TGT_ACCUM = 4,        /* rgba32f  w*h*16 B   ref: src/rt/task/composite_task.cpp:20-22 */
     RTB_TGT_RGBA8 = 5,        /* rgba8    w*h*4 B    (what presentToCpu copies out) */
@@ -147,6 +147,19 @@ typedef enum rtb_option {
                                       scene_graph.cpp:343-376,378-522) need not stall the frame; same hits, somewhat higher SAH
                                       cost.  Falls back to the host builder for fewer than 2 triangles or a tree too deep for
                                       the traversal stack. */
+    RTB_OPT_LIGHTS = 10,           /* BEYOND THE REFERENCE, which samples lights[0] only and scales by lightCount (ref: res/shaders/
+                                      nv_all.shadow.comp:97, nv_all.lighting.comp:88,98).  0 (default) = that.
+                                      1 = every light gets its own shadow ray per sample and its own Cook-Torrance term; the shadow
+                                      mask then has lightCount * samples layers (layer = light * samples + sample) and the sum is
+                                      not scaled.  2 = the same result through per-tile light lists: for every 16x16-pixel screen
+                                      tile the lights that can reach one of its hit points (at most LIGHTS_PER_TILE = 32 — ref:
+                                      res/shaders/defines.glsl:6, "Raytracing optimization.md":1-14; a tile with more keeps the
+                                      full loop), so that shadow-ray set-up and lighting walk 32 lights instead of thousands. */
+    RTB_OPT_HISTORY_ALPHA = 11,    /* BEYOND THE REFERENCE: the bits of a float a in [0,1].  a > 0: the lighting texture is blended
+                                      over frames through the History texture the reference allocates but never uses (ref: src/rt/
+                                      task/shadow_task.cpp:20-22,212 "Do denoising"): history = history * (1 - a) + lighting * a,
+                                      stored in both; composite reads the blend.  The first frame after rtb_resize or an option
+                                      change starts the history (a = 1).  0 (default) = off. */
     RTB_OPT_FRAME_GRAPH = 9,       /* 1 (default): RTB_PASS_FRAME is recorded into two CUDA graphs (everything before the shade launch /
                                       the shade launch) the second time it is dispatched with nothing changed, and replayed from
                                       then on — what the reference does with its CommandList (recorded once, replayed per frame

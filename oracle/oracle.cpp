@@ -105,6 +105,12 @@ inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline float ubits(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 int g_mode = 0;   // ORC_MODE_DEBUG / ORC_MODE_RELEASE (D10)
+// Beyond the reference (the reference hard-codes lightId = 0 and multiplies by lightCount):
+//   g_all_lights   every light gets its own shadow ray and its own Cook-Torrance term; layer = light * samples + sample
+//   g_history      temporal blend of the lighting texture through the History texture the reference allocates but never
+//                  uses (src/rt/task/shadow_task.cpp:20-22,212 "Do denoising"): history = history * (1 - a) + lighting * a
+int g_all_lights = 0;
+float g_history_alpha = 0.0f;   // 0 = off
 
 const float noHit = 3.4028235e38f;          // SH/primitive.glsl:6
 const uint32_t noRayHit = 0xFFFFFFFFu;      // SH/primitive.glsl:7
@@ -725,14 +731,14 @@ void raygenPixel(const Scene& sc, const CameraRec& cam, const SeedRec& seed, uin
 
 // SH/nv_all.shadow.comp:50-143, one (pixel, sample); returns the lane's `hit`
 bool shadowPixel(const Scene& sc, const CameraRec& cam, const SeedRec& seed, uint32_t samples, uint32_t x, uint32_t y,
-                 uint32_t i, const float dirT[4], float* rayOut) {
+                 uint32_t i, const float dirT[4], float* rayOut, uint32_t lightId = 0) {
     uint32_t object = fbits(dirT[3]);
     vec3 hitPos = v3(cam.eye) + vec3{dirT[0], dirT[1], dirT[2]};
     vec2 loc = {(float)x, (float)y};
     vec2 uv = (loc + rand2(loc + vec2{seed.randomX, seed.randomY})) / 128.0f;
     uv = uv + hammersley(i, samples);
     vec2 random = rand2(uv);
-    const LightRec& light = sc.light[0];   // lightId = 0, nv_all.shadow.comp:97
+    const LightRec& light = sc.light[lightId];   // lightId = 0 in the reference, nv_all.shadow.comp:97
     float brightness, dist;
     vec3 l = getDirToLight(light, hitPos, brightness, dist, random);
     Ray ray = {hitPos, -l};
@@ -765,15 +771,18 @@ bool lightingPixel(const Scene& sc, const CameraRec& cam, uint32_t samples, uint
     vec3 light = {0, 0, 0};
     vec2 loc = {(float)x, (float)y};
     vec2 uv = (loc + rand2(loc + vec2{0.0f, 0.0f})) / 128.0f;   // D8: unbound seed reads as zero
-    for (uint32_t i = 0; i < samples; ++i) {
-        vec2 uvi = uv + hammersley(i, samples);
-        vec2 random = rand2(uvi);
-        uint32_t word = bits[indexToLightNV(x, y, w, h, i)];
-        uint32_t bit = (x & 15u) | ((y & 1u) << 4);
-        if (!(word & (1u << bit)))
-            light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, sc.light[0], hitPos, n, v, NdotV, random);
-    }
-    out = light / (float)samples * (float)sc.lightCount;
+    const uint32_t nl = g_all_lights ? sc.lightCount : 1u;
+    for (uint32_t L = 0; L < nl; ++L)
+        for (uint32_t i = 0; i < samples; ++i) {
+            vec2 uvi = uv + hammersley(i, samples);
+            vec2 random = rand2(uvi);
+            uint32_t word = bits[indexToLightNV(x, y, w, h, L * samples + i)];
+            uint32_t bit = (x & 15u) | ((y & 1u) << 4);
+            if (!(word & (1u << bit)))
+                light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, sc.light[L], hitPos, n, v, NdotV, random);
+        }
+    // the reference samples light 0 only and scales by the light count (nv_all.lighting.comp:98); with every light evaluated the sum stands
+    out = g_all_lights ? light / (float)samples : light / (float)samples * (float)sc.lightCount;
     return true;
 }
 
@@ -854,6 +863,18 @@ void parallelFor(int64_t n, int64_t chunk, F&& body) {
 extern "C" {
 
 void orc_set_threads(int n) { g_threads = n; }
+void orc_set_all_lights(int on) { g_all_lights = on ? 1 : 0; }
+void orc_set_history(float alpha) { g_history_alpha = alpha; }
+// the History blend (ours): history and lighting are rgba16f; the blend is evaluated in binary32 and stored round-to-nearest-even;
+// alpha of the first frame of a sequence is 1 (history = lighting), which the caller expresses by passing first != 0
+void orc_history_blend(uint16_t* history_f16, uint16_t* lighting_f16, uint64_t texels, int first) {
+    const float a = first ? 1.0f : g_history_alpha;
+    for (uint64_t i = 0; i < texels * 4; ++i) {
+        const float hv = f16_to_f32(history_f16[i]), lv = f16_to_f32(lighting_f16[i]);
+        const uint16_t o = f32_to_f16_rtne(hv * (1.0f - a) + lv * a);
+        history_f16[i] = o; lighting_f16[i] = o;   // composite reads the blended texture
+    }
+}
 void orc_set_mode(int mode) { g_mode = mode == ORC_MODE_RELEASE ? ORC_MODE_RELEASE : ORC_MODE_DEBUG; }
 int orc_get_mode(void) { return g_mode; }
 int orc_get_threads(void) { return threadCount(); }
@@ -1190,8 +1211,11 @@ void orc_shadow(const orc_scene* s, const void* cam144, const void* seed24, uint
     const int64_t stripsY = (H + 1) / 2, stripsX = (W + 15) / 16;
     // one "warp" = one 16x2 strip of one sample (nv_all.shadow.comp:40-48); the ballot early-out at :69-82
     // leaves the word zero, and lanes whose own pixel missed contribute hit = false.
-    parallelFor((int64_t)samples * stripsY, 2, [&](int64_t job) {
-        const int64_t i = job / stripsY, sy = job % stripsY;
+    const uint32_t layers = g_all_lights ? samples * sc.lightCount : samples;
+    parallelFor((int64_t)layers * stripsY, 2, [&](int64_t job) {
+        const int64_t layer = job / stripsY, sy = job % stripsY;
+        const int64_t i = layer % samples;
+        const uint32_t lightId = (uint32_t)(layer / samples);
         {
             for (int64_t sx = 0; sx < stripsX; ++sx) {
                 uint32_t word = 0;
@@ -1205,11 +1229,11 @@ void orc_shadow(const orc_scene* s, const void* cam144, const void* seed24, uint
                         uint32_t x = (uint32_t)sx * 16 + (l & 15), y = (uint32_t)sy * 2 + (l >> 4);
                         if (x >= W || y >= H) continue;
                         size_t px = (size_t)y * W + x;
-                        float* ro = shadow_rays_out ? shadow_rays_out + 6 * ((size_t)i * W * H + px) : nullptr;
-                        if (shadowPixel(sc, cam, seed, samples, x, y, (uint32_t)i, dirT + 4 * px, ro)) word |= 1u << l;
+                        float* ro = shadow_rays_out ? shadow_rays_out + 6 * ((size_t)layer * W * H + px) : nullptr;
+                        if (shadowPixel(sc, cam, seed, samples, x, y, (uint32_t)i, dirT + 4 * px, ro, lightId)) word |= 1u << l;
                     }
                 // nv_all.shadow.comp:69-82: a subgroup without hits leaves early; only DEBUG builds store the zero word (D10)
-                if (any || g_mode == ORC_MODE_DEBUG) bits[indexToLightNV((uint32_t)sx * 16, (uint32_t)sy * 2, W, H, (uint32_t)i)] = word;
+                if (any || g_mode == ORC_MODE_DEBUG) bits[indexToLightNV((uint32_t)sx * 16, (uint32_t)sy * 2, W, H, (uint32_t)layer)] = word;
             }
         }
     });
@@ -1256,7 +1280,7 @@ void orc_frame(const orc_scene* s, const void* cam144, void* seed24, uint32_t sa
     std::vector<float> dT, uN; std::vector<uint32_t> b; std::vector<uint16_t> lf;
     if (!dirT) { dT.resize(4 * px); dirT = dT.data(); }
     if (!uvN) { uN.resize(4 * px); uvN = uN.data(); }
-    if (!bits) { b.resize(shadowWords(cam.width, cam.height, samples)); bits = b.data(); }
+    if (!bits) { b.resize(shadowWords(cam.width, cam.height, samples * (g_all_lights ? s->info[0] : 1u))); bits = b.data(); }
     if (!lighting_f16) { lf.resize(4 * px); lighting_f16 = lf.data(); }
     orc_init_pass(seed24);
     orc_raygen(s, cam144, seed24, dirT, uvN, nullptr, nullptr);

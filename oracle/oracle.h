@@ -52,6 +52,11 @@ enum {
 
 enum { ORC_MODE_DEBUG = 0, ORC_MODE_RELEASE = 1 };   /* which build of the shaders is modelled (oracle.cpp D10) */
 void orc_set_mode(int mode);
+/* Beyond the reference (definitions in oracle.cpp next to g_all_lights): every light evaluated instead of
+   light 0 x lightCount (shadow layers = light * samples + sample), and the temporal History blend of the lighting texture */
+void orc_set_all_lights(int on);
+void orc_set_history(float alpha);
+void orc_history_blend(uint16_t* history_f16, uint16_t* lighting_f16, uint64_t texels, int first);
 int  orc_get_mode(void);
 void orc_set_threads(int n);
 int  orc_get_threads(void);

@@ -154,6 +154,18 @@ class Oracle:
     def mode(self):
         return int(self.lib.orc_get_mode())
 
+    def set_all_lights(self, on):
+        """every light evaluated (layer = light * samples + sample) instead of the reference's light 0 x lightCount"""
+        self.lib.orc_set_all_lights(C.c_int(1 if on else 0))
+        self.all_lights = bool(on)
+
+    def set_history(self, alpha):
+        self.lib.orc_set_history(C.c_float(alpha))
+
+    def history_blend(self, history, lighting, first):
+        self.lib.orc_history_blend.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        self.lib.orc_history_blend(_ptr(history), _ptr(lighting), history.size // 4, 1 if first else 0)
+
     # ---- packing -------------------------------------------------------------------------------
     def f16_trunc(self, v):
         return int(self.lib.orc_f16_trunc(np.float32(v)))
@@ -291,10 +303,13 @@ class Oracle:
         self.lib.orc_occlusion_rays(C.byref(cs), _ptr(rays), n, _ptr(md), _ptr(prev), _ptr(occ))
         return occ
 
+    def _layers(self, scene, samples):
+        return samples * (int(scene.info[0]) if getattr(self, "all_lights", False) else 1)
+
     def shadow(self, scene, cam, seed, samples, dirT, want_rays=False):
         w, h = self._wh(cam)
-        bits = np.zeros(shadow_words(w, h, samples), np.uint32)
-        rays = np.zeros((samples, h, w, 6), np.float32) if want_rays else None
+        bits = np.zeros(shadow_words(w, h, self._layers(scene, samples)), np.uint32)
+        rays = np.zeros((self._layers(scene, samples), h, w, 6), np.float32) if want_rays else None
         cs = scene.c()
         self.lib.orc_shadow(C.byref(cs), _ptr(cam), _ptr(seed), samples, _ptr(dirT), _ptr(bits), _ptr(rays))
         return (bits, rays) if want_rays else bits
@@ -319,7 +334,7 @@ class Oracle:
         w, h = self._wh(cam)
         pre = prefill or {}
         out = dict(dirT=pre.get("dirT", np.zeros((h, w, 4), np.float32)).copy(), uvN=pre.get("uvN", np.zeros((h, w, 4), np.float32)).copy(),
-                   bits=pre.get("bits", np.zeros(shadow_words(w, h, samples), np.uint32)).copy(),
+                   bits=pre.get("bits", np.zeros(shadow_words(w, h, self._layers(scene, samples)), np.uint32)).copy(),
                    lighting=pre.get("lighting", np.zeros((h, w, 4), np.uint16)).copy(), rgba8=np.zeros((h, w), np.uint32))
         cs = scene.c()
         self.lib.orc_frame(C.byref(cs), _ptr(cam), _ptr(seed), samples, _ptr(out["dirT"]), _ptr(out["uvN"]),
