@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.environ.get("RTB_LIB_OUT", os.path.join(HERE, "librtb200.so"))   # RTB_LIB_OUT / RTB_NVCC_EXTRA: tuning variants
 SOURCES = ["rtb_api.cu", "rtb_kernels.cu", "rtb_refit.cu", "rtb_sort.cu", "rtb_build.cu", "rtb_probe.cu", "rtb_bvh.cpp", "rtb_host.cpp"]
-HEADERS = ["rtb_types.h", "rtb_math.cuh", "rtb_crmath.h", "rtb_kernels.cuh", "rtb_trace8.cuh", "rtb_trace8p.cuh", "rtb_trace8f.cuh", "rtb_trace8b.cuh", "rtb_path.cuh", "rtb_node8_encode.h", "rtb_bvh.h",
+HEADERS = ["rtb_types.h", "rtb_math.cuh", "rtb_crmath.h", "rtb_kernels.cuh", "rtb_trace8.cuh", "rtb_trace8p.cuh", "rtb_trace8f.cuh", "rtb_trace8b.cuh", "rtb_trace8s.cuh", "rtb_path.cuh", "rtb_node8_encode.h", "rtb_bvh.h",
            os.path.join(ROOT, "include", "rtb200.h"), os.path.join(ROOT, "include", "igx_rt.hpp")]
 
 NVCC_FLAGS = [

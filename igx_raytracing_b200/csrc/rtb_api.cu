@@ -77,6 +77,14 @@ struct rtb_ctx {
     FrameMap laneFm[2]{};             // the two half-frame maps: lane h of rank r is virtual rank h * n + r of 2 n
     cudaStream_t laneStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
     uint32_t lanesOpt = 1;            // RTB_OPT_FRAME_LANES
+    // spheres / cubes through their own trees (rtb_trace8s.cuh), built on the device when a type has at least primTreeMin primitives
+    struct PrimTreeBufs {
+        DevBuf<TriangleRec> proxies; DevBuf<Node8> nodes; DevBuf<TravTri> tt; DevBuf<float> nodeBox; DevBuf<uint32_t> maxBits; DevBuf<double> areaSums;
+        std::vector<uint32_t> levelFirst; uint32_t nodeCount = 0, count = 0; bool valid = false, dirty = true;
+        void release() { proxies.release(); nodes.release(); tt.release(); nodeBox.release(); maxBits.release(); areaSums.release(); }
+    } primTree[2];                    // 0 spheres, 1 cubes
+    uint32_t primTreeMin = 64;        // RTB_OPT_PRIMITIVE_TREES: 0 = never
+    DevBuf<PrimHit> primHitS[2], primHitC[2], rinPrimS, rinPrimC;   // winners per wavefront slot (per lane) / per rays-in ray
     // beyond the reference: every light evaluated, tile light lists, History blend (LightsView in rtb_kernels.cuh)
     uint32_t lightsOpt = 0;           // RTB_OPT_LIGHTS: 0 reference (light 0 x lightCount), 1 all lights, 2 all lights through tile lists
     float historyAlpha = 0.0f;        // RTB_OPT_HISTORY_ALPHA (float bits): 0 = off
@@ -133,6 +141,7 @@ SceneView sceneView(const rtb_ctx* c) {
     v.info = c->info;
     v.nodes = c->nodes.p; v.nodes8 = c->nodes8.p; v.travTris = c->travTris.p; v.nodeCount = c->nodeCount;
     v.releaseBuild = c->releaseBuild;
+    v.sphereTree = c->primTree[0].valid ? 1u : 0u; v.cubeTree = c->primTree[1].valid ? 1u : 0u;
     v.useBvh = !c->accelValid ? ACCEL_KIND_BRUTE : (c->accelMode == RTB_ACCEL_BVH ? ACCEL_KIND_CWBVH : (c->accelMode == RTB_ACCEL_BVH2 ? ACCEL_KIND_BVH2 : ACCEL_KIND_BRUTE));
     return v;
 }
@@ -234,6 +243,32 @@ int primaryPackets(const rtb_ctx* c) {
     return patch < PACKET_RATIO * c->stats.leafNodeExtent ? PACKETS_FRUSTUM : PACKETS_OFF;
 }
 
+// Spheres / cubes get a tree of their own when there are many (RTB_OPT_PRIMITIVE_TREES) and the triangles are not searched by the
+// reference's loop (RTB_ACCEL_BRUTE keeps every loop verbatim).  Built on the device over proxy triangles (rtb_trace8s.cuh) by the
+// builder and refit kernels the triangle tree uses; rebuilt when the type's buffer or count changed.  Synchronises when it builds.
+int ensurePrimTrees(rtb_ctx* c) {
+    for (int kind = 0; kind < 2; ++kind) {
+        rtb_ctx::PrimTreeBufs& T = c->primTree[kind];
+        const uint32_t n = kind == 0 ? c->info.sphereCount : c->info.cubeCount;
+        const bool want = c->primTreeMin && n >= std::max(c->primTreeMin, 2u) && c->accelMode != RTB_ACCEL_BRUTE && (c->accelValid || !c->info.triangleCount);
+        if (!want) { if (T.valid) { T.valid = false; ++c->stamp; } continue; }
+        if (T.valid && !T.dirty && T.count == n) continue;
+        const uint32_t cap = n + 64;
+        RTB_CUDA(c, T.proxies.alloc(n)); RTB_CUDA(c, T.nodes.alloc(cap)); RTB_CUDA(c, T.tt.alloc(n)); RTB_CUDA(c, T.nodeBox.alloc((size_t)cap * 6));
+        RTB_CUDA(c, T.maxBits.alloc(1)); RTB_CUDA(c, T.areaSums.alloc(2));
+        launch_proxy_triangles(kind, c->spheres.p, c->cubes.p, n, T.proxies.p, c->stream);
+        bool tooDeep = false;
+        uint32_t nodeCount = 0, leafSlots = 0; float leafExtent = 0.0f;
+        const cudaError_t e = device_build_cwbvh(T.proxies.p, n, T.nodes.p, cap, T.tt.p, T.nodeBox.p, T.maxBits.p, T.areaSums.p, 20, 1, T.levelFirst, nodeCount,
+                                                 leafSlots, leafExtent, &tooDeep, c->stream);
+        if (e != cudaSuccess) return cudaFail(c, e, "device_build_cwbvh (spheres / cubes)");
+        T.valid = !tooDeep; T.dirty = false; T.count = n; T.nodeCount = nodeCount;   // too deep (thousands of coincident primitives): the loops stay
+        ++c->stamp;
+    }
+    return RTB_OK;
+}
+PrimTree primTreeOf(const rtb_ctx* c, int kind) { return PrimTree{c->primTree[kind].nodes.p, c->primTree[kind].tt.p, c->primTree[kind].nodeCount}; }
+
 // `mark` (single-lane frame dispatch only) records an event after each phase so the traversal launches can be timed alone.
 // lane < 0: the whole frame on the context's stream; lane 0 / 1: that half-frame lane (lane 1 on its own stream).
 struct LaneRef { const FrameMap& fm; rtb_ctx::LaneBufs& b; cudaStream_t st; };
@@ -247,7 +282,8 @@ int passRaygen(rtb_ctx* c, bool mark, int lane = -1) {
     const LaneRef L = laneOf(c, lane);
     const SceneView sv = sceneView(c);
     if (lane <= 0) c->lastPrimaryPackets = primaryPackets(c);
-    if (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt) {
+    const bool trees = sv.sphereTree || sv.cubeTree;
+    if (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt && !trees) {
         // one launch: rays generated in registers, traced, G-buffer written (the phase events collapse onto the trace phase)
         if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], L.st));
         launch_primary_fused(L.fm, sv, &c->camera, c->seed.p, c->dirT.p, c->uvN.p, L.b.workCounter.p, L.st);
@@ -258,7 +294,19 @@ int passRaygen(rtb_ctx* c, bool mark, int lane = -1) {
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], L.st));
     launch_trace_closest(sv, L.b.rays.p, L.fm.localSlots, L.b.hits.p, L.b.workCounter.p, c->countersOn ? c->counters.p : nullptr, c->lastPrimaryPackets, L.st);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], L.st));
-    launch_finish_primary(L.fm, sv, L.b.rays.p, L.b.hits.p, c->dirT.p, c->uvN.p, L.st);
+    const int li = lane == 1 ? 1 : 0;
+    const PrimHit *ws = nullptr, *wc = nullptr;
+    if (sv.sphereTree) {
+        RTB_CUDA(c, c->primHitS[li].alloc(L.fm.localSlots));
+        launch_prims_closest(0, sv, primTreeOf(c, 0), L.b.rays.p, L.fm.localSlots, nullptr, L.b.hits.p, nullptr, c->primHitS[li].p, L.st);
+        ws = c->primHitS[li].p;
+    }
+    if (sv.cubeTree) {
+        RTB_CUDA(c, c->primHitC[li].alloc(L.fm.localSlots));
+        launch_prims_closest(1, sv, primTreeOf(c, 1), L.b.rays.p, L.fm.localSlots, nullptr, L.b.hits.p, ws, c->primHitC[li].p, L.st);
+        wc = c->primHitC[li].p;
+    }
+    launch_finish_primary(L.fm, sv, L.b.rays.p, L.b.hits.p, c->dirT.p, c->uvN.p, L.st, ws, wc);
     if (c->countersOn) launch_count_hits(L.fm, c->dirT.p, c->counters.p, L.st);
     return RTB_OK;
 }
@@ -342,6 +390,12 @@ int clearShadowBits(rtb_ctx* c) {
     return RTB_OK;
 }
 
+// occlusion by spheres / cubes that have a tree of their own: the same rays, after the triangles' any-hit launch
+void shadowPrimPasses(rtb_ctx* c, const SceneView& sv, const FrameMap& fm, const RayRec* rays, uint32_t n, const uint32_t* countPtr, const uint32_t* slotIds, cudaStream_t st) {
+    if (sv.sphereTree) launch_prims_any(0, sv, primTreeOf(c, 0), rays, n, countPtr, nullptr, c->bits.p, slotIds, fm, st);
+    if (sv.cubeTree) launch_prims_any(1, sv, primTreeOf(c, 1), rays, n, countPtr, nullptr, c->bits.p, slotIds, fm, st);
+}
+
 int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
     // (the RELEASE build's clear reads the G-buffer, so with lanes it runs after both lanes' nearest-hit launches: see the frame dispatch)
     if (lane < 0) { const int rc = clearShadowBits(c); if (rc) return rc; }
@@ -372,6 +426,7 @@ int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
             RTB_CUDA(c, cudaMemsetAsync(B.queueCount.p, 0, 4, L.st));
             launch_shadowgen_lights(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->bits.p, q, lv, L.st);
             launch_trace_any_bits(L.fm, sv, q.rays, capacity, c->bits.p, B.workCounter.p, counters, q.slotIds, q.count, L.st);
+            shadowPrimPasses(c, sv, L.fm, q.rays, capacity, q.count, q.slotIds, L.st);
         }
         return RTB_OK;
     }
@@ -381,6 +436,7 @@ int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
         launch_shadowgen(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, B.rays.p, c->bits.p, nullptr, nullptr, L.st);
         if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], L.st));
         launch_trace_any_bits(L.fm, sv, B.rays.p, maxRays, c->bits.p, B.workCounter.p, counters, nullptr, nullptr, L.st);
+        shadowPrimPasses(c, sv, L.fm, B.rays.p, maxRays, nullptr, nullptr, L.st);
         return RTB_OK;
     }
     // queue of live rays, optionally sorted in light space
@@ -408,6 +464,7 @@ int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
         launch_trace_beam_bits(L.fm, sv, B.rays.p, maxRays, c->bits.p, B.workCounter.p, counters, slots, B.queueCount.p, fb, L.st);
     } else
         launch_trace_any_bits(L.fm, sv, B.rays.p, maxRays, c->bits.p, B.workCounter.p, counters, slots, B.queueCount.p, L.st);
+    shadowPrimPasses(c, sv, L.fm, B.rays.p, maxRays, B.queueCount.p, slots, L.st);
     return RTB_OK;
 }
 int passShade(rtb_ctx* c, int what, int lane = -1) {
@@ -554,6 +611,8 @@ void rtb_destroy(rtb_ctx* c) {
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->lane[0].release(); c->lane[1].release(); c->counters.release();
     c->lightTileCount.release(); c->lightTileList.release(); c->history.release();
+    for (int k = 0; k < 2; ++k) { c->primTree[k].release(); c->primHitS[k].release(); c->primHitC[k].release(); }
+    c->rinPrimS.release(); c->rinPrimC.release();
     if (c->graphA) cudaGraphExecDestroy(c->graphA);
     if (c->graphB) cudaGraphExecDestroy(c->graphB);
     if (c->laneStream) cudaStreamDestroy(c->laneStream);
@@ -596,6 +655,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             }
             return RTB_OK;
         }
+        case RTB_OPT_PRIMITIVE_TREES: c->primTreeMin = value; return RTB_OK;
         case RTB_OPT_LIGHTS:
             if (value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_LIGHTS: 0 reference (light 0 x lightCount), 1 all lights, 2 all lights through tile lists");
             c->lightsOpt = value; c->historyValid = false; return RTB_OK;
@@ -686,6 +746,8 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
     if (off > cap || bytes > cap - off) return fail(c, RTB_ERR_CAPACITY, "rtb_upload: range exceeds the capacity given to rtb_create");
     if (!bytes) return RTB_OK;
     if (id == RTB_BUF_TRIANGLES) { std::memcpy(c->triangleMirror.data() + off, src, bytes); c->accelValid = false; ++c->stamp; }
+    if (id == RTB_BUF_SPHERES) c->primTree[0].dirty = true;
+    if (id == RTB_BUF_CUBES) c->primTree[1].dirty = true;
     if (id == RTB_BUF_LIGHTS && off < sizeof(LightRec)) ++c->stamp;   // lights[0] picks the occlusion rays' sort key
     if (id == RTB_BUF_LIGHTS && off < sizeof(LightRec)) std::memcpy(reinterpret_cast<uint8_t*>(&c->light0) + off, src, std::min(bytes, sizeof(LightRec) - off));
     // pageable source: cudaMemcpyAsync stages it before returning, so the caller may reuse src at once (like GPUBuffer::flush)
@@ -804,6 +866,7 @@ int rtb_accel_info_get(const rtb_ctx* c, rtb_accel_info* out) {
     out->mode = c->accelMode; out->node_count = c->nodeCount; out->node_bytes = c->accelMode == RTB_ACCEL_BVH ? sizeof(Node8) : sizeof(BvhNode); out->leaf_count = c->stats.leafCount;
     out->max_depth = c->stats.maxDepth; out->tri_record_bytes = sizeof(TravTri); out->sah_cost = c->stats.sahCost; out->build_ms = c->stats.buildMs;
     out->leaf_node_extent = c->stats.leafNodeExtent; out->refits = c->refits; out->primary_packets = (uint32_t)c->lastPrimaryPackets; out->builder = c->builtBy;
+    out->sphere_tree_nodes = c->primTree[0].valid ? c->primTree[0].nodeCount : 0u; out->cube_tree_nodes = c->primTree[1].valid ? c->primTree[1].nodeCount : 0u;
     return RTB_OK;
 }
 
@@ -811,6 +874,7 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
     if (pass != RTB_PASS_INIT) { const int rc = checkReady(c); if (rc) return rc; }
+    if (pass != RTB_PASS_INIT) { const int rc = ensurePrimTrees(c); if (rc) return rc; }
     int rc = RTB_OK;
     switch (pass) {
         case RTB_PASS_INIT: if ((rc = waitCopy(c, {RTB_TGT_SEED}))) return rc; launch_init(c->seed.p, c->stream); break;
@@ -1005,7 +1069,9 @@ int rtb_path_frame(rtb_ctx* c, uint32_t bounces) {
     }
     cudaEvent_t* ev = c->pathEv.data();
     cudaEvent_t evBegin = ev[4 * (PATH_MAX_BOUNCES + 1)], evEnd = ev[4 * (PATH_MAX_BOUNCES + 1) + 1];
-    const SceneView sv = sceneView(c);
+    { const int rc = ensurePrimTrees(c); if (rc) return rc; }   // depth 0 (passRaygen) uses them
+    SceneView sv = sceneView(c);
+    sv.sphereTree = sv.cubeTree = 0u;   // the bounce vertices and their shadow rays keep the linear loops
     TraceCounters* cc = c->countersOn ? c->counters.p : nullptr;
     const PathBuffers pb{c->pathT.p, c->pathL.p, c->pathDirect.p};
     auto closestQ = [&](uint32_t d) { RayQueue q{}; q.rays = c->pathRays[d & 1].p; q.slotIds = c->pathSlots[d & 1].p; q.count = c->pathCounts.p + 2 * d; return q; };       // rays traced at depth d (d >= 1)
@@ -1104,9 +1170,21 @@ int rtb_trace_rays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* pr
     int rc = stageRays(c, rays, n, prev, nullptr);
     if (rc) return rc;
     RTB_CUDA(c, c->rinHits.alloc((size_t)n)); RTB_CUDA(c, c->rinObj.alloc((size_t)n)); RTB_CUDA(c, c->rinT.alloc((size_t)n)); RTB_CUDA(c, c->rinUv.alloc((size_t)n));
+    { const int rc2 = ensurePrimTrees(c); if (rc2) return rc2; }
     const SceneView sv = sceneView(c);
     launch_trace_closest(sv, c->rinRays.p, (uint32_t)n, c->rinHits.p, c->lane[0].workCounter.p, nullptr, c->packetsOpt == 2 ? PACKETS_OFF : (int)c->packetsOpt, c->stream);
-    launch_finish_rays(sv, c->rinRays.p, c->rinHits.p, (uint32_t)n, c->rinObj.p, c->rinT.p, c->rinUv.p, c->stream);
+    const PrimHit *ws = nullptr, *wc = nullptr;
+    if (sv.sphereTree) {
+        RTB_CUDA(c, c->rinPrimS.alloc((size_t)n));
+        launch_prims_closest(0, sv, primTreeOf(c, 0), c->rinRays.p, (uint32_t)n, nullptr, c->rinHits.p, nullptr, c->rinPrimS.p, c->stream);
+        ws = c->rinPrimS.p;
+    }
+    if (sv.cubeTree) {
+        RTB_CUDA(c, c->rinPrimC.alloc((size_t)n));
+        launch_prims_closest(1, sv, primTreeOf(c, 1), c->rinRays.p, (uint32_t)n, nullptr, c->rinHits.p, ws, c->rinPrimC.p, c->stream);
+        wc = c->rinPrimC.p;
+    }
+    launch_finish_rays(sv, c->rinRays.p, c->rinHits.p, (uint32_t)n, c->rinObj.p, c->rinT.p, c->rinUv.p, c->stream, ws, wc);
     RTB_CUDA(c, cudaGetLastError());
     if (object) RTB_CUDA(c, cudaMemcpyAsync(object, c->rinObj.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (t) RTB_CUDA(c, cudaMemcpyAsync(t, c->rinT.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1124,9 +1202,12 @@ int rtb_occlusion_rays(rtb_ctx* c, const float* rays, uint64_t n, const float* m
     int rc = stageRays(c, rays, n, prev, maxDist);
     if (rc) return rc;
     RTB_CUDA(c, c->rinOcc.alloc((size_t)n)); RTB_CUDA(c, c->rinOcc2.alloc((size_t)n));
+    { const int rc2 = ensurePrimTrees(c); if (rc2) return rc2; }
     const SceneView sv = sceneView(c);
     launch_occlusion_others(sv, c->rinRays.p, (uint32_t)n, c->rinOcc.p, c->stream);
     launch_trace_any_bytes(sv, c->rinRays.p, (uint32_t)n, c->rinOcc2.p, c->lane[0].workCounter.p, c->stream);
+    if (sv.sphereTree) launch_prims_any(0, sv, primTreeOf(c, 0), c->rinRays.p, (uint32_t)n, nullptr, c->rinOcc.p, nullptr, nullptr, FrameMap{}, c->stream);
+    if (sv.cubeTree) launch_prims_any(1, sv, primTreeOf(c, 1), c->rinRays.p, (uint32_t)n, nullptr, c->rinOcc.p, nullptr, nullptr, FrameMap{}, c->stream);
     RTB_CUDA(c, cudaGetLastError());
     std::vector<uint8_t> a((size_t)n), b((size_t)n);
     RTB_CUDA(c, cudaMemcpyAsync(a.data(), c->rinOcc.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));

@@ -265,16 +265,20 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_bvh(const TraceArgs a) 
 
 }  // namespace rtb
 #include "rtb_trace8.cuh"
+#include "rtb_trace8s.cuh"
 #include "rtb_trace8p.cuh"
 #include "rtb_trace8f.cuh"
 #include "rtb_trace8b.cuh"
 namespace rtb {
 
-// persistent grid: one resident wave (SM count x blocks that fit per SM), fewer when the wavefront is small
+// persistent grid: one resident wave (SM count x blocks that fit per SM), fewer when the wavefront is small.  The size is cached
+// per kernel AND per device (a process may drive contexts on several devices)
+struct OccCache { int v[32] = {}; int& get() { int d = 0; cudaGetDevice(&d); return v[d & 31]; } };
 static int g_traceBlocks = 0;
 template <int MODE, bool COUNT, bool WIDE>
 static void launchTraceBvh(const TraceArgs& a, cudaStream_t st) {
-    static int blocks = 0;
+    static OccCache cache;
+    int& blocks = cache.get();
     auto kernel = WIDE ? k_trace_cwbvh<MODE, COUNT> : k_trace_bvh<MODE, COUNT>;
     if (!blocks) {
         int dev = 0, sms = 0, perSm = 0;
@@ -309,7 +313,8 @@ static uint32_t persistentBlocks(K kernel, int& cache, uint32_t n) {
 }
 template <bool COUNT, bool FRUSTUM>
 static void launchPacket(const TraceArgs& a, cudaStream_t st) {
-    static int blocks = 0;
+    static OccCache cache;
+    int& blocks = cache.get();
     cudaMemsetAsync(a.workCounter, 0, sizeof(uint32_t), st);
     if (FRUSTUM) {
         auto kernel = k_trace_cwbvh_frustum<COUNT, false>;
@@ -395,7 +400,8 @@ static TraceArgs makeArgs(const SceneView& sv, const RayRec* rays, uint32_t n, u
 void launch_primary_fused(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, float4* dirT, float4* uvN,
                           uint32_t* workCounter, cudaStream_t st) {
     if (!fm.localSlots) return;
-    static int blocks = 0;
+    static OccCache cache;
+    int& blocks = cache.get();
     TraceArgs a = makeArgs(sv, nullptr, fm.localSlots, workCounter, nullptr);
     FusedArgs f{fm, *cam, seed, sv, dirT, uvN};
     cudaMemsetAsync(workCounter, 0, sizeof(uint32_t), st);
@@ -439,7 +445,8 @@ void launch_trace_any_bits(const FrameMap& fm, const SceneView& sv, const RayRec
 void launch_trace_beam_bits(const FrameMap& fm, const SceneView& sv, const RayRec* rays, uint32_t n, uint32_t* bits, uint32_t* workCounter,
                             TraceCounters* counters, const uint32_t* slotIds, const uint32_t* countPtr, const RayQueue& fallback, cudaStream_t st) {
     if (!n || sv.info.triangleCount == 0) return;
-    static int blocks = 0, blocksCount = 0;
+    static OccCache cache, cacheCount;
+    int &blocks = cache.get(), &blocksCount = cacheCount.get();
     TraceArgs a = makeArgs(sv, rays, n, workCounter, counters);
     a.bits = bits; a.fm = fm; a.slotIds = slotIds; a.countPtr = countPtr;
     cudaMemsetAsync(workCounter, 0, sizeof(uint32_t), st);
@@ -467,14 +474,31 @@ void launch_trace_any_bytes(const SceneView& sv, const RayRec* rays, uint32_t n,
 // K1b: the rest of traceGeometry after the triangle loop, then the G-buffer stores
 // --------------------------------------------------------------------------------------------------------
 // SH/trace.glsl:31-63: spheres, cubes, planes in order with running ids; then the normal selection.
-RTB_DI void finishGeometry(const SceneView& sv, const Ray& ray, uint32_t prev, const TriHit& th, Hit& hit, vec3& objectNormal) {
+// sph / cub: the winner of the type's tree traversal (rtb_trace8s.cuh) when that type has a tree — the reference's function then
+// runs on that one primitive (it is accepted: its distance undercuts what the earlier stages left) — or nullptr: the linear loop.
+RTB_DI void finishGeometry(const SceneView& sv, const Ray& ray, uint32_t prev, const TriHit& th, Hit& hit, vec3& objectNormal,
+                           const PrimHit* sph = nullptr, const PrimHit* cub = nullptr) {
     hit.hitT = th.id == NO_RAY_HIT ? NO_HIT : th.t;
     hit.uv = mk2(th.u, th.v);
     hit.object = th.id == NO_RAY_HIT ? 0u : th.id;
     hit.geometryNormal = mk3(0.0f, 0.0f, 0.0f);
     uint32_t j = sv.info.triangleCount;
+    if (sph) {
+        if (sph->id != NO_RAY_HIT && rayIntersectSphere(ray, __ldg(sv.spheres + sph->id), hit, j + sph->id, prev)) hit.object = j + sph->id;
+        j += sv.info.sphereCount;
+    } else
     for (uint32_t i = 0; i < sv.info.sphereCount; ++i, ++j)
         if (rayIntersectSphere(ray, __ldg(sv.spheres + i), hit, j, prev)) hit.object = j;
+    if (cub) {
+        if (cub->id != NO_RAY_HIT) {
+            float c[6];
+            const float2* cp = reinterpret_cast<const float2*>(sv.cubes + 6 * (size_t)cub->id);
+            const float2 c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
+            c[0] = c0.x; c[1] = c0.y; c[2] = c1.x; c[3] = c1.y; c[4] = c2.x; c[5] = c2.y;
+            if (rayIntersectCube(ray, c, hit, j + cub->id, prev)) hit.object = j + cub->id;
+        }
+        j += sv.info.cubeCount;
+    } else
     for (uint32_t i = 0; i < sv.info.cubeCount; ++i, ++j) {
         float c[6];
         const float2* cp = reinterpret_cast<const float2*>(sv.cubes + 6 * (size_t)i);
@@ -493,7 +517,8 @@ RTB_DI void finishGeometry(const SceneView& sv, const Ray& ray, uint32_t prev, c
 }
 
 __global__ void __launch_bounds__(256) k_finish_primary(const FrameMap fm, const SceneView sv, const RayRec* __restrict__ rays,
-                                                        const TriHit* __restrict__ hits, float4* __restrict__ dirT, float4* __restrict__ uvN) {
+                                                        const TriHit* __restrict__ hits, float4* __restrict__ dirT, float4* __restrict__ uvN,
+                                                        const PrimHit* __restrict__ sph, const PrimHit* __restrict__ cub) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= fm.localSlots) return;
     uint32_t x, y;
@@ -503,7 +528,10 @@ __global__ void __launch_bounds__(256) k_finish_primary(const FrameMap fm, const
     TriHit th; th.t = hv.x; th.id = fbits(hv.y); th.u = hv.z; th.v = hv.w;
     Ray ray; ray.pos = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
     Hit hit; vec3 objectNormal;
-    finishGeometry(sv, ray, NO_RAY_HIT, th, hit, objectNormal);
+    PrimHit ws, wc;
+    if (sph) ws = sph[i];
+    if (cub) wc = cub[i];
+    finishGeometry(sv, ray, NO_RAY_HIT, th, hit, objectNormal, sph ? &ws : nullptr, cub ? &wc : nullptr);
     // SH/raygen.comp:39-51
     float4 out0;
     if (hit.hitT == NO_HIT) out0 = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ubits(NO_RAY_HIT));
@@ -515,9 +543,10 @@ __global__ void __launch_bounds__(256) k_finish_primary(const FrameMap fm, const
     if (!sv.releaseBuild || hit.hitT < NO_HIT)   // the RELEASE build stores uvObjectNormal for hits only (SH/raygen.comp:46-51)
         uvN[px] = make_float4(hit.uv.x, hit.uv.y, ubits(ex), ubits(ey));
 }
-void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits, float4* dirT, float4* uvN, cudaStream_t st) {
+void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits, float4* dirT, float4* uvN, cudaStream_t st,
+                           const PrimHit* sph, const PrimHit* cub) {
     if (!fm.localSlots) return;
-    k_finish_primary<<<(fm.localSlots + 255) / 256, 256, 0, st>>>(fm, sv, rays, hits, dirT, uvN);
+    k_finish_primary<<<(fm.localSlots + 255) / 256, 256, 0, st>>>(fm, sv, rays, hits, dirT, uvN, sph, cub);
 }
 
 // instrumented frames only: pixels whose nearest hit is ANY primitive (= the shadow rays the reference traces per sample)
@@ -535,7 +564,8 @@ void launch_count_hits(const FrameMap& fm, const float4* dirT, TraceCounters* co
 }
 
 __global__ void __launch_bounds__(256) k_finish_rays(const SceneView sv, const RayRec* __restrict__ rays, const TriHit* __restrict__ hits,
-                                                     uint32_t n, uint32_t* __restrict__ object, float* __restrict__ t, float2* __restrict__ uv) {
+                                                     uint32_t n, uint32_t* __restrict__ object, float* __restrict__ t, float2* __restrict__ uv,
+                                                     const PrimHit* __restrict__ sph, const PrimHit* __restrict__ cub) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 o = __ldg(reinterpret_cast<const float4*>(rays + i)), d = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
@@ -543,14 +573,39 @@ __global__ void __launch_bounds__(256) k_finish_rays(const SceneView sv, const R
     TriHit th; th.t = hv.x; th.id = fbits(hv.y); th.u = hv.z; th.v = hv.w;
     Ray ray; ray.pos = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
     Hit hit; vec3 objectNormal;
-    finishGeometry(sv, ray, fbits(o.w), th, hit, objectNormal);
+    PrimHit ws, wc;
+    if (sph) ws = sph[i];
+    if (cub) wc = cub[i];
+    finishGeometry(sv, ray, fbits(o.w), th, hit, objectNormal, sph ? &ws : nullptr, cub ? &wc : nullptr);
     if (object) object[i] = hit.hitT == NO_HIT ? NO_RAY_HIT : hit.object;
     if (t) t[i] = hit.hitT;
     if (uv) uv[i] = make_float2(hit.uv.x, hit.uv.y);
 }
-void launch_finish_rays(const SceneView& sv, const RayRec* rays, const TriHit* hits, uint32_t n, uint32_t* object, float* t, float2* uv, cudaStream_t st) {
+void launch_finish_rays(const SceneView& sv, const RayRec* rays, const TriHit* hits, uint32_t n, uint32_t* object, float* t, float2* uv, cudaStream_t st,
+                        const PrimHit* sph, const PrimHit* cub) {
     if (!n) return;
-    k_finish_rays<<<(n + 255) / 256, 256, 0, st>>>(sv, rays, hits, n, object, t, uv);
+    k_finish_rays<<<(n + 255) / 256, 256, 0, st>>>(sv, rays, hits, n, object, t, uv, sph, cub);
+}
+
+static PrimTraceArgs primArgs(int kind, const SceneView& sv, const PrimTree& tree, const RayRec* rays, uint32_t n, const uint32_t* countPtr) {
+    PrimTraceArgs a{};
+    a.rays = rays; a.n = n; a.countPtr = countPtr;
+    a.nodes8 = reinterpret_cast<const uint4*>(tree.nodes); a.nodes8Alias = a.nodes8; a.tt = reinterpret_cast<const float4*>(tree.tt);
+    a.spheres = sv.spheres; a.cubes = sv.cubes;
+    a.firstObject = sv.info.triangleCount + (kind == 1 ? sv.info.sphereCount : 0u);
+    return a;
+}
+void launch_prims_closest(int kind, const SceneView& sv, const PrimTree& tree, const RayRec* rays, uint32_t n, const uint32_t* countPtr,
+                          const TriHit* triHits, const PrimHit* before, PrimHit* out, cudaStream_t st) {
+    PrimTraceArgs a = primArgs(kind, sv, tree, rays, n, countPtr);
+    a.triHits = triHits; a.before = before; a.out = out;
+    launch_trace_prims(kind, false, a, st);
+}
+void launch_prims_any(int kind, const SceneView& sv, const PrimTree& tree, const RayRec* rays, uint32_t n, const uint32_t* countPtr, uint8_t* bytes,
+                      uint32_t* bits, const uint32_t* slotIds, const FrameMap& fm, cudaStream_t st) {
+    PrimTraceArgs a = primArgs(kind, sv, tree, rays, n, countPtr);
+    a.bytes = bytes; a.bits = bits; a.slotIds = slotIds; a.fm = fm;
+    launch_trace_prims(kind, true, a, st);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -563,11 +618,15 @@ RTB_DI bool occludedByOthers(const SceneView& sv, const Ray& ray, float maxDist,
     Hit hit;
     hit.hitT = NO_HIT; hit.uv = mk2(0.0f, 0.0f); hit.object = 0; hit.geometryNormal = mk3(0.0f, 0.0f, 0.0f);
     uint32_t j = sv.info.triangleCount;
+    if (sv.sphereTree) j += sv.info.sphereCount;   // (answered by the spheres' tree traversal)
+    else
     for (uint32_t i = 0; i < sv.info.sphereCount; ++i, ++j) {
         if (j == prev) continue;
         const float t = sphereCandidateT(ray, __ldg(sv.spheres + i));
         if (t < hit.hitT) hit.hitT = t;
     }
+    if (sv.cubeTree) j += sv.info.cubeCount;
+    else
     for (uint32_t i = 0; i < sv.info.cubeCount; ++i, ++j) {
         float c[6];
         const float2* cp = reinterpret_cast<const float2*>(sv.cubes + 6 * (size_t)i);
@@ -644,7 +703,7 @@ __global__ void __launch_bounds__(256, RTB_SHADOWGEN_MINBLOCKS) k_shadowgen(cons
             if (maxDist != -1.0f) {
                 if (occludedByOthers(sv, ray, maxDist, object))
                     atomicOr(bits + indexToLight(x, y, fm.w, fm.h, sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
-                else if (maxDist > 0.0f) {
+                else if (maxDist > 0.0f || sv.sphereTree || sv.cubeTree) {   // (a cube entered from inside occludes at a distance below zero)
                     ro = make_float4(ray.pos.x, ray.pos.y, ray.pos.z, ubits(object));
                     rd = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, maxDist);
                 }
@@ -721,7 +780,7 @@ __global__ void __launch_bounds__(256) k_occlusion_others(const SceneView sv, Ra
     Ray ray; ray.pos = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
     const bool occ = occludedByOthers(sv, ray, d.w, fbits(o.w));
     occluded[i] = occ ? 1 : 0;
-    if (occ || !(d.w > 0.0f)) rays[i].tmax = -1.0f;   // nothing left for the triangle search
+    if (occ || (!(d.w > 0.0f) && !sv.sphereTree && !sv.cubeTree)) rays[i].tmax = -1.0f;   // nothing left for the searches that follow
 }
 void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t st, const uint32_t* countPtr) {
     if (!n) return;
@@ -992,7 +1051,7 @@ __global__ void __launch_bounds__(256) k_shadowgen_lights(const FrameMap fm, con
                 if (maxDist != -1.0f) {
                     if (occludedByOthers(sv, ray, maxDist, object))
                         atomicOr(bits + indexToLight(x, y, fm.w, fm.h, L * samples + sample), 1u << ((x & 15u) | ((y & 1u) << 4)));
-                    else if (maxDist > 0.0f) {
+                    else if (maxDist > 0.0f || sv.sphereTree || sv.cubeTree) {
                         ro = make_float4(ray.pos.x, ray.pos.y, ray.pos.z, ubits(object));
                         rd = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, maxDist);
                         live = true;

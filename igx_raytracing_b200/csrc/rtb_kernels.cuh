@@ -27,10 +27,16 @@ struct SceneView {
     const BvhNode* nodes; const Node8* nodes8; const TravTri* travTris; uint32_t nodeCount;   // of the structure in use
     uint32_t useBvh;              // ACCEL_KIND_*
     uint32_t releaseBuild;        // RTB_OPT_SHADER_BUILD: 0 = the reference's DEBUG shader build (what ships), 1 = RELEASE
+    // spheres / cubes through their own trees (rtb_trace8s.cuh): when set, the linear loops of that type are skipped by
+    // finishGeometry (given the traversal's winner) and by occludedByOthers (the traversal answers)
+    uint32_t sphereTree, cubeTree;
 };
 enum : uint32_t { ACCEL_KIND_BRUTE = 0, ACCEL_KIND_CWBVH = 1, ACCEL_KIND_BVH2 = 2 };
 
 struct TraceCounters { unsigned long long rays, nodes, tris, hits; };
+// spheres / cubes through their own trees (rtb_trace8s.cuh): the winner of a type's traversal (id within the type, NO_RAY_HIT = none)
+struct PrimHit { float t; uint32_t id; };
+struct PrimTree { const Node8* nodes; const TravTri* tt; uint32_t nodeCount; };
 
 // Light-space 2D coordinate of an occlusion ray (rtb_sort.cu): rays with equal coordinates travel along the same line.
 struct RayBin {
@@ -59,7 +65,7 @@ void launch_primary_fused(const FrameMap& fm, const SceneView& sv, const CameraR
                           uint32_t* workCounter, cudaStream_t s);
 // spheres, cubes, planes after the triangles, normal interpolation, G-buffer stores (raygen.comp:39-51)
 void launch_finish_primary(const FrameMap& fm, const SceneView& sv, const RayRec* rays, const TriHit* hits,
-                           float4* dirT, float4* uvN, cudaStream_t s);
+                           float4* dirT, float4* uvN, cudaStream_t s, const PrimHit* sph = nullptr, const PrimHit* cub = nullptr);
 // instrumented frames: counters->hits = pixels of this rank whose nearest hit is any primitive
 void launch_count_hits(const FrameMap& fm, const float4* dirT, TraceCounters* counters, cudaStream_t s);
 // shadow.comp ray set-up + occlusion by the non-triangle primitives; leaves triangle work in `rays`
@@ -111,9 +117,17 @@ enum { SHADE_LIGHTING = 1, SHADE_COMPOSITE = 2, SHADE_BOTH = 3 };
 void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
                   const float4* dirT, const float4* uvN, const uint32_t* bits, uint2* lighting, float4* accum,
                   uint32_t* rgba8, uint32_t* rgba8Tiled, cudaStream_t s, const LightsView* lights = nullptr);
-// rays-in helpers
+// spheres / cubes through their own trees (rtb_trace8s.cuh)
+// nearest sphere / cube for every ray given what the earlier stages left (triHits, `before`); kind 0 spheres, 1 cubes
+void launch_prims_closest(int kind, const SceneView& sv, const PrimTree& tree, const RayRec* rays, uint32_t n, const uint32_t* countPtr,
+                          const TriHit* triHits, const PrimHit* before, PrimHit* out, cudaStream_t s);
+// any hit: ORs into `bytes` (rays-in) or into the shadow words (slotIds as launch_trace_any_bits)
+void launch_prims_any(int kind, const SceneView& sv, const PrimTree& tree, const RayRec* rays, uint32_t n, const uint32_t* countPtr, uint8_t* bytes,
+                      uint32_t* bits, const uint32_t* slotIds, const FrameMap& fm, cudaStream_t s);
+void launch_proxy_triangles(int kind, const float4* spheres, const float* cubes, uint32_t n, TriangleRec* out, cudaStream_t s);
+// rays-in helpers (sph / cub: the winners of the type's tree traversal, or nullptr for the linear loops)
 void launch_finish_rays(const SceneView& sv, const RayRec* rays, const TriHit* hits, uint32_t n, uint32_t* object, float* t,
-                        float2* uv, cudaStream_t s);
+                        float2* uv, cudaStream_t s, const PrimHit* sph = nullptr, const PrimHit* cub = nullptr);
 void launch_occlusion_others(const SceneView& sv, RayRec* rays, uint32_t n, uint8_t* occluded, cudaStream_t s, const uint32_t* countPtr = nullptr);
 // rank 0: gathered [nranks][slotsPerRank] tiled pixels -> scan-line rgba8
 void launch_untile(const FrameMap& fm, const uint32_t* tiledAll, uint32_t slotsPerRank, uint32_t* rgba8, cudaStream_t s);

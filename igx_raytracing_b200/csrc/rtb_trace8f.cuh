@@ -43,7 +43,8 @@ namespace rtb {
 struct FusedArgs {
     FrameMap fm; CameraRec cam; const SeedRec* seed; SceneView sv; float4* dirT; float4* uvN;
 };
-RTB_DI void finishGeometry(const SceneView& sv, const Ray& ray, uint32_t prev, const TriHit& th, Hit& hit, vec3& objectNormal);   // rtb_kernels.cu
+RTB_DI void finishGeometry(const SceneView& sv, const Ray& ray, uint32_t prev, const TriHit& th, Hit& hit, vec3& objectNormal,
+                           const PrimHit* sph, const PrimHit* cub);   // rtb_kernels.cu
 
 // Per-lane description of the quadrant's interval ray, in the form each of the two walks wants it.
 struct QuadPlain {      // every axis has a sign: mirrored so that the quadrant travels towards +
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTB_FR_MINBLOCKS) k_trace_cwbvh
             if (live) {   // k_finish_primary, on registers
                 Ray ray; ray.pos = mk3(ox, oy, oz); ray.dir = mk3(dx, dy, dz);
                 Hit hit; vec3 objectNormal;
-                finishGeometry(f.sv, ray, NO_RAY_HIT, h, hit, objectNormal);
+                finishGeometry(f.sv, ray, NO_RAY_HIT, h, hit, objectNormal, nullptr, nullptr);
                 float4 out0;
                 if (hit.hitT == NO_HIT) out0 = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ubits(NO_RAY_HIT));
                 else { const vec3 v = ray.dir * hit.hitT; out0 = make_float4(v.x, v.y, v.z, ubits(hit.object)); }

@@ -103,6 +103,8 @@ typedef struct rtb_accel_info {
     uint32_t refits;          /* rtb_refit_accel calls served by a device refit since the last host build */
     uint32_t primary_packets; /* how the last RAYGEN / FRAME dispatch walked the camera rays: 0 per ray, 1 union packets, 3 frustum packets */
     uint32_t builder;         /* who built the tree in use: 0 host (binned SAH + optimal collapse), 1 device (RTB_OPT_ACCEL_BUILDER) */
+    uint32_t sphere_tree_nodes, cube_tree_nodes; /* nodes of the sphere / cube trees the last dispatch or rays-in call searched
+                                                    (RTB_OPT_PRIMITIVE_TREES); 0 = that type is in the reference's linear loop */
 } rtb_accel_info;
 
 /* Counters of the last instrumented dispatch (rtb_set_option(RTB_OPT_COUNTERS, 1)); the timed build
@@ -147,6 +149,13 @@ typedef enum rtb_option {
                                       scene_graph.cpp:343-376,378-522) need not stall the frame; same hits, somewhat higher SAH
                                       cost.  Falls back to the host builder for fewer than 2 triangles or a tree too deep for
                                       the traversal stack. */
+    RTB_OPT_PRIMITIVE_TREES = 12,  /* spheres and cubes stay in the reference's linear loops (ref: res/shaders/trace.glsl:31-40,83-90) while a
+                                      type has fewer than this many primitives (default 64; 0 = always); from there on the type gets
+                                      an 8-wide tree of its own, built on the device over the primitives' boxes and rebuilt when its
+                                      buffer or count changes, and a traversal that returns what the loop returns — lowest index on
+                                      equal sphere distances, highest on equal cube distances, cubes entered from inside included
+                                      (the reference allows 32768 spheres and 16384 cubes: ref: igx/include/helpers/
+                                      scene_graph.hpp:137-142).  RTB_ACCEL_BRUTE keeps every loop.  Planes are infinite: always looped. */
     RTB_OPT_LIGHTS = 10,           /* BEYOND THE REFERENCE, which samples lights[0] only and scales by lightCount (ref: res/shaders/
                                       nv_all.shadow.comp:97, nv_all.lighting.comp:88,98).  0 (default) = that.
                                       1 = every light gets its own shadow ray per sample and its own Cook-Torrance term; the shadow
