@@ -241,6 +241,7 @@ def main():
                     help="RTB_OPT_SHADOW_ORDER: occlusion rays in wavefront-slot order, as a queue of live rays, or that queue sorted in light space")
     ap.add_argument("--builder", default="host", choices=["host", "device", "device3"], help="RTB_OPT_ACCEL_BUILDER: who builds the 8-wide tree")
     ap.add_argument("--no-graph", action="store_true", help="RTB_OPT_FRAME_GRAPH = 0: launch every frame directly instead of replaying its CUDA graphs")
+    ap.add_argument("--no-overlap", action="store_true", help="RTB_OPT_FRAME_OVERLAP = 0: one recorded frame after the other instead of frame k+1's camera rays under frame k's shadow + shade launches")
     ap.add_argument("--lanes", type=int, default=1, choices=[1, 2], help="RTB_OPT_FRAME_LANES: a frame as one lane or as two half-frame lanes on two streams")
     ap.add_argument("--median-frames", type=int, default=100, help="frames timed one by one for the median (capped to ~10 s)")
     args = ap.parse_args()
@@ -296,6 +297,7 @@ def main():
     ctx.set_option(rtb.OPT_ACCEL_BUILDER, {"host": 0, "device": 1, "device3": 2}[args.builder])
     ctx.set_option(rtb.OPT_FRAME_LANES, args.lanes)
     ctx.set_option(rtb.OPT_FRAME_GRAPH, 0 if args.no_graph else 1)
+    ctx.set_option(rtb.OPT_FRAME_OVERLAP, 0 if args.no_overlap else 1)
     ctx.resize(w, h, samples)
     ctx.upload_scene(scene, None)
     ctx.build_accel(rtb.ACCEL_BVH)
@@ -665,7 +667,7 @@ def main():
                            "sah_cost": info.sah_cost, "build_ms": info.build_ms, "leaf_node_extent": info.leaf_node_extent, "bytes": bvh_bytes,
                            "builder": {0: "host (binned SAH, optimal collapse)", 1: "device (Morton sort, radix tree, greedy collapse)"}.get(info.builder, "?")},
                    "primary_packets": {0: "per ray", 1: "union packets", 3: "frustum packets"}.get(info.primary_packets, str(info.primary_packets)), "packets_option": args.packets,
-                   "shadow_order": args.shadow_order, "frame_lanes": args.lanes, "frame_graph": not args.no_graph,
+                   "shadow_order": args.shadow_order, "frame_lanes": args.lanes, "frame_graph": not args.no_graph, "frame_overlap": not (args.no_overlap or args.no_graph or args.lanes == 2 or bool(bounces)),
                    "phase_note": "phase_ms_rank0 is measured with direct launches in one lane (back to back); the timed frames replay the frame's CUDA graphs" if not args.no_graph else "direct launches",
                    "phase_ms_rank0": {k: float(v) for k, v in zip(["init", "raygen", "trace_primary", "finish", "shadowgen", "trace_shadow", "shade", "total"], phases)}},
         "clocks": clocks,

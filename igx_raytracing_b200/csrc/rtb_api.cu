@@ -97,6 +97,24 @@ struct rtb_ctx {
     uint64_t stamp = 1, lastFrameStamp = 0, graphStamp = 0;
     cudaGraphExec_t graphA = nullptr, graphB = nullptr;
     bool capturing = false;
+    // Consecutive frames overlap (RTB_OPT_FRAME_OVERLAP; recorded frames only): a frame is FRONT = K0 + camera rays + nearest hit +
+    // G-buffer on `frontStream` and BACK = shadow rays + occlusion + lighting + composite on `stream`.  What FRONT hands to BACK —
+    // G-buffer, wavefront buffers, the Seed as K0 left it — exists twice (`alt` is the set not in use; the sets are swapped at every
+    // overlapped frame, so c->dirT etc. always are the latest frame's), so FRONT of frame k+1 runs while BACK of frame k drains:
+    // the tails of the persistent launches are filled by the other stream's work.
+    uint32_t overlapOpt = 1;
+    cudaStream_t frontStream = nullptr;
+    cudaEvent_t evFrontDone[2] = {nullptr, nullptr}, evBackDone[2] = {nullptr, nullptr}, evJoinF = nullptr, evJoinB = nullptr;
+    bool backDoneSet[2] = {false, false};
+    bool frontDirty = false;          // the front stream holds work the back stream has not been ordered after
+    bool frontNeedsBack = true;       // the back stream holds work (uploads, direct passes) the front stream must be ordered after
+    int setIndex = 0;                 // which physical set c->dirT etc. hold
+    bool altAllocated = false;
+    struct FrameSet { DevBuf<float4> dirT, uvN; LaneBufs lane; DevBuf<PrimHit> primHitS, primHitC; } alt;
+    DevBuf<SeedRec> seedSnap;         // [set]
+    SeedRec* seedUse = nullptr;       // non-null while an overlapped frame is being recorded: the set's snapshot
+    cudaGraphExec_t ovFront[2] = {nullptr, nullptr}, ovShadow[2] = {nullptr, nullptr}, ovShade[2] = {nullptr, nullptr};
+    uint64_t ovStamp[2] = {0, 0};
     DevBuf<TraceCounters> counters;   // [0] primary, [1] shadow
     bool countersOn = false;
     uint32_t countersMode = 0;        // 1: per-ray algorithmic counts (per-lane kernel); 2: what the kernels in use fetch
@@ -163,8 +181,11 @@ void makeFrameMap(rtb_ctx* c) {
 
 uint32_t shadowWords(uint32_t w, uint32_t h, uint32_t samples) { return ((w + 15) / 16) * ((h + 1) / 2) * samples; }
 
+void releaseAlt(rtb_ctx* c);
 int allocFrame(rtb_ctx* c) {
     makeFrameMap(c);
+    if (c->frontStream) { RTB_CUDA(c, cudaStreamSynchronize(c->frontStream)); c->frontDirty = false; }
+    releaseAlt(c);   // the second set of FRONT -> BACK buffers (frame overlap) follows the frame size: reallocated when next needed
     const size_t px = (size_t)c->width * c->height;
     RTB_CUDA(c, c->dirT.alloc(px)); RTB_CUDA(c, c->uvN.alloc(px)); RTB_CUDA(c, c->accum.alloc(px));
     RTB_CUDA(c, c->lighting.alloc(px)); RTB_CUDA(c, c->rgba8.alloc(px));
@@ -196,6 +217,21 @@ int drainCopy(rtb_ctx* c) {
     if (c->copyTarget >= 0) { RTB_CUDA(c, cudaEventSynchronize(c->evCopied)); c->copyTarget = -1; }
     return RTB_OK;
 }
+
+// the Seed the launches of a frame read: the buffer K0 updates in place, or — overlapped frames — the set's snapshot of it
+const SeedRec* seedFor(const rtb_ctx* c) { return c->seedUse ? c->seedUse : c->seed.p; }
+
+// frame overlap: order the context's stream after everything the front stream holds (before anything that reads or writes what
+// FRONT writes: G-buffer, Seed, wavefront buffers); joinFront alone keeps the next FRONT free to run ahead
+int joinFront(rtb_ctx* c) {
+    if (!c->frontStream || !c->frontDirty) return RTB_OK;
+    RTB_CUDA(c, cudaEventRecord(c->evJoinF, c->frontStream));
+    RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evJoinF, 0));
+    c->frontDirty = false;
+    return RTB_OK;
+}
+// ... and the context's stream is about to get work the next FRONT depends on (scene uploads, builds, direct passes, allocations)
+int quiesce(rtb_ctx* c) { c->frontNeedsBack = true; return joinFront(c); }
 
 // scene counts against the capacities of rtb_create, and the acceleration structure against the triangle buffer:
 // shared by the dispatch path and the rays-in entry points (both index the scene buffers by these counts)
@@ -254,6 +290,7 @@ int ensurePrimTrees(rtb_ctx* c) {
         if (!want) { if (T.valid) { T.valid = false; ++c->stamp; } continue; }
         if (T.valid && !T.dirty && T.count == n) continue;
         const uint32_t cap = n + 64;
+        { const int rc = quiesce(c); if (rc) return rc; }   // (frames in flight on the front stream read the tree)
         RTB_CUDA(c, T.proxies.alloc(n)); RTB_CUDA(c, T.nodes.alloc(cap)); RTB_CUDA(c, T.tt.alloc(n)); RTB_CUDA(c, T.nodeBox.alloc((size_t)cap * 6));
         RTB_CUDA(c, T.maxBits.alloc(1)); RTB_CUDA(c, T.areaSums.alloc(2));
         launch_proxy_triangles(kind, c->spheres.p, c->cubes.p, n, T.proxies.p, c->stream);
@@ -286,11 +323,11 @@ int passRaygen(rtb_ctx* c, bool mark, int lane = -1) {
     if (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt && !trees) {
         // one launch: rays generated in registers, traced, G-buffer written (the phase events collapse onto the trace phase)
         if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], L.st));
-        launch_primary_fused(L.fm, sv, &c->camera, c->seed.p, c->dirT.p, c->uvN.p, L.b.workCounter.p, L.st);
+        launch_primary_fused(L.fm, sv, &c->camera, seedFor(c), c->dirT.p, c->uvN.p, L.b.workCounter.p, L.st);
         if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], L.st));
         return RTB_OK;
     }
-    launch_raygen(L.fm, &c->camera, c->seed.p, L.b.rays.p, L.st);
+    launch_raygen(L.fm, &c->camera, seedFor(c), L.b.rays.p, L.st);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[2], L.st));
     launch_trace_closest(sv, L.b.rays.p, L.fm.localSlots, L.b.hits.p, L.b.workCounter.p, c->countersOn ? c->counters.p : nullptr, c->lastPrimaryPackets, L.st);
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[3], L.st));
@@ -424,7 +461,7 @@ int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
         for (uint32_t first = 0; first < sv.info.lightCount; first += lightsPerChunk) {
             lv.lightBegin = first; lv.lightEnd = std::min(sv.info.lightCount, first + lightsPerChunk);
             RTB_CUDA(c, cudaMemsetAsync(B.queueCount.p, 0, 4, L.st));
-            launch_shadowgen_lights(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->bits.p, q, lv, L.st);
+            launch_shadowgen_lights(L.fm, sv, &c->camera, seedFor(c), c->samples, c->dirT.p, c->bits.p, q, lv, L.st);
             launch_trace_any_bits(L.fm, sv, q.rays, capacity, c->bits.p, B.workCounter.p, counters, q.slotIds, q.count, L.st);
             shadowPrimPasses(c, sv, L.fm, q.rays, capacity, q.count, q.slotIds, L.st);
         }
@@ -433,7 +470,7 @@ int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
     const uint32_t maxRays = L.fm.localSlots * c->samples;
     if (!c->shadowOrder || sv.useBvh != ACCEL_KIND_CWBVH || !sv.info.triangleCount || !maxRays) {
         // slot order: one record per (sample, slot), what the first-generation kernels and the reference loop consume
-        launch_shadowgen(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, B.rays.p, c->bits.p, nullptr, nullptr, L.st);
+        launch_shadowgen(L.fm, sv, &c->camera, seedFor(c), c->samples, c->dirT.p, B.rays.p, c->bits.p, nullptr, nullptr, L.st);
         if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], L.st));
         launch_trace_any_bits(L.fm, sv, B.rays.p, maxRays, c->bits.p, B.workCounter.p, counters, nullptr, nullptr, L.st);
         shadowPrimPasses(c, sv, L.fm, B.rays.p, maxRays, nullptr, nullptr, L.st);
@@ -453,7 +490,7 @@ int passShadow(rtb_ctx* c, bool mark, int lane = -1) {
         q.rays = B.queueRays.p; q.cell = B.queueCell.p; q.rank = B.queueRank.p; q.hist = B.queueHist.p; q.blockSums = B.queueSums.p;
     } else
         q.rays = B.rays.p;
-    launch_shadowgen(L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, B.rays.p, c->bits.p, &q, &bin, L.st);
+    launch_shadowgen(L.fm, sv, &c->camera, seedFor(c), c->samples, c->dirT.p, B.rays.p, c->bits.p, &q, &bin, L.st);
     const uint32_t* slots = B.queueSlots.p;
     if (bin.kind) { launch_sort_rays(q, cells, maxRays, B.rays.p, B.sortedSlots.p, L.st); slots = B.sortedSlots.p; }
     if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[5], L.st));
@@ -473,7 +510,7 @@ int passShade(rtb_ctx* c, int what, int lane = -1) {
     const SceneView sv = sceneView(c);
     LightsView lv;
     { const int rc = lightsView(c, lv, what != SHADE_COMPOSITE); if (rc) return rc; }
-    launch_shade(what, L.fm, sv, &c->camera, c->seed.p, c->samples, c->dirT.p, c->uvN.p, c->bits.p, c->lighting.p, c->accum.p,
+    launch_shade(what, L.fm, sv, &c->camera, seedFor(c), c->samples, c->dirT.p, c->uvN.p, c->bits.p, c->lighting.p, c->accum.p,
                  c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, L.st, &lv);
     if (lv.history && !c->historyValid) { c->historyValid = true; ++c->stamp; }   // the recorded launches hold alpha by value
     return RTB_OK;
@@ -557,6 +594,101 @@ int captureFrame(rtb_ctx* c, int (*part)(rtb_ctx*, bool), cudaGraphExec_t* out) 
     return RTB_OK;
 }
 
+// ---- frame overlap -------------------------------------------------------------------------------------------------------------
+// (not with the RELEASE shader build: its skipped stores leave what the SAME texture held a frame earlier, so the G-buffer must be one)
+bool useOverlap(const rtb_ctx* c) { return c->overlapOpt && c->graphOpt && !c->countersOn && !c->releaseBuild && !useLanes(c) && c->fm.localSlots; }
+
+int overlapFront(rtb_ctx* c, bool) {
+    launch_init(c->seed.p, c->stream, c->seedUse);
+    return passRaygen(c, false);
+}
+int overlapShadow(rtb_ctx* c, bool) { return passShadow(c, false); }
+int overlapShade(rtb_ctx* c, bool) { return passShade(c, SHADE_BOTH); }
+
+void swapSets(rtb_ctx* c) {
+    std::swap(c->dirT, c->alt.dirT); std::swap(c->uvN, c->alt.uvN); std::swap(c->lane[0], c->alt.lane);
+    std::swap(c->primHitS[0], c->alt.primHitS); std::swap(c->primHitC[0], c->alt.primHitC);
+    c->setIndex ^= 1;
+}
+void releaseAlt(rtb_ctx* c) {
+    c->alt.dirT.release(); c->alt.uvN.release(); c->alt.lane.release(); c->alt.primHitS.release(); c->alt.primHitC.release();
+    c->altAllocated = false;
+    for (int k = 0; k < 2; ++k) c->ovStamp[k] = 0;
+}
+int prepareOverlap(rtb_ctx* c) {
+    if (!c->frontStream) {
+        RTB_CUDA(c, cudaStreamCreateWithFlags(&c->frontStream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            RTB_CUDA(c, cudaEventCreateWithFlags(&c->evFrontDone[k], cudaEventDisableTiming));
+            RTB_CUDA(c, cudaEventCreateWithFlags(&c->evBackDone[k], cudaEventDisableTiming));
+        }
+        RTB_CUDA(c, cudaEventCreateWithFlags(&c->evJoinF, cudaEventDisableTiming));
+        RTB_CUDA(c, cudaEventCreateWithFlags(&c->evJoinB, cudaEventDisableTiming));
+        RTB_CUDA(c, c->seedSnap.alloc(2));
+    }
+    if (!c->altAllocated) {
+        const size_t px = (size_t)c->width * c->height;
+        RTB_CUDA(c, c->alt.dirT.alloc(px)); RTB_CUDA(c, c->alt.uvN.alloc(px));
+        RTB_CUDA(c, c->alt.lane.rays.alloc((size_t)c->fm.localSlots * (c->samples ? c->samples : 1)));
+        RTB_CUDA(c, c->alt.lane.hits.alloc(c->fm.localSlots));
+        RTB_CUDA(c, c->alt.lane.workCounter.alloc(1));
+        RTB_CUDA(c, cudaMemsetAsync(c->alt.dirT.p, 0, c->alt.dirT.bytes(), c->stream));   // pixels of other ranks stay defined
+        RTB_CUDA(c, cudaMemsetAsync(c->alt.uvN.p, 0, c->alt.uvN.bytes(), c->stream));
+        RTB_CUDA(c, cudaMemsetAsync(c->alt.lane.workCounter.p, 0, 4, c->stream));
+        c->altAllocated = true;
+        c->frontNeedsBack = true;
+    }
+    return RTB_OK;
+}
+int captureOn(rtb_ctx* c, cudaStream_t st, int (*part)(rtb_ctx*, bool), cudaGraphExec_t* out) {
+    cudaStream_t keep = c->stream;
+    c->stream = st;
+    const int rc = captureFrame(c, part, out);
+    c->stream = keep;
+    return rc;
+}
+// one overlapped frame: swap the sets, FRONT on the front stream, BACK on the context's stream
+int overlappedFrame(rtb_ctx* c) {
+    int rc;
+    if ((rc = prepareOverlap(c))) return rc;
+    swapSets(c);
+    const int s = c->setIndex;
+    if (c->ovStamp[s] != c->stamp || !c->ovFront[s]) {
+        c->seedUse = c->seedSnap.p + s;
+        rc = captureOn(c, c->frontStream, overlapFront, &c->ovFront[s]);
+        if (!rc) rc = captureFrame(c, overlapShadow, &c->ovShadow[s]);
+        if (!rc) rc = captureFrame(c, overlapShade, &c->ovShade[s]);
+        c->seedUse = nullptr;
+        if (rc) { c->ovStamp[s] = 0; return rc; }
+        c->ovStamp[s] = c->stamp;
+    }
+    // FRONT: after what the context's stream holds for it, after the BACK that last read this set, after a read-back of its targets
+    if (c->frontNeedsBack) {
+        RTB_CUDA(c, cudaEventRecord(c->evJoinB, c->stream));
+        RTB_CUDA(c, cudaStreamWaitEvent(c->frontStream, c->evJoinB, 0));
+        c->frontNeedsBack = false;
+    } else if (c->backDoneSet[s])
+        RTB_CUDA(c, cudaStreamWaitEvent(c->frontStream, c->evBackDone[s], 0));
+    if (c->copyTarget == RTB_TGT_SEED || c->copyTarget == RTB_TGT_DIR_T || c->copyTarget == RTB_TGT_UV_NORMAL) {
+        RTB_CUDA(c, cudaStreamWaitEvent(c->frontStream, c->evCopied, 0));
+        RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evCopied, 0));
+        c->copyTarget = -1;
+    }
+    RTB_CUDA(c, cudaGraphLaunch(c->ovFront[s], c->frontStream));
+    RTB_CUDA(c, cudaEventRecord(c->evFrontDone[s], c->frontStream));
+    // BACK
+    RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evFrontDone[s], 0));
+    c->frontDirty = false;
+    if ((rc = waitCopy(c, {RTB_TGT_SHADOW_BITS}))) return rc;
+    RTB_CUDA(c, cudaGraphLaunch(c->ovShadow[s], c->stream));
+    if ((rc = waitCopy(c, {RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}))) return rc;
+    RTB_CUDA(c, cudaGraphLaunch(c->ovShade[s], c->stream));
+    RTB_CUDA(c, cudaEventRecord(c->evBackDone[s], c->stream));
+    c->backDoneSet[s] = true;
+    c->frameTimed = false;
+    return RTB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -602,8 +734,20 @@ int rtb_create(rtb_ctx** out, int cudaDevice, const rtb_limits* limits) {
 void rtb_destroy(rtb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->frontStream) cudaStreamSynchronize(c->frontStream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
+    for (int k = 0; k < 2; ++k) {
+        if (c->ovFront[k]) cudaGraphExecDestroy(c->ovFront[k]);
+        if (c->ovShadow[k]) cudaGraphExecDestroy(c->ovShadow[k]);
+        if (c->ovShade[k]) cudaGraphExecDestroy(c->ovShade[k]);
+        if (c->evFrontDone[k]) cudaEventDestroy(c->evFrontDone[k]);
+        if (c->evBackDone[k]) cudaEventDestroy(c->evBackDone[k]);
+    }
+    if (c->evJoinF) cudaEventDestroy(c->evJoinF);
+    if (c->evJoinB) cudaEventDestroy(c->evJoinB);
+    if (c->frontStream) cudaStreamDestroy(c->frontStream);
+    c->alt.dirT.release(); c->alt.uvN.release(); c->alt.lane.release(); c->alt.primHitS.release(); c->alt.primHitC.release(); c->seedSnap.release();
     if (c->evReady) cudaEventDestroy(c->evReady);
     if (c->evCopied) cudaEventDestroy(c->evCopied);
     c->triangles.release(); c->spheres.release(); c->cubes.release(); c->planes.release(); c->lights.release(); c->materials.release();
@@ -649,6 +793,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             c->tileRank = rank; c->tileCount = count;
             if (c->width) {
                 RTB_BIND(c);
+                { const int rc = quiesce(c); if (rc) return rc; }
                 RTB_CUDA(c, cudaStreamSynchronize(c->stream));
                 const int rc = allocFrame(c);
                 if (rc) { c->tileRank = oldRank; c->tileCount = oldCount; c->width = c->height = 0; makeFrameMap(c); return rc; }   // frame resources are gone: resize again
@@ -665,6 +810,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
             c->historyAlpha = a; c->historyValid = false; return RTB_OK;
         }
         case RTB_OPT_FRAME_GRAPH: c->graphOpt = value ? 1u : 0u; return RTB_OK;
+        case RTB_OPT_FRAME_OVERLAP: c->overlapOpt = value ? 1u : 0u; return RTB_OK;
         case RTB_OPT_FRAME_LANES:
             if (value < 1 || value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_FRAME_LANES: 1 or 2");
             c->lanesOpt = value; return RTB_OK;
@@ -684,6 +830,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
 int rtb_set_stream(rtb_ctx* c, void* s) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
+    { const int rc = quiesce(c); if (rc) return rc; }
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = s ? static_cast<cudaStream_t>(s) : c->ownStream;
     ++c->stamp;
@@ -696,6 +843,7 @@ int rtb_resize(rtb_ctx* c, uint32_t w, uint32_t h, uint32_t shadowSamples) {
     RTB_BIND(c);
     if (w == c->width && h == c->height && shadowSamples == c->samples) return RTB_OK;
     if ((uint64_t)((w + 31) / 32) * ((h + 31) / 32) * 1024ull * shadowSamples > 0xFFFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_resize: too many shadow rays per frame");
+    { const int rc = quiesce(c); if (rc) return rc; }
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     { const int rc = drainCopy(c); if (rc) return rc; }
     c->width = w; c->height = h; c->samples = shadowSamples; c->shadowSamplesProp = shadowSamples;
@@ -745,6 +893,14 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
     }
     if (off > cap || bytes > cap - off) return fail(c, RTB_ERR_CAPACITY, "rtb_upload: range exceeds the capacity given to rtb_create");
     if (!bytes) return RTB_OK;
+    if (id == RTB_BUF_SEED && c->frontStream && !c->frontNeedsBack) {
+        // overlapped frames: K0 of the next frame runs on the front stream, ahead of what the context's stream still holds of the
+        // last one; the Seed buffer belongs to that stream (the running frame reads its own snapshot)
+        RTB_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, src, bytes, cudaMemcpyHostToDevice, c->frontStream));
+        c->frontDirty = true;
+        return RTB_OK;
+    }
+    { const int rc = quiesce(c); if (rc) return rc; }
     if (id == RTB_BUF_TRIANGLES) { std::memcpy(c->triangleMirror.data() + off, src, bytes); c->accelValid = false; ++c->stamp; }
     if (id == RTB_BUF_SPHERES) c->primTree[0].dirty = true;
     if (id == RTB_BUF_CUBES) c->primTree[1].dirty = true;
@@ -759,6 +915,7 @@ int rtb_upload_skybox(rtb_ctx* c, uint32_t w, uint32_t h, const uint16_t* px) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
     ++c->stamp;
+    { const int rc = quiesce(c); if (rc) return rc; }
     if (!w || !h || !px) { c->skyW = c->skyH = 0; return RTB_OK; }
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     RTB_CUDA(c, c->skybox.alloc((size_t)w * h));
@@ -771,6 +928,7 @@ int rtb_build_accel(rtb_ctx* c, rtb_accel_mode mode) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
     if (mode != RTB_ACCEL_BRUTE && mode != RTB_ACCEL_BVH && mode != RTB_ACCEL_BVH2) return fail(c, RTB_ERR_ARG, "rtb_build_accel: unknown mode");
+    { const int rc = quiesce(c); if (rc) return rc; }
     c->accelMode = mode;
     c->accelValid = false;   // until this build has succeeded
     ++c->stamp;
@@ -840,6 +998,7 @@ int rtb_refit_accel(rtb_ctx* c) {
     RTB_BIND(c);
     if (c->accelMode != RTB_ACCEL_BVH || !c->nodeCount || c->builtTriangles != c->info.triangleCount || c->stats.levelFirst.size() < 2)
         return rtb_build_accel(c, c->accelMode);
+    { const int rc = quiesce(c); if (rc) return rc; }
     RTB_CUDA(c, c->nodeBox.alloc((size_t)c->nodeCount * 6)); RTB_CUDA(c, c->maxBits.alloc(1)); RTB_CUDA(c, c->areaSums.alloc(2));
     launch_refit(c->triangles.p, c->info.triangleCount, c->travTris.p, c->info.triangleCount, c->nodes8.p, c->stats.levelFirst.data(),
                  (uint32_t)c->stats.levelFirst.size() - 1, c->nodeBox.p, c->maxBits.p, c->areaSums.p, c->stream);
@@ -876,6 +1035,7 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
     if (pass != RTB_PASS_INIT) { const int rc = checkReady(c); if (rc) return rc; }
     if (pass != RTB_PASS_INIT) { const int rc = ensurePrimTrees(c); if (rc) return rc; }
     int rc = RTB_OK;
+    if (pass != RTB_PASS_FRAME && (rc = quiesce(c))) return rc;
     switch (pass) {
         case RTB_PASS_INIT: if ((rc = waitCopy(c, {RTB_TGT_SEED}))) return rc; launch_init(c->seed.p, c->stream); break;
         case RTB_PASS_RAYGEN: rc = passRaygen(c, false); break;
@@ -885,6 +1045,8 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
         case RTB_PASS_FRAME: {
             if (c->countersOn) RTB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(TraceCounters), c->stream));
             if (useLanes(c)) { if ((rc = prepareLanes(c))) return rc; }
+            if (useOverlap(c) && c->lastFrameStamp == c->stamp) { rc = overlappedFrame(c); break; }   // recorded frames, FRONT of this one under BACK of the last
+            if ((rc = quiesce(c))) return rc;
             // copies still in flight (rtb_readback_async) are waited for outside the recorded work: before part A those of its
             // targets, before part B those of the shade targets — so a frame's read-back overlaps the next frame's traversal
             if ((rc = waitCopy(c, {RTB_TGT_SEED, RTB_TGT_DIR_T, RTB_TGT_UV_NORMAL, RTB_TGT_SHADOW_BITS}))) return rc;
@@ -915,6 +1077,7 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
 
 int rtb_device_ptr(rtb_ctx* c, rtb_target t, void** out, size_t* bytes) {
     if (!c || !out) return RTB_ERR_ARG;
+    if (c->frontDirty) { RTB_BIND(c); const int rc = joinFront(c); if (rc) return rc; }   // the caller works on the context's stream
     const size_t px = (size_t)c->width * c->height;
     void* p = nullptr; size_t n = 0;
     switch (t) {
@@ -944,6 +1107,7 @@ int rtb_readback(rtb_ctx* c, rtb_target t, void* dst, size_t bytes) {
     const int rc = rtb_device_ptr(c, t, &p, &n);
     if (rc) return rc;
     if (bytes > n) return fail(c, RTB_ERR_ARG, "rtb_readback: more bytes requested than the target holds");
+    { const int rc2 = joinFront(c); if (rc2) return rc2; }
     RTB_CUDA(c, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, c->stream));
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));
     return RTB_OK;
@@ -957,6 +1121,7 @@ int rtb_readback_async(rtb_ctx* c, rtb_target t, void* dst, size_t bytes) {
     if (rc) return rc;
     if (bytes > n) return fail(c, RTB_ERR_ARG, "rtb_readback_async: more bytes requested than the target holds");
     if ((rc = drainCopy(c))) return rc;   // one read-back in flight at a time
+    if ((rc = joinFront(c))) return rc;
     if (!c->copyStream) {
         RTB_CUDA(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
         RTB_CUDA(c, cudaEventCreateWithFlags(&c->evReady, cudaEventDisableTiming));
@@ -1023,6 +1188,7 @@ int rtb_probe_l2_read_gbs(rtb_ctx* c, size_t bytes, double* outGbs) {
 int rtb_sync(rtb_ctx* c) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
+    if (c->frontStream) RTB_CUDA(c, cudaStreamSynchronize(c->frontStream));
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));   // (a frame in lanes has joined the lane stream back into this one)
     if (c->copyStream) RTB_CUDA(c, cudaStreamSynchronize(c->copyStream));
     return RTB_OK;
@@ -1057,6 +1223,7 @@ int rtb_path_frame(rtb_ctx* c, uint32_t bounces) {
     RTB_BIND(c);
     if (bounces > PATH_MAX_BOUNCES) return fail(c, RTB_ERR_ARG, "rtb_path_frame: at most 15 bounces");
     { const int rc = checkReady(c); if (rc) return rc; }
+    { const int rc = quiesce(c); if (rc) return rc; }
     { const int rc = waitCopy(c, {RTB_TGT_SEED, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
     const uint32_t slots = c->fm.localSlots, depths = bounces + 1;
     RTB_CUDA(c, c->pathT.alloc(slots)); RTB_CUDA(c, c->pathL.alloc(slots)); RTB_CUDA(c, c->pathDirect.alloc(slots));
@@ -1167,6 +1334,7 @@ int rtb_trace_rays(rtb_ctx* c, const float* rays, uint64_t n, const uint32_t* pr
     if (n > 0x7FFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_trace_rays: too many rays");
     { const int rc = checkScene(c); if (rc) return rc; }
     if (!n) return RTB_OK;
+    { const int rc = quiesce(c); if (rc) return rc; }
     int rc = stageRays(c, rays, n, prev, nullptr);
     if (rc) return rc;
     RTB_CUDA(c, c->rinHits.alloc((size_t)n)); RTB_CUDA(c, c->rinObj.alloc((size_t)n)); RTB_CUDA(c, c->rinT.alloc((size_t)n)); RTB_CUDA(c, c->rinUv.alloc((size_t)n));
@@ -1199,6 +1367,7 @@ int rtb_occlusion_rays(rtb_ctx* c, const float* rays, uint64_t n, const float* m
     if (n > 0x7FFFFFFFull) return fail(c, RTB_ERR_ARG, "rtb_occlusion_rays: too many rays");
     { const int rc = checkScene(c); if (rc) return rc; }
     if (!n) return RTB_OK;
+    { const int rc = quiesce(c); if (rc) return rc; }
     int rc = stageRays(c, rays, n, prev, maxDist);
     if (rc) return rc;
     RTB_CUDA(c, c->rinOcc.alloc((size_t)n)); RTB_CUDA(c, c->rinOcc2.alloc((size_t)n));

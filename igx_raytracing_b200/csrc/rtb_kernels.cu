@@ -49,14 +49,17 @@ RTB_DI void queueAppend(const RayQueue& q, bool live, float4 ro, float4 rd, uint
 // --------------------------------------------------------------------------------------------------------
 // K0
 // --------------------------------------------------------------------------------------------------------
-__global__ void k_init(SeedRec* seed) {
+// `snap` (may be null): a second copy of the result — the copy the frame's other launches read when consecutive frames overlap
+// (rtb_api.cu, frame overlap): the next frame's K0 then rewrites `seed` while this frame's shadow and shade launches still run
+__global__ void k_init(SeedRec* seed, SeedRec* snap) {
     SeedRec s = *seed;
     vec2 off = rand2(mk2(s.cpuOffsetX, s.cpuOffsetY) + (float)s.sampleCount);
     s.randomX = off.x; s.randomY = off.y;
     ++s.sampleCount; ++s.sampleOffset;
     *seed = s;
+    if (snap) *snap = s;
 }
-void launch_init(SeedRec* seed, cudaStream_t st) { k_init<<<1, 1, 0, st>>>(seed); }
+void launch_init(SeedRec* seed, cudaStream_t st, SeedRec* snap) { k_init<<<1, 1, 0, st>>>(seed, snap); }
 
 // --------------------------------------------------------------------------------------------------------
 // K1a: primary rays

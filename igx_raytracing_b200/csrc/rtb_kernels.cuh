@@ -51,7 +51,7 @@ struct RayQueue {
     uint32_t* cell; uint32_t* rank; uint32_t* hist; uint32_t* blockSums;   // binning (RayBin.kind != 0)
 };
 
-void launch_init(SeedRec* seed, cudaStream_t s);
+void launch_init(SeedRec* seed, cudaStream_t s, SeedRec* snap = nullptr);
 void launch_raygen(const FrameMap& fm, const CameraRec* cam, const SeedRec* seed, RayRec* rays, cudaStream_t s);
 // nearest triangle for every ray slot (BVH or brute force according to sv.useBvh).  packets != PACKETS_OFF: 32 consecutive
 // slots are a coherent patch and the 8-wide tree is walked once per warp — every lane testing every child box

@@ -149,6 +149,13 @@ typedef enum rtb_option {
                                       scene_graph.cpp:343-376,378-522) need not stall the frame; same hits, somewhat higher SAH
                                       cost.  Falls back to the host builder for fewer than 2 triangles or a tree too deep for
                                       the traversal stack. */
+    RTB_OPT_FRAME_OVERLAP = 13,    /* default 1: recorded frames (RTB_OPT_FRAME_GRAPH) of consecutive RTB_PASS_FRAME dispatches overlap — init +
+                                      camera rays + nearest hit + G-buffer of frame k+1 run on a second stream while shadow rays, lighting
+                                      and composite of frame k drain, on two sets of the buffers the first half hands to the second (the
+                                      Seed as init.comp left it included).  Same launches, same pixels; the tails of the persistent
+                                      launches are filled (one rank of eight: 0.65 -> 0.57 ms per 4K soup frame).  Everything else the
+                                      API offers is ordered after both streams; pointers from rtb_device_ptr(DIR_T / UV_NORMAL) name the
+                                      latest frame's set and are valid until the next RTB_PASS_FRAME.  0: one frame after the other. */
     RTB_OPT_PRIMITIVE_TREES = 12,  /* spheres and cubes stay in the reference's linear loops (ref: res/shaders/trace.glsl:31-40,83-90) while a
                                       type has fewer than this many primitives (default 64; 0 = always); from there on the type gets
                                       an 8-wide tree of its own, built on the device over the primitives' boxes and rebuilt when its

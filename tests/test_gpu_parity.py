@@ -844,3 +844,63 @@ def test_frame_graph_replay_identical_and_rerecorded_on_change(rtb, oracle):
     bad = int((replayed[0][0].view(np.uint32) != acc.view(np.uint32)).any(-1).sum())
     assert bad <= 4
     assert int((replayed[0][1] != want["rgba8"]).sum()) <= 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tiles", [1, 4])
+def test_overlapped_frames_identical(rtb, tiles):
+    """RTB_OPT_FRAME_OVERLAP: the camera rays of frame k+1 run under the shadow + shade launches of frame k, on two sets of
+    G-buffer / wavefront / Seed buffers.  A sequence that exercises every ordering rule — per-frame seed uploads, an asynchronous
+    read-back of every frame, G-buffer read-backs in between, a sphere upload (no re-recording), per-pass dispatches and rays-in
+    calls between overlapped frames, progressive accumulation — gives the same bytes as one frame after the other."""
+    import torch
+    w, h = 640, 360
+    scene = soup_scene(rtb, 150_000)
+    base = rtb.niels_scene(0.0)
+    scene.update(spheres=base["spheres"], cubes=base["cubes"], planes=base["planes"],
+                 material_indices=np.zeros(150_000 + 10, np.uint32), info=np.array([1, 1, 150_000, 7, 2, 1, 1, 0, 0], np.uint32))
+    rays = np.random.default_rng(4).normal(size=(4096, 6)).astype(np.float32)
+
+    def run(overlap):
+        ctx = rtb.Context(max_triangles=150_000)
+        ctx.set_option(rtb.OPT_FRAME_OVERLAP, overlap)
+        ctx.set_option(rtb.OPT_TILE_COUNT, tiles)
+        ctx.set_option(rtb.OPT_TILE_RANK, tiles - 1)
+        ctx.resize(w, h, 2)
+        ctx.upload_scene(scene, None)
+        ctx.build_accel(rtb.ACCEL_BVH)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0, 0, 13.9), flags=2))
+        pins = [torch.empty(w * h, dtype=torch.int32).pin_memory() for _ in range(2)]
+        out = []
+        seed = rtb.make_seed((1.0, 5.0))
+        ctx.upload(rtb.BUF_SEED, seed)
+        for k in range(14):
+            if k in (5, 6, 7):   # the host rewrites the first 20 bytes of Seed, as CompositeTask::update does every frame
+                now = ctx.readback(rtb.TGT_SEED).copy() if k == 5 else None
+                s2 = rtb.make_seed((1.0 + k, 5.0))
+                ctx.upload(rtb.BUF_SEED, s2[:20])
+            if k == 9:       # moved spheres: an upload the recorded launches need not know about
+                sph = base["spheres"].view(np.float32).reshape(-1, 4).copy()
+                sph[:, 1] += 0.5
+                ctx.upload(rtb.BUF_SPHERES, sph.view(np.uint8).reshape(-1))
+            if k == 11:      # per-pass dispatches and a rays-in call between recorded frames
+                ctx.dispatch(rtb.PASS_INIT)
+                ctx.dispatch(rtb.PASS_RAYGEN)
+                out.append(ctx.trace_rays(rays)[0].copy())
+            ctx.dispatch(rtb.PASS_FRAME)
+            ctx.readback_async_into(rtb.TGT_RGBA8, pins[k & 1].data_ptr(), w * h * 4)
+            if k in (3, 8, 12):
+                out.append(ctx.readback(rtb.TGT_DIR_T).copy())
+                out.append(ctx.readback(rtb.TGT_SEED).copy())
+            if k >= 1 and k % 2 == 0:
+                ctx.readback_wait()
+                out.append(pins[k & 1].numpy().copy())
+        ctx.readback_wait()
+        out += [ctx.readback(t).copy() for t in (rtb.TGT_DIR_T, rtb.TGT_UV_NORMAL, rtb.TGT_SHADOW_BITS, rtb.TGT_LIGHTING, rtb.TGT_ACCUM, rtb.TGT_RGBA8, rtb.TGT_SEED)]
+        ctx.close()
+        return out
+
+    a, b = run(0), run(1)
+    assert len(a) == len(b)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert np.array_equal(np.asarray(x).view(np.uint8), np.asarray(y).view(np.uint8)), f"output {i} differs between overlapped and sequential frames"
