@@ -647,12 +647,20 @@ def main():
         kernels_per_frame = path.kernel_launches
     else:   # init, fused camera-ray launch (or raygen, nearest hit, finish), shadow-ray set-up, occlusion, lighting + composite
         kernels_per_frame = (5 if info.primary_packets == 3 else 7) * spp
+    gather_path = "NCCL gather to rank 0 + rtb_untile + one device-to-host copy (copy engine) over rank 0's PCIe link, all on a second stream under the next frame"
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 168 * world, "d2h_bytes_per_step": w * h * 4, "ms_per_step": e2e_ms / args.steps,
-           "path": "NCCL gather to rank 0 + rtb_untile + one device-to-host copy (copy engine) over rank 0's PCIe link, all on a second stream under the next frame" if world > 1
-                   else "rtb_readback_async of the rgba8 frame into pinned memory (copy engine, overlaps the next frame)"}
+           "path": gather_path if world > 1 else "rtb_readback_async of the rgba8 frame into pinned memory (copy engine, overlaps the next frame)"}
     if e2e_host_ms is not None:
-        e2e["via_present_host"] = {"value": rays_per_frame / (e2e_host_ms / args.steps * 1e-3) / 1e6, "ms_per_step": e2e_host_ms / args.steps,
-                                   "path": "no gather: every rank's rtb_present_host kernel writes its tiles into ONE page-locked host frame in shared memory (%d PCIe links); the kernel waits for SM slots behind the next frame's persistent launches" % world}
+        # two routes from N GPUs to one host frame, both through the public API and timed alike: the faster one is the e2e number
+        # (rank 0's single PCIe link bounds the gather route from N = 8 on), the other is listed beside it
+        host = {"value": rays_per_frame / (e2e_host_ms / args.steps * 1e-3) / 1e6, "ms_per_step": e2e_host_ms / args.steps,
+                "path": "no gather: every rank's rtb_present_host kernel writes its tiles into ONE page-locked host frame in shared memory (%d PCIe links); the kernel takes SM slots between the next frame's persistent launches" % world}
+        gather = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "path": gather_path}
+        if host["value"] > gather["value"]:
+            e2e.update(host)
+            e2e["via_nccl_gather"] = gather
+        else:
+            e2e["via_present_host"] = host
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
