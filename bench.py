@@ -540,10 +540,12 @@ def main():
         ctx.set_option(rtb.OPT_FRAME_GRAPH, 0 if args.no_graph else 1)
         t_primary, t_shadow = float(phases[2]) * 1e-3, float(phases[5]) * 1e-3
     else:
-        for _ in range(3):
+        ctx.set_option(rtb.OPT_FRAME_OVERLAP, 0)   # the launches one after the other, so that each can be timed alone (the timed frames run
+        for _ in range(3):                         # the occlusion launch of depth d beside the nearest-hit launch of depth d + 1)
             ctx.path_frame(bounces)
         ctx.sync()
         path = ctx.path_stats()
+        ctx.set_option(rtb.OPT_FRAME_OVERLAP, 0 if args.no_overlap else 1)
         t_primary, t_shadow = path.closest_ms * 1e-3, path.shadow_ms * 1e-3
     barrier()
 
@@ -675,7 +677,7 @@ def main():
                            "sah_cost": info.sah_cost, "build_ms": info.build_ms, "leaf_node_extent": info.leaf_node_extent, "bytes": bvh_bytes,
                            "builder": {0: "host (binned SAH, optimal collapse)", 1: "device (Morton sort, radix tree, greedy collapse)"}.get(info.builder, "?")},
                    "primary_packets": {0: "per ray", 1: "union packets", 3: "frustum packets"}.get(info.primary_packets, str(info.primary_packets)), "packets_option": args.packets,
-                   "shadow_order": args.shadow_order, "frame_lanes": args.lanes, "frame_graph": not args.no_graph, "frame_overlap": not (args.no_overlap or args.no_graph or args.lanes == 2 or bool(bounces)),
+                   "shadow_order": args.shadow_order, "frame_lanes": args.lanes, "frame_graph": not args.no_graph, "frame_overlap": (not args.no_overlap) if bounces else not (args.no_overlap or args.no_graph or args.lanes == 2),
                    "phase_note": "phase_ms_rank0 is measured with direct launches in one lane (back to back); the timed frames replay the frame's CUDA graphs" if not args.no_graph else "direct launches",
                    "phase_ms_rank0": {k: float(v) for k, v in zip(["init", "raygen", "trace_primary", "finish", "shadowgen", "trace_shadow", "shade", "total"], phases)}},
         "clocks": clocks,

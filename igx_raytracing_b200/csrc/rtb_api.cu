@@ -1223,8 +1223,11 @@ int rtb_path_frame(rtb_ctx* c, uint32_t bounces) {
     RTB_BIND(c);
     if (bounces > PATH_MAX_BOUNCES) return fail(c, RTB_ERR_ARG, "rtb_path_frame: at most 15 bounces");
     { const int rc = checkReady(c); if (rc) return rc; }
-    { const int rc = quiesce(c); if (rc) return rc; }
-    { const int rc = waitCopy(c, {RTB_TGT_SEED, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
+    // consecutive path frames overlap like recorded RTB_PASS_FRAMEs (overlappedFrame): init + depth 0 of frame k+1 on the front stream,
+    // on the other set of G-buffer / wavefront / Seed-snapshot buffers, under the deep, latency-bound launches of frame k
+    const bool ov = c->overlapOpt && !c->countersOn && !c->releaseBuild && c->fm.localSlots;
+    if (!ov) { const int rc = quiesce(c); if (rc) return rc; }
+    { const int rc = waitCopy(c, {RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}); if (rc) return rc; }
     const uint32_t slots = c->fm.localSlots, depths = bounces + 1;
     RTB_CUDA(c, c->pathT.alloc(slots)); RTB_CUDA(c, c->pathL.alloc(slots)); RTB_CUDA(c, c->pathDirect.alloc(slots));
     for (int k = 0; k < 2; ++k) { RTB_CUDA(c, c->pathRays[k].alloc(slots)); RTB_CUDA(c, c->pathSlots[k].alloc(slots)); }
@@ -1247,35 +1250,70 @@ int rtb_path_frame(rtb_ctx* c, uint32_t bounces) {
     RTB_CUDA(c, cudaEventRecord(evBegin, c->stream));
     RTB_CUDA(c, cudaMemsetAsync(c->pathCounts.p, 0, c->pathCounts.bytes(), c->stream));
     if (c->countersOn) RTB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(TraceCounters), c->stream));
-    launch_init(c->seed.p, c->stream); ++launches;
-    // depth 0: the reference's G-buffer, by the launches RTB_PASS_FRAME uses
-    RTB_CUDA(c, cudaEventRecord(ev[0], c->stream));
-    { const int rc = passRaygen(c, false); if (rc) return rc; }
-    RTB_CUDA(c, cudaEventRecord(ev[1], c->stream));
-    launches += (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt) ? 1u : 3u;
-    auto shadows = [&](uint32_t d) -> int {   // the shadow rays of depth d's vertices, then their direct terms
-        const RayQueue sq = shadowQ(d);
-        RTB_CUDA(c, cudaEventRecord(ev[4 * d + 2], c->stream));
-        launch_occlusion_others(sv, sq.rays, slots, c->pathOccA.p, c->stream, sq.count);
-        launch_trace_any_bytes(sv, sq.rays, slots, c->pathOccB.p, c->lane[0].workCounter.p, c->stream, cc ? cc + 1 : nullptr, sq.count);
-        RTB_CUDA(c, cudaEventRecord(ev[4 * d + 3], c->stream));
-        launch_path_shadow_resolve(sq, slots, c->pathOccA.p, c->pathOccB.p, pb, c->stream);
-        launches += 3;
-        return RTB_OK;
-    };
-    launch_path_start(c->fm, sv, &c->camera, c->seed.p, bounces, c->dirT.p, c->uvN.p, pb, shadowQ(0), closestQ(1), c->stream); ++launches;
-    { const int rc = shadows(0); if (rc) return rc; }
-    for (uint32_t d = 1; d < depths; ++d) {
-        const RayQueue in = closestQ(d);
-        RTB_CUDA(c, cudaEventRecord(ev[4 * d], c->stream));
-        launch_trace_closest(sv, in.rays, slots, c->lane[0].hits.p, c->lane[0].workCounter.p, cc, PACKETS_OFF, c->stream, in.count);
-        RTB_CUDA(c, cudaEventRecord(ev[4 * d + 1], c->stream));
-        launch_path_vertex(c->fm, sv, &c->camera, c->seed.p, d, bounces, in, c->lane[0].hits.p, pb, shadowQ(d), closestQ(d + 1), c->stream);
-        launches += 2;
-        const int rc = shadows(d); if (rc) return rc;
+    struct SeedUse { rtb_ctx* c; ~SeedUse() { c->seedUse = nullptr; } } seedGuard{c};   // every return below drops the snapshot again
+    cudaStream_t back = c->stream;
+    int set = 0;
+    if (ov) {
+        { const int rc = prepareOverlap(c); if (rc) return rc; }
+        swapSets(c);
+        set = c->setIndex;
+        c->seedUse = c->seedSnap.p + set;
+        if (c->frontNeedsBack) {
+            RTB_CUDA(c, cudaEventRecord(c->evJoinB, back));
+            RTB_CUDA(c, cudaStreamWaitEvent(c->frontStream, c->evJoinB, 0));
+            c->frontNeedsBack = false;
+        } else if (c->backDoneSet[set])
+            RTB_CUDA(c, cudaStreamWaitEvent(c->frontStream, c->evBackDone[set], 0));
+        c->stream = c->frontStream;   // init + depth 0 are launched by the pass functions on the context's current stream
     }
-    launch_path_resolve(c->fm, sv, &c->camera, c->seed.p, pb, c->accum.p, c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, c->stream); ++launches;
+    int rcFront = waitCopy(c, {RTB_TGT_SEED});
+    if (!rcFront) {
+        launch_init(c->seed.p, c->stream, c->seedUse); ++launches;
+        // depth 0: the reference's G-buffer, by the launches RTB_PASS_FRAME uses
+        if (cudaEventRecord(ev[0], c->stream) != cudaSuccess) rcFront = RTB_ERR_CUDA;
+        if (!rcFront) rcFront = passRaygen(c, false);
+        if (!rcFront && cudaEventRecord(ev[1], c->stream) != cudaSuccess) rcFront = RTB_ERR_CUDA;
+    }
+    c->stream = back;
+    if (rcFront) return rcFront == RTB_ERR_CUDA ? cudaFail(c, cudaGetLastError(), "rtb_path_frame: depth 0") : rcFront;
+    if (ov) {
+        RTB_CUDA(c, cudaEventRecord(c->evFrontDone[set], c->frontStream));
+        RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evFrontDone[set], 0));
+        c->frontDirty = false;
+    }
+    launches += (c->lastPrimaryPackets == PACKETS_FRUSTUM && !c->countersOn && c->fuseOpt) ? 1u : 3u;
+    // The occlusion launches of depth d and the nearest-hit launch of depth d + 1 both consume what vertex d produced and touch no
+    // common buffer: with RTB_OPT_FRAME_OVERLAP they run side by side on two streams — the deeper launches hold a few thousand
+    // rays and are bound by the longest ray's chain of dependent fetches, not by throughput.  The path state is still updated in
+    // the order of the definition: shadow terms of depth d, then vertex d + 1.
+    const bool sideBySide = c->overlapOpt && !c->countersOn && depths > 1;
+    if (sideBySide) { const int rc = prepareLanes(c); if (rc) return rc; }
+    launch_path_start(c->fm, sv, &c->camera, seedFor(c), bounces, c->dirT.p, c->uvN.p, pb, shadowQ(0), closestQ(1), c->stream); ++launches;
+    for (uint32_t d = 0; d < depths; ++d) {
+        const bool more = d + 1 < depths;
+        const bool fork = sideBySide && more;
+        cudaStream_t so = fork ? c->laneStream : c->stream;
+        if (fork) { const int rc = forkLanes(c); if (rc) return rc; }
+        const RayQueue sq = shadowQ(d);
+        RTB_CUDA(c, cudaEventRecord(ev[4 * d + 2], so));
+        launch_occlusion_others(sv, sq.rays, slots, c->pathOccA.p, so, sq.count);
+        launch_trace_any_bytes(sv, sq.rays, slots, c->pathOccB.p, fork ? c->lane[1].workCounter.p : c->lane[0].workCounter.p, so, cc ? cc + 1 : nullptr, sq.count);
+        RTB_CUDA(c, cudaEventRecord(ev[4 * d + 3], so));
+        launches += 2;
+        const RayQueue in = more ? closestQ(d + 1) : RayQueue{};
+        if (more) {
+            RTB_CUDA(c, cudaEventRecord(ev[4 * (d + 1)], c->stream));
+            launch_trace_closest(sv, in.rays, slots, c->lane[0].hits.p, c->lane[0].workCounter.p, cc, PACKETS_OFF, c->stream, in.count);
+            RTB_CUDA(c, cudaEventRecord(ev[4 * (d + 1) + 1], c->stream));
+            ++launches;
+        }
+        if (fork) { const int rc = joinLanes(c); if (rc) return rc; }
+        launch_path_shadow_resolve(sq, slots, c->pathOccA.p, c->pathOccB.p, pb, c->stream); ++launches;
+        if (more) { launch_path_vertex(c->fm, sv, &c->camera, seedFor(c), d + 1, bounces, in, c->lane[0].hits.p, pb, shadowQ(d + 1), closestQ(d + 1 + 1), c->stream); ++launches; }
+    }
+    launch_path_resolve(c->fm, sv, &c->camera, seedFor(c), pb, c->accum.p, c->rgba8.p, c->tileCount > 1 ? c->rgba8Tiled.p : nullptr, c->stream); ++launches;
     RTB_CUDA(c, cudaEventRecord(evEnd, c->stream));
+    if (ov) { RTB_CUDA(c, cudaEventRecord(c->evBackDone[set], c->stream)); c->backDoneSet[set] = true; }
     RTB_CUDA(c, cudaGetLastError());
     c->pathDepths = depths; c->pathBounces = bounces; c->pathKernelLaunches = launches; c->pathTimed = true;
     return RTB_OK;

@@ -112,3 +112,54 @@ def test_path_frame_10m_mesh_bvh_equals_brute_on_a_tile_subsample(rtb):
     bad = int((a["accum"][..., :3].view(np.uint32) != b["accum"][..., :3].view(np.uint32)).any(-1).sum())
     assert bad <= 4, f"{bad} pixels differ between the BVH and the linear loop"
     assert np.array_equal(a["tiled"], b["tiled"]) or bad > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tile", [None, (2, 3)])
+def test_overlapped_path_frames_identical(rtb, tile):
+    """RTB_OPT_FRAME_OVERLAP for path frames: init + depth 0 of frame k+1 on the front stream under the deeper launches of frame k, and
+    the occlusion launch of depth d beside the nearest-hit launch of depth d+1.  Accumulating path frames mixed with RTB_PASS_FRAME,
+    seed uploads and read-backs: the same bytes as with one launch after the other."""
+    import torch
+    w, h = 480, 270
+    scene = dict(triangles=rtb.gen_heightfield(245, 0xB200), lights=rtb.niels_scene()["lights"][:32],
+                 materials=rtb.pack_material((0.8, 0.8, 0.8), (0.05, 0.05, 0.05), (0, 0, 0), 0.0, 1.0, 1.0),
+                 material_indices=np.zeros(2 * 245 * 245, np.uint32), info=np.array([1, 1, 2 * 245 * 245, 0, 0, 0, 1, 0, 0], np.uint32))
+
+    def run(overlap):
+        ctx = rtb.Context(max_triangles=2 * 245 * 245)
+        ctx.set_option(rtb.OPT_FRAME_OVERLAP, overlap)
+        if tile:
+            ctx.set_option(rtb.OPT_TILE_COUNT, tile[1])
+            ctx.set_option(rtb.OPT_TILE_RANK, tile[0])
+        ctx.resize(w, h, 1)
+        ctx.upload_scene(scene, synthetic_sky())
+        ctx.build_accel(rtb.ACCEL_BVH)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(0.0, 7.5, 0.0), pitch=1.5707964, left_fov=120.0, right_fov=120.0, flags=2))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((4.0, 1.0)))
+        pins = [torch.empty(w * h, dtype=torch.int32).pin_memory() for _ in range(2)]
+        out = []
+        for k in range(10):
+            if k == 4:
+                ctx.upload(rtb.BUF_SEED, rtb.make_seed((9.0, 2.0))[:20])
+            if k == 6:
+                ctx.dispatch(rtb.PASS_FRAME)
+                out.append(ctx.readback(rtb.TGT_SHADOW_BITS).copy())
+            ctx.path_frame(4 if k != 7 else 1)
+            ctx.readback_async_into(rtb.TGT_RGBA8, pins[k & 1].data_ptr(), w * h * 4)
+            if k in (2, 8):
+                out.append(ctx.readback(rtb.TGT_DIR_T).copy())
+                out.append(np.array(ctx.path_stats().as_dict()["closest_rays_at_depth"]))
+            if k % 3 == 2:
+                ctx.readback_wait()
+                out.append(pins[k & 1].numpy().copy())
+        ctx.readback_wait()
+        out += [ctx.readback(t).copy() for t in (rtb.TGT_DIR_T, rtb.TGT_UV_NORMAL, rtb.TGT_ACCUM, rtb.TGT_RGBA8, rtb.TGT_SEED)]
+        ctx.close()
+        return out
+
+    a, b = run(0), run(1)
+    assert len(a) == len(b)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert np.array_equal(np.asarray(x).view(np.uint8), np.asarray(y).view(np.uint8)), f"output {i} differs between overlapped and sequential path frames"
+    assert a[1][1] > 1000, "the bounce rays must hit the field again"
