@@ -90,6 +90,12 @@ struct rtb_ctx {
     float historyAlpha = 0.0f;        // RTB_OPT_HISTORY_ALPHA (float bits): 0 = off
     bool historyValid = false;        // false: the next lighting pass starts the History texture (alpha 1)
     DevBuf<uint32_t> lightTileCount, lightTileList; DevBuf<uint2> history;
+    // what lighting.comp derives per (pixel, sample) from the frame size alone (LightsView.lightCache); refilled when the key changes
+    DevBuf<float4> lightCache;
+    struct LightCacheKey { uint32_t w = 0, h = 0, samples = 0, rank = 0, count = 0, kind = 0; uint64_t lightEpoch = 0;
+                           bool operator==(const LightCacheKey& o) const { return w == o.w && h == o.h && samples == o.samples && rank == o.rank && count == o.count && kind == o.kind && lightEpoch == o.lightEpoch; } } lightCacheKey;
+    uint64_t light0Epoch = 1;         // bumped when lights[0] is rewritten
+    uint32_t lightCacheOpt = 1;       // RTB_OPT_LIGHT_CACHE
     uint32_t bitsLayers = 0;          // layers the shadow-word buffer currently holds
     // RTB_PASS_FRAME as two CUDA graphs (everything before the shade launch / the shade launch), replayed while nothing the
     // recorded launches hold by value has changed: `stamp` counts those changes
@@ -408,6 +414,25 @@ int lightsView(rtb_ctx* c, LightsView& lv, bool forLighting) {
     lv.tilesX = (c->width + 15u) / 16u;
     lv.lightBegin = 0; lv.lightEnd = c->info.lightCount;
     if (lv.mode == 2u) { lv.tileCount = c->lightTileCount.p; lv.tileList = c->lightTileList.p; }
+    if (forLighting && c->lightCacheOpt && c->width && c->info.lightCount) {
+        // kind 2 (the direction itself) for the reference's one directional light, kind 1 (the random pair) otherwise; none beyond 1.5 GB
+        rtb_ctx::LightCacheKey key;
+        key.w = c->width; key.h = c->height; key.samples = c->samples; key.rank = c->tileRank; key.count = c->tileCount;
+        key.kind = (!lv.mode && (c->light0.colorBType >> 16) != LIGHT_POINT) ? 2u : 1u;
+        key.lightEpoch = key.kind == 2u ? c->light0Epoch : 0u;
+        const size_t entries = (size_t)c->width * c->height * c->samples;
+        if (entries * sizeof(float4) <= (3ull << 29)) {
+            if (!(key == c->lightCacheKey) || !c->lightCache.p) {
+                if (!c->capturing) {   // (a recorded frame follows a direct one with the same state: the cache is there by then)
+                    if (c->lightCache.count < entries) { RTB_CUDA(c, cudaStreamSynchronize(c->stream)); RTB_CUDA(c, c->lightCache.alloc(entries)); }
+                    launch_light_cache(c->fm, sceneView(c), c->samples, key.kind, c->lightCache.p, c->stream);
+                    c->lightCacheKey = key;
+                    ++c->stamp;   // recorded launches hold the cache kind by value
+                }
+            }
+            if (key == c->lightCacheKey && c->lightCache.p) { lv.cacheKind = key.kind; lv.lightCache = c->lightCache.p; }
+        }
+    }
     if (forLighting && c->historyAlpha > 0.0f) {
         const size_t px = (size_t)c->width * c->height;
         if (c->history.count < px) { RTB_CUDA(c, cudaStreamSynchronize(c->stream)); RTB_CUDA(c, c->history.alloc(px)); c->historyValid = false; }
@@ -573,6 +598,7 @@ int framePartB(rtb_ctx* c, bool mark) {
         if (mark) RTB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
         return RTB_OK;
     }
+    { LightsView lv; if ((rc = lightsView(c, lv, true))) return rc; }   // (fills the light cache, if it must, before the lanes fork)
     if ((rc = forkLanes(c))) return rc;
     for (int lane = 0; lane < 2; ++lane) if ((rc = passShade(c, SHADE_BOTH, lane))) return rc;
     return joinLanes(c);
@@ -754,7 +780,7 @@ void rtb_destroy(rtb_ctx* c) {
     c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release(); c->nodeBox.release(); c->maxBits.release(); c->areaSums.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->lane[0].release(); c->lane[1].release(); c->counters.release();
-    c->lightTileCount.release(); c->lightTileList.release(); c->history.release();
+    c->lightTileCount.release(); c->lightTileList.release(); c->history.release(); c->lightCache.release();
     for (int k = 0; k < 2; ++k) { c->primTree[k].release(); c->primHitS[k].release(); c->primHitC[k].release(); }
     c->rinPrimS.release(); c->rinPrimC.release();
     if (c->graphA) cudaGraphExecDestroy(c->graphA);
@@ -811,6 +837,7 @@ int rtb_set_option(rtb_ctx* c, rtb_option opt, uint32_t value) {
         }
         case RTB_OPT_FRAME_GRAPH: c->graphOpt = value ? 1u : 0u; return RTB_OK;
         case RTB_OPT_FRAME_OVERLAP: c->overlapOpt = value ? 1u : 0u; return RTB_OK;
+        case RTB_OPT_LIGHT_CACHE: c->lightCacheOpt = value ? 1u : 0u; return RTB_OK;
         case RTB_OPT_FRAME_LANES:
             if (value < 1 || value > 2) return fail(c, RTB_ERR_ARG, "RTB_OPT_FRAME_LANES: 1 or 2");
             c->lanesOpt = value; return RTB_OK;
@@ -904,7 +931,7 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
     if (id == RTB_BUF_TRIANGLES) { std::memcpy(c->triangleMirror.data() + off, src, bytes); c->accelValid = false; ++c->stamp; }
     if (id == RTB_BUF_SPHERES) c->primTree[0].dirty = true;
     if (id == RTB_BUF_CUBES) c->primTree[1].dirty = true;
-    if (id == RTB_BUF_LIGHTS && off < sizeof(LightRec)) ++c->stamp;   // lights[0] picks the occlusion rays' sort key
+    if (id == RTB_BUF_LIGHTS && off < sizeof(LightRec)) { ++c->stamp; ++c->light0Epoch; }   // lights[0] picks the occlusion rays' sort key and fills the light cache
     if (id == RTB_BUF_LIGHTS && off < sizeof(LightRec)) std::memcpy(reinterpret_cast<uint8_t*>(&c->light0) + off, src, std::min(bytes, sizeof(LightRec) - off));
     // pageable source: cudaMemcpyAsync stages it before returning, so the caller may reuse src at once (like GPUBuffer::flush)
     RTB_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, src, bytes, cudaMemcpyHostToDevice, c->stream));

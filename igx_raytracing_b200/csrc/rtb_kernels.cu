@@ -833,14 +833,24 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
             const vec3 v = normalize(dxyz);
             const float NdotV = fmaxf(dot(v, -n), 0.0f);
             const vec2 loc = mk2((float)x, (float)y);
-            const vec2 uv = (loc + rand2(loc + mk2(0.0f, 0.0f))) / 128.0f;   // Seed is unbound in lighting.comp: reads as zero (decree D8)
+            vec2 uv = mk2(0.0f, 0.0f);
+            if (!lv.cacheKind) uv = (loc + rand2(loc + mk2(0.0f, 0.0f))) / 128.0f;   // Seed is unbound in lighting.comp: reads as zero (decree D8)
+            const size_t plane = (size_t)fm.w * fm.h;
             const uint32_t bit = 1u << ((x & 15u) | ((y & 1u) << 4));
             if (!EXT || lv.mode == 0u) {
                 const LightRec l0 = sv.lights[0];
                 for (uint32_t s = 0; s < samples; ++s) {
-                    const vec2 random = rand2(uv + hammersley(s, samples));
                     const uint32_t word = __ldg(bits + indexToLight(x, y, fm.w, fm.h, s));
-                    if (!(word & bit)) light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, l0, hitPos, n, v, NdotV, random);
+                    if (word & bit) continue;
+                    if (lv.cacheKind == 2u) {   // the direction to the directional light 0 as getDirToLight returns it, from the cache
+                        const float4 cv = __ldg(lv.lightCache + s * plane + px);
+                        light = light + shadeLightDir(F0, m.albedo, m.roughness, m.metallic, l0, mk3(cv.x, cv.y, cv.z), 1.0f, n, v, NdotV);
+                    } else {
+                        vec2 random;
+                        if (lv.cacheKind == 1u) { const float4 cv = __ldg(lv.lightCache + s * plane + px); random = mk2(cv.x, cv.y); }
+                        else random = rand2(uv + hammersley(s, samples));
+                        light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, l0, hitPos, n, v, NdotV, random);
+                    }
                 }
                 light = light / (float)samples * (float)sv.info.lightCount;
             } else {
@@ -856,7 +866,9 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
                     const uint32_t L = list ? __ldg(list + e) : e;
                     const LightRec ll = sv.lights[L];
                     for (uint32_t s = 0; s < samples; ++s) {
-                        const vec2 random = rand2(uv + hammersley(s, samples));
+                        vec2 random;
+                        if (lv.cacheKind == 1u) { const float4 cv = __ldg(lv.lightCache + s * plane + px); random = mk2(cv.x, cv.y); }
+                        else random = rand2(uv + hammersley(s, samples));
                         const uint32_t word = __ldg(bits + indexToLight(x, y, fm.w, fm.h, L * samples + s));
                         if (!(word & bit)) light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, ll, hitPos, n, v, NdotV, random);
                     }
@@ -909,6 +921,29 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
     if (rgba8) rgba8[px] = out;
     if (rgba8Tiled) rgba8Tiled[tiledSlot(fm, i)] = out;
 }
+// LightsView.lightCache: what lighting.comp computes per (pixel, sample) before it looks at the hit — the same expressions as k_shade
+__global__ void __launch_bounds__(256) k_light_cache(const FrameMap fm, const SceneView sv, uint32_t samples, uint32_t kind, float4* __restrict__ cache) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= fm.localSlots * samples) return;
+    const uint32_t s = j / fm.localSlots, i = j - s * fm.localSlots;
+    uint32_t x, y;
+    if (!slotToPixel(fm, i, x, y)) return;
+    const vec2 loc = mk2((float)x, (float)y);
+    const vec2 uv = (loc + rand2(loc + mk2(0.0f, 0.0f))) / 128.0f;
+    const vec2 random = rand2(uv + hammersley(s, samples));
+    float4 out = make_float4(random.x, random.y, 0.0f, 0.0f);
+    if (kind == 2u) {
+        float brightness, dist;
+        const vec3 l = getDirToLight(sv.lights[0], mk3(0.0f, 0.0f, 0.0f), brightness, dist, random);   // directional: the position is not used
+        out = make_float4(l.x, l.y, l.z, 0.0f);
+    }
+    cache[(size_t)s * fm.w * fm.h + (size_t)y * fm.w + x] = out;
+}
+void launch_light_cache(const FrameMap& fm, const SceneView& sv, uint32_t samples, uint32_t kind, float4* cache, cudaStream_t st) {
+    const uint32_t n = fm.localSlots * samples;
+    if (n) k_light_cache<<<(n + 255) / 256, 256, 0, st>>>(fm, sv, samples, kind, cache);
+}
+
 void launch_shade(int what, const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const SeedRec* seed, uint32_t samples,
                   const float4* dirT, const float4* uvN, const uint32_t* bits, uint2* lighting, float4* accum,
                   uint32_t* rgba8, uint32_t* rgba8Tiled, cudaStream_t st, const LightsView* lights) {

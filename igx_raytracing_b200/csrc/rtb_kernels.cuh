@@ -105,7 +105,14 @@ struct LightsView {
     uint32_t lightBegin, lightEnd; // shadow-ray generation only: the lights of this launch (the queue is filled in chunks of lights)
     float historyAlpha;            // > 0: lighting = history * (1 - a) + lighting * a through `history` (rgba16f), stored in both
     uint2* history;
+    // lighting.comp derives its random pair from the pixel, the sample index and the sample count alone (its Seed block is unbound
+    // and reads as zero: decree D8), so the pair — and, for a directional light 0, the light direction it yields — is the same in
+    // every frame of a given size: kept per (sample, pixel) instead of four exact-reduction binary64 sines per pixel and frame.
+    //   cacheKind 0: none, computed in the kernel; 1: xy = random; 2: xyz = normalised direction to (directional) light 0
+    uint32_t cacheKind;
+    const float4* lightCache;      // [sample * w * h + y * w + x]
 };
+void launch_light_cache(const FrameMap& fm, const SceneView& sv, uint32_t samples, uint32_t kind, float4* cache, cudaStream_t s);
 void launch_light_tiles(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const float4* dirT, uint32_t* tileCount, uint32_t* tileList, cudaStream_t s);
 // shadow rays of every light in [lv.lightBegin, lv.lightEnd) for every hit pixel and sample, appended to `queue`
 // (slot id = layer * localSlots + slot); occluders other than triangles are answered here

@@ -330,10 +330,9 @@ RTB_DI float ndfGGX(vec3 n, vec3 h, float roughness) {                          
 RTB_DI float geomSchlickGGX(float NdotV, float k) { return NdotV / (NdotV * (1.0f - k) + k); }
 RTB_DI float pow5(float f) { float f2 = f * f; return f2 * f2 * f; }
 
-RTB_DI vec3 shadeLight(vec3 F0, vec3 albedo, float roughness, float metallic, const LightRec& light, vec3 pos,
-                       vec3 n, vec3 v, float NdotV, vec2 random) {                                          // :135-159, :64-94
-    float brightness, dst;
-    vec3 l = getDirToLight(light, pos, brightness, dst, random);
+// the Cook-Torrance term of one light once its direction and brightness are known (the body of shadeLight after getDirToLight)
+RTB_DI vec3 shadeLightDir(vec3 F0, vec3 albedo, float roughness, float metallic, const LightRec& light, vec3 l, float brightness,
+                          vec3 n, vec3 v, float NdotV) {                                                    // :139-159, :64-94
     float k = roughness + 1.0f;
     k *= k / 8.0f;
     float NdotL = fmaxf(dot(n, l), 0.0f);
@@ -347,6 +346,12 @@ RTB_DI vec3 shadeLight(vec3 F0, vec3 albedo, float roughness, float metallic, co
     vec3 kD = (1.0f - F) * (1.0f - metallic);
     vec3 color = kD * albedo + kS;
     return color * unpackColor3(light.colorRG, light.colorBType) * brightness * NdotL;
+}
+RTB_DI vec3 shadeLight(vec3 F0, vec3 albedo, float roughness, float metallic, const LightRec& light, vec3 pos,
+                       vec3 n, vec3 v, float NdotV, vec2 random) {                                          // :135-159
+    float brightness, dst;
+    vec3 l = getDirToLight(light, pos, brightness, dst, random);
+    return shadeLightDir(F0, albedo, roughness, metallic, light, l, brightness, n, v, NdotV);
 }
 
 struct MatU { vec3 albedo, ambient, emissive; float metallic, roughness; };

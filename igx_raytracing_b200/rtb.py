@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("RTB_LIB", os.path.join(HERE, "librtb200.so"))   # RTB
 PASS_INIT, PASS_RAYGEN, PASS_SHADOW, PASS_LIGHTING, PASS_COMPOSITE, PASS_FRAME = range(6)
 TGT_DIR_T, TGT_UV_NORMAL, TGT_SHADOW_BITS, TGT_LIGHTING, TGT_ACCUM, TGT_RGBA8, TGT_SEED, TGT_RGBA8_TILED, TGT_ACCEL_NODES, TGT_ACCEL_TRIANGLES = range(10)
 ACCEL_BRUTE, ACCEL_BVH, ACCEL_BVH2 = 0, 1, 2
-OPT_COUNTERS, OPT_TILE_RANK, OPT_TILE_COUNT, OPT_SHADER_BUILD, OPT_PRIMARY_PACKETS, OPT_FUSE_PRIMARY, OPT_SHADOW_ORDER, OPT_ACCEL_BUILDER, OPT_FRAME_LANES, OPT_FRAME_GRAPH, OPT_LIGHTS, OPT_HISTORY_ALPHA, OPT_PRIMITIVE_TREES, OPT_FRAME_OVERLAP = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13
+OPT_COUNTERS, OPT_TILE_RANK, OPT_TILE_COUNT, OPT_SHADER_BUILD, OPT_PRIMARY_PACKETS, OPT_FUSE_PRIMARY, OPT_SHADOW_ORDER, OPT_ACCEL_BUILDER, OPT_FRAME_LANES, OPT_FRAME_GRAPH, OPT_LIGHTS, OPT_HISTORY_ALPHA, OPT_PRIMITIVE_TREES, OPT_FRAME_OVERLAP, OPT_LIGHT_CACHE = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
 BUILDER_HOST, BUILDER_DEVICE = 0, 1
 SHADER_DEBUG, SHADER_RELEASE = 0, 1
 NO_RAY_HIT = 0xFFFFFFFF

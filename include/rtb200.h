@@ -156,6 +156,12 @@ typedef enum rtb_option {
                                       launches are filled (one rank of eight: 0.65 -> 0.57 ms per 4K soup frame).  Everything else the
                                       API offers is ordered after both streams; pointers from rtb_device_ptr(DIR_T / UV_NORMAL) name the
                                       latest frame's set and are valid until the next RTB_PASS_FRAME.  0: one frame after the other. */
+    RTB_OPT_LIGHT_CACHE = 14,      /* default 1: the random pair lighting.comp derives per pixel and shadow sample depends on the pixel, the
+                                      sample index and the sample count only (its Seed block is unbound: it reads zeros), so it — and for a
+                                      directional light 0 the light direction it yields — is computed once per frame size (and light 0) and
+                                      read back by the lighting pass: 16 bytes per pixel and sample instead of four exact-reduction binary64
+                                      sines (and the sun-disc sample) per pixel and frame.  Same values, same pixels.  Not kept beyond
+                                      1.5 GB.  0: evaluated in the kernel every frame. */
     RTB_OPT_PRIMITIVE_TREES = 12,  /* spheres and cubes stay in the reference's linear loops (ref: res/shaders/trace.glsl:31-40,83-90) while a
                                       type has fewer than this many primitives (default 64; 0 = always); from there on the type gets
                                       an 8-wide tree of its own, built on the device over the primitives' boxes and rebuilt when its

@@ -904,3 +904,54 @@ def test_overlapped_frames_identical(rtb, tiles):
     assert len(a) == len(b)
     for i, (x, y) in enumerate(zip(a, b)):
         assert np.array_equal(np.asarray(x).view(np.uint8), np.asarray(y).view(np.uint8)), f"output {i} differs between overlapped and sequential frames"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["sun_first", "point_first", "all_lights", "tile_rank"])
+def test_light_cache_does_not_change_a_bit(rtb, sky, case):
+    """RTB_OPT_LIGHT_CACHE: lighting.comp's per-pixel random pair (and the direction to a directional light 0) read from a cache
+    filled once per frame size instead of being evaluated every frame.  Cache on == cache off in every target, over several frames,
+    after light 0 was rewritten (a new sun direction: the cached directions are stale) and after a resize."""
+    scene = rtb.niels_scene(0.3)
+    if case == "point_first":
+        lights = np.asarray(scene["lights"]).reshape(3, 32)
+        scene["lights"] = np.concatenate([lights[1], lights[2], lights[0]])   # the host would never order them so; the shaders do not care
+    outs = {}
+    for cache in (1, 0):
+        ctx = rtb.Context()
+        ctx.set_option(rtb.OPT_LIGHT_CACHE, cache)
+        if case == "all_lights":
+            ctx.set_option(rtb.OPT_LIGHTS, 1)
+        if case == "tile_rank":
+            ctx.set_option(rtb.OPT_TILE_COUNT, 3)
+            ctx.set_option(rtb.OPT_TILE_RANK, 1)
+        w, h = 333, 190
+        ctx.resize(w, h, 3)
+        ctx.upload_scene(scene, sky)
+        ctx.build_accel(rtb.ACCEL_BVH)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(6, 5, 12), flags=2))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((2.0, 7.0)))
+        got = []
+        for step in range(3):
+            if step == 1:   # a different first light: same type, other direction / position
+                l0 = np.asarray(scene["lights"]).reshape(-1, 32)[0].copy()
+                if case == "point_first":
+                    l0[:12].view(np.float32)[:] = [1.0, 2.5, 0.5]
+                else:
+                    l0 = rtb.pack_light_directional((0.3, -1.0, 0.4), (0.9, 0.8, 0.7))
+                ctx.upload(rtb.BUF_LIGHTS, np.asarray(l0).view(np.uint8).reshape(-1)[:32])
+            if step == 2:
+                w, h = 200, 120
+                ctx.resize(w, h, 2)
+                ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(6, 5, 12), flags=2))
+            for _ in range(4):
+                ctx.dispatch(rtb.PASS_FRAME)
+            got.append([ctx.readback(t).copy() for t in (rtb.TGT_LIGHTING, rtb.TGT_ACCUM, rtb.TGT_RGBA8)])
+            ctx.dispatch(rtb.PASS_INIT); ctx.dispatch(rtb.PASS_RAYGEN); ctx.dispatch(rtb.PASS_SHADOW); ctx.dispatch(rtb.PASS_LIGHTING)
+            got[-1].append(ctx.readback(rtb.TGT_LIGHTING).copy())
+        ctx.close()
+        outs[cache] = got
+    for step in range(3):
+        for a, b in zip(outs[1][step], outs[0][step]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"{case}, step {step}: the cache changed a target"
+    assert not np.array_equal(outs[1][0][0].view(np.uint8), outs[1][1][0].view(np.uint8)), "the new first light must change the lighting"
