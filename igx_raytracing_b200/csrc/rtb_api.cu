@@ -95,6 +95,7 @@ struct rtb_ctx {
     struct LightCacheKey { uint32_t w = 0, h = 0, samples = 0, rank = 0, count = 0, kind = 0; uint64_t lightEpoch = 0;
                            bool operator==(const LightCacheKey& o) const { return w == o.w && h == o.h && samples == o.samples && rank == o.rank && count == o.count && kind == o.kind && lightEpoch == o.lightEpoch; } } lightCacheKey;
     uint64_t light0Epoch = 1;         // bumped when lights[0] is rewritten
+    DevBuf<SunFrame> sunFrame; uint64_t sunEpoch = 0; bool sunValid = false;   // SceneView.sun0
     uint32_t lightCacheOpt = 1;       // RTB_OPT_LIGHT_CACHE
     uint32_t bitsLayers = 0;          // layers the shadow-word buffer currently holds
     // RTB_PASS_FRAME as two CUDA graphs (everything before the shade launch / the shade launch), replayed while nothing the
@@ -165,6 +166,7 @@ SceneView sceneView(const rtb_ctx* c) {
     v.info = c->info;
     v.nodes = c->nodes.p; v.nodes8 = c->nodes8.p; v.travTris = c->travTris.p; v.nodeCount = c->nodeCount;
     v.releaseBuild = c->releaseBuild;
+    v.sun0 = c->sunValid ? c->sunFrame.p : nullptr;
     v.sphereTree = c->primTree[0].valid ? 1u : 0u; v.cubeTree = c->primTree[1].valid ? 1u : 0u;
     v.useBvh = !c->accelValid ? ACCEL_KIND_BRUTE : (c->accelMode == RTB_ACCEL_BVH ? ACCEL_KIND_CWBVH : (c->accelMode == RTB_ACCEL_BVH2 ? ACCEL_KIND_BVH2 : ACCEL_KIND_BRUTE));
     return v;
@@ -238,6 +240,19 @@ int joinFront(rtb_ctx* c) {
 }
 // ... and the context's stream is about to get work the next FRONT depends on (scene uploads, builds, direct passes, allocations)
 int quiesce(rtb_ctx* c) { c->frontNeedsBack = true; return joinFront(c); }
+
+// SceneView.sun0: the light-only part of a directional lights[0], re-evaluated on the context's stream after lights[0] was rewritten
+// (the launches of a frame in flight precede it on that stream; the front stream's launches do not read lights)
+int ensureSunFrame(rtb_ctx* c) {
+    const bool want = c->lightCacheOpt && (c->light0.colorBType >> 16) != LIGHT_POINT;
+    if (!want) { if (c->sunValid) { c->sunValid = false; ++c->stamp; } return RTB_OK; }
+    if (c->sunValid && c->sunEpoch == c->light0Epoch) return RTB_OK;
+    RTB_CUDA(c, c->sunFrame.alloc(1));
+    launch_sun_frame(c->lights.p, c->sunFrame.p, c->stream);
+    if (!c->sunValid) { c->sunValid = true; ++c->stamp; }   // recorded launches hold the pointer (or its absence) by value
+    c->sunEpoch = c->light0Epoch;
+    return RTB_OK;
+}
 
 // scene counts against the capacities of rtb_create, and the acceleration structure against the triangle buffer:
 // shared by the dispatch path and the rays-in entry points (both index the scene buffers by these counts)
@@ -780,7 +795,7 @@ void rtb_destroy(rtb_ctx* c) {
     c->materialIndices.release(); c->skybox.release(); c->seed.release(); c->nodes.release(); c->nodes8.release(); c->travTris.release(); c->nodeBox.release(); c->maxBits.release(); c->areaSums.release();
     c->dirT.release(); c->uvN.release(); c->accum.release(); c->lighting.release(); c->bits.release(); c->rgba8.release(); c->rgba8Tiled.release();
     c->lane[0].release(); c->lane[1].release(); c->counters.release();
-    c->lightTileCount.release(); c->lightTileList.release(); c->history.release(); c->lightCache.release();
+    c->lightTileCount.release(); c->lightTileList.release(); c->history.release(); c->lightCache.release(); c->sunFrame.release();
     for (int k = 0; k < 2; ++k) { c->primTree[k].release(); c->primHitS[k].release(); c->primHitC[k].release(); }
     c->rinPrimS.release(); c->rinPrimC.release();
     if (c->graphA) cudaGraphExecDestroy(c->graphA);
@@ -1061,6 +1076,7 @@ int rtb_dispatch(rtb_ctx* c, rtb_pass pass) {
     RTB_BIND(c);
     if (pass != RTB_PASS_INIT) { const int rc = checkReady(c); if (rc) return rc; }
     if (pass != RTB_PASS_INIT) { const int rc = ensurePrimTrees(c); if (rc) return rc; }
+    if (pass != RTB_PASS_INIT) { const int rc = ensureSunFrame(c); if (rc) return rc; }
     int rc = RTB_OK;
     if (pass != RTB_PASS_FRAME && (rc = quiesce(c))) return rc;
     switch (pass) {
@@ -1267,6 +1283,7 @@ int rtb_path_frame(rtb_ctx* c, uint32_t bounces) {
     cudaEvent_t* ev = c->pathEv.data();
     cudaEvent_t evBegin = ev[4 * (PATH_MAX_BOUNCES + 1)], evEnd = ev[4 * (PATH_MAX_BOUNCES + 1) + 1];
     { const int rc = ensurePrimTrees(c); if (rc) return rc; }   // depth 0 (passRaygen) uses them
+    { const int rc = ensureSunFrame(c); if (rc) return rc; }
     SceneView sv = sceneView(c);
     sv.sphereTree = sv.cubeTree = 0u;   // the bounce vertices and their shadow rays keep the linear loops
     TraceCounters* cc = c->countersOn ? c->counters.p : nullptr;

@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(256, RTB_SHADOWGEN_MINBLOCKS) k_shadowgen(cons
             const vec2 random = rand2(uv);
             const LightRec light = sv.lights[0];   // lightId = 0 (SH/nv_all.shadow.comp:97)
             float brightness, dist;
-            const vec3 l = getDirToLight(light, hitPos, brightness, dist, random);
+            const vec3 l = getDirToLight(light, hitPos, brightness, dist, random, sv.sun0);
             Ray ray; ray.pos = hitPos; ray.dir = -l;
             float maxDist = -1.0f;
             if (dist >= 0.0f) {
@@ -849,7 +849,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
                         vec2 random;
                         if (lv.cacheKind == 1u) { const float4 cv = __ldg(lv.lightCache + s * plane + px); random = mk2(cv.x, cv.y); }
                         else random = rand2(uv + hammersley(s, samples));
-                        light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, l0, hitPos, n, v, NdotV, random);
+                        light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, l0, hitPos, n, v, NdotV, random, sv.sun0);
                     }
                 }
                 light = light / (float)samples * (float)sv.info.lightCount;
@@ -870,7 +870,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
                         if (lv.cacheKind == 1u) { const float4 cv = __ldg(lv.lightCache + s * plane + px); random = mk2(cv.x, cv.y); }
                         else random = rand2(uv + hammersley(s, samples));
                         const uint32_t word = __ldg(bits + indexToLight(x, y, fm.w, fm.h, L * samples + s));
-                        if (!(word & bit)) light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, ll, hitPos, n, v, NdotV, random);
+                        if (!(word & bit)) light = light + shadeLight(F0, m.albedo, m.roughness, m.metallic, ll, hitPos, n, v, NdotV, random, L == 0u ? sv.sun0 : nullptr);
                     }
                 }
                 light = light / (float)samples;
@@ -921,6 +921,23 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) k_shade(const FrameM
     if (rgba8) rgba8[px] = out;
     if (rgba8Tiled) rgba8Tiled[tiledSlot(fm, i)] = out;
 }
+// SunFrame of lights[0]: the light-only subexpressions of getDirToLight / getSunDirection, evaluated by the same functions
+__global__ void k_sun_frame(const LightRec* __restrict__ lights, SunFrame* __restrict__ out) {
+    const LightRec light = lights[0];
+    vec2 radOrigin = unpackHalf2x16(light.radOrigin);
+    radOrigin = mk2(fmaxf(radOrigin.x, 0.0f), fmaxf(radOrigin.y, 0.0f));
+    const vec3 direction = normalize(decodeNormal(light.dir[0], light.dir[1]));
+    const vec3 bitangent = getPerpendicularVector(direction);
+    const vec3 tangent = cross(bitangent, direction);
+    SunFrame f;
+    f.h = cr_cos(radOrigin.x);
+    f.dir[0] = direction.x; f.dir[1] = direction.y; f.dir[2] = direction.z;
+    f.bitangent[0] = bitangent.x; f.bitangent[1] = bitangent.y; f.bitangent[2] = bitangent.z;
+    f.tangent[0] = tangent.x; f.tangent[1] = tangent.y; f.tangent[2] = tangent.z;
+    *out = f;
+}
+void launch_sun_frame(const LightRec* lights, SunFrame* out, cudaStream_t st) { k_sun_frame<<<1, 1, 0, st>>>(lights, out); }
+
 // LightsView.lightCache: what lighting.comp computes per (pixel, sample) before it looks at the hit — the same expressions as k_shade
 __global__ void __launch_bounds__(256) k_light_cache(const FrameMap fm, const SceneView sv, uint32_t samples, uint32_t kind, float4* __restrict__ cache) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -934,7 +951,7 @@ __global__ void __launch_bounds__(256) k_light_cache(const FrameMap fm, const Sc
     float4 out = make_float4(random.x, random.y, 0.0f, 0.0f);
     if (kind == 2u) {
         float brightness, dist;
-        const vec3 l = getDirToLight(sv.lights[0], mk3(0.0f, 0.0f, 0.0f), brightness, dist, random);   // directional: the position is not used
+        const vec3 l = getDirToLight(sv.lights[0], mk3(0.0f, 0.0f, 0.0f), brightness, dist, random, sv.sun0);   // directional: the position is not used
         out = make_float4(l.x, l.y, l.z, 0.0f);
     }
     cache[(size_t)s * fm.w * fm.h + (size_t)y * fm.w + x] = out;
@@ -1078,7 +1095,7 @@ __global__ void __launch_bounds__(256) k_shadowgen_lights(const FrameMap fm, con
             if (L >= lv.lightBegin && L < lv.lightEnd) {
                 const LightRec light = sv.lights[L];
                 float brightness, dist;
-                const vec3 l = getDirToLight(light, hitPos, brightness, dist, random);
+                const vec3 l = getDirToLight(light, hitPos, brightness, dist, random, L == 0u ? sv.sun0 : nullptr);
                 Ray ray; ray.pos = hitPos; ray.dir = -l;
                 float maxDist = -1.0f;
                 if (dist >= 0.0f) {

@@ -19,7 +19,12 @@ struct FrameMap {
     uint32_t tiledMul, tiledAdd;
 };
 
+// what getSunDirection (SH/rand_util.glsl:66-85) and getDirToLight (SH/light.glsl:127-130) derive from a directional light alone:
+// computed once per upload of lights[0] by k_sun_frame with the shaders' own expressions, read by every pixel afterwards
+struct SunFrame { float h; float dir[3], bitangent[3], tangent[3]; };
+
 struct SceneView {
+    const SunFrame* sun0;         // of lights[0] when it is directional and the frame is current; null: evaluated per pixel
     const TriangleRec* triangles; const float4* spheres; const float* cubes; const float4* planes;
     const LightRec* lights; const MaterialRec* materials; const uint32_t* materialIndices;
     const uint2* skybox; uint32_t skyW, skyH;
@@ -112,6 +117,7 @@ struct LightsView {
     uint32_t cacheKind;
     const float4* lightCache;      // [sample * w * h + y * w + x]
 };
+void launch_sun_frame(const LightRec* lights, SunFrame* out, cudaStream_t s);
 void launch_light_cache(const FrameMap& fm, const SceneView& sv, uint32_t samples, uint32_t kind, float4* cache, cudaStream_t s);
 void launch_light_tiles(const FrameMap& fm, const SceneView& sv, const CameraRec* cam, const float4* dirT, uint32_t* tileCount, uint32_t* tileList, cudaStream_t s);
 // shadow rays of every light in [lv.lightBegin, lv.lightEnd) for every hit pixel and sample, appended to `queue`

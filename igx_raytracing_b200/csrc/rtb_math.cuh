@@ -298,7 +298,18 @@ RTB_DI float smoothstepf(float e0, float e1, float x) {   // reversed edges eval
     return t * t * (3.0f - 2.0f * t);
 }
 
-RTB_DI vec3 getDirToLight(const LightRec& light, vec3 pos, float& brightness, float& dist, vec2 random) {   // :98-133
+// getSunDirection with everything that depends on the light alone taken from `f` (k_sun_frame evaluates those expressions once)
+RTB_DI vec3 getSunDirectionPre(vec2 random, const SunFrame& f) {
+    float h = f.h;
+    float phi = (2.0f * PI_F) * random.x;
+    float z = h + (1.0f - h) * random.y;
+    float sinT = sqrtf(1.0f - z * z);
+    float x = cr_cos(phi) * sinT;
+    float y = cr_sin(phi) * sinT;
+    return mk3(f.bitangent[0], f.bitangent[1], f.bitangent[2]) * x + mk3(f.tangent[0], f.tangent[1], f.tangent[2]) * y + mk3(f.dir[0], f.dir[1], f.dir[2]) * z;
+}
+
+RTB_DI vec3 getDirToLight(const LightRec& light, vec3 pos, float& brightness, float& dist, vec2 random, const SunFrame* sun = nullptr) {   // :98-133
     vec3 l;
     brightness = 1.0f;
     dist = -1.0f;
@@ -313,7 +324,9 @@ RTB_DI vec3 getDirToLight(const LightRec& light, vec3 pos, float& brightness, fl
         float r = radOrigin.x - radOrigin.y;
         float d = fmaxf(dist - radOrigin.y, 0.0f);
         brightness = cr_pow(smoothstepf(r, 0.0f, d), ubits(light.dir[0]));
-    } else
+    } else if (sun)
+        l = getSunDirectionPre(random, *sun);
+    else
         l = getSunDirection(random, normalize(decodeNormal(light.dir[0], light.dir[1])), radOrigin.x);
     return normalize(l);
 }
@@ -348,9 +361,9 @@ RTB_DI vec3 shadeLightDir(vec3 F0, vec3 albedo, float roughness, float metallic,
     return color * unpackColor3(light.colorRG, light.colorBType) * brightness * NdotL;
 }
 RTB_DI vec3 shadeLight(vec3 F0, vec3 albedo, float roughness, float metallic, const LightRec& light, vec3 pos,
-                       vec3 n, vec3 v, float NdotV, vec2 random) {                                          // :135-159
+                       vec3 n, vec3 v, float NdotV, vec2 random, const SunFrame* sun = nullptr) {           // :135-159
     float brightness, dst;
-    vec3 l = getDirToLight(light, pos, brightness, dst, random);
+    vec3 l = getDirToLight(light, pos, brightness, dst, random, sun);
     return shadeLightDir(F0, albedo, roughness, metallic, light, l, brightness, n, v, NdotV);
 }
 

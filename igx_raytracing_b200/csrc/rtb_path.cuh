@@ -47,10 +47,10 @@ RTB_DI VertexOut pathVertex(const SceneView& sv, vec2 uvBase, uint32_t depth, ui
         const LightRec light = sv.lights[0];
         const vec3 F0 = mix(mk3(0.04f, 0.04f, 0.04f), m.albedo, m.metallic);
         const float NdotV = fmaxf(dot(v, -n), 0.0f);
-        const vec3 c = shadeLight(F0, m.albedo, m.roughness, m.metallic, light, pos, n, v, NdotV, random) * (float)sv.info.lightCount;
+        const vec3 c = shadeLight(F0, m.albedo, m.roughness, m.metallic, light, pos, n, v, NdotV, random, sv.sun0) * (float)sv.info.lightCount;
         const vec3 contribution = T * c;
         float brightness, dist;
-        const vec3 l = getDirToLight(light, pos, brightness, dist, random);
+        const vec3 l = getDirToLight(light, pos, brightness, dist, random, sv.sun0);
         float maxDist = -1.0f;
         if (dist >= 0.0f) {
             const vec2 radOrigin = unpackHalf2x16(light.radOrigin);
