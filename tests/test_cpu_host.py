@@ -315,3 +315,23 @@ def test_reference_arm_runs_without_the_product_package():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_python_binding_constants_follow_the_header(rtb):
+    """Every enumerator of include/rtb200.h that the ctypes binding names (options, passes, targets, buffers, accel modes, status
+    codes) carries the header's value: the binding is written by hand."""
+    import os
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "rtb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    enums = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(RTB_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)}
+    assert len(enums) > 40
+    checked = 0
+    for name, value in enums.items():
+        short = name[4:]   # RTB_OPT_LIGHTS -> OPT_LIGHTS
+        if hasattr(rtb, short):
+            assert getattr(rtb, short) == value, f"{name}: header {value}, binding {getattr(rtb, short)}"
+            checked += 1
+    assert checked >= 30, checked
+    for opt in ("OPT_FRAME_OVERLAP", "OPT_LIGHT_CACHE", "OPT_PRIMITIVE_TREES", "OPT_FRAME_GRAPH", "OPT_FRAME_LANES", "OPT_LIGHTS", "OPT_HISTORY_ALPHA"):
+        assert hasattr(rtb, opt), opt
