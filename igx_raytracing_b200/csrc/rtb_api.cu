@@ -110,14 +110,15 @@ struct rtb_ctx {
     // overlapped frame, so c->dirT etc. always are the latest frame's), so FRONT of frame k+1 runs while BACK of frame k drains:
     // the tails of the persistent launches are filled by the other stream's work.
     uint32_t overlapOpt = 1;
-    cudaStream_t frontStream = nullptr;
+    cudaStream_t frontStream = nullptr, midStream = nullptr;   // FRONT; shadow rays + occlusion when the frame runs in three stages
+    cudaEvent_t evMidDone[2] = {nullptr, nullptr};
     cudaEvent_t evFrontDone[2] = {nullptr, nullptr}, evBackDone[2] = {nullptr, nullptr}, evJoinF = nullptr, evJoinB = nullptr;
     bool backDoneSet[2] = {false, false};
     bool frontDirty = false;          // the front stream holds work the back stream has not been ordered after
     bool frontNeedsBack = true;       // the back stream holds work (uploads, direct passes) the front stream must be ordered after
     int setIndex = 0;                 // which physical set c->dirT etc. hold
     bool altAllocated = false;
-    struct FrameSet { DevBuf<float4> dirT, uvN; LaneBufs lane; DevBuf<PrimHit> primHitS, primHitC; } alt;
+    struct FrameSet { DevBuf<float4> dirT, uvN; LaneBufs lane; DevBuf<PrimHit> primHitS, primHitC; DevBuf<uint32_t> bits; } alt;
     DevBuf<SeedRec> seedSnap;         // [set]
     SeedRec* seedUse = nullptr;       // non-null while an overlapped frame is being recorded: the set's snapshot
     cudaGraphExec_t ovFront[2] = {nullptr, nullptr}, ovShadow[2] = {nullptr, nullptr}, ovShade[2] = {nullptr, nullptr};
@@ -192,7 +193,7 @@ uint32_t shadowWords(uint32_t w, uint32_t h, uint32_t samples) { return ((w + 15
 void releaseAlt(rtb_ctx* c);
 int allocFrame(rtb_ctx* c) {
     makeFrameMap(c);
-    if (c->frontStream) { RTB_CUDA(c, cudaStreamSynchronize(c->frontStream)); c->frontDirty = false; }
+    if (c->frontStream) { RTB_CUDA(c, cudaStreamSynchronize(c->frontStream)); RTB_CUDA(c, cudaStreamSynchronize(c->midStream)); c->frontDirty = false; }
     releaseAlt(c);   // the second set of FRONT -> BACK buffers (frame overlap) follows the frame size: reallocated when next needed
     const size_t px = (size_t)c->width * c->height;
     RTB_CUDA(c, c->dirT.alloc(px)); RTB_CUDA(c, c->uvN.alloc(px)); RTB_CUDA(c, c->accum.alloc(px));
@@ -415,8 +416,10 @@ int ensureShadowWords(rtb_ctx* c) {
     if (layers == c->bitsLayers && c->bits.p) return RTB_OK;
     const size_t words = shadowWords(c->width, c->height, layers);
     if (words > c->bits.count) {
+        if (c->frontStream) { RTB_CUDA(c, cudaStreamSynchronize(c->frontStream)); RTB_CUDA(c, cudaStreamSynchronize(c->midStream)); c->frontDirty = false; }
         RTB_CUDA(c, cudaStreamSynchronize(c->stream));
         RTB_CUDA(c, c->bits.alloc(words));
+        releaseAlt(c);   // the other set's shadow words are too small as well: reallocated when next needed
     }
     RTB_CUDA(c, cudaMemsetAsync(c->bits.p, 0, c->bits.bytes(), c->stream));
     c->bitsLayers = layers;
@@ -649,17 +652,20 @@ int overlapShade(rtb_ctx* c, bool) { return passShade(c, SHADE_BOTH); }
 void swapSets(rtb_ctx* c) {
     std::swap(c->dirT, c->alt.dirT); std::swap(c->uvN, c->alt.uvN); std::swap(c->lane[0], c->alt.lane);
     std::swap(c->primHitS[0], c->alt.primHitS); std::swap(c->primHitC[0], c->alt.primHitC);
+    std::swap(c->bits, c->alt.bits);
     c->setIndex ^= 1;
 }
 void releaseAlt(rtb_ctx* c) {
-    c->alt.dirT.release(); c->alt.uvN.release(); c->alt.lane.release(); c->alt.primHitS.release(); c->alt.primHitC.release();
+    c->alt.dirT.release(); c->alt.uvN.release(); c->alt.lane.release(); c->alt.primHitS.release(); c->alt.primHitC.release(); c->alt.bits.release();
     c->altAllocated = false;
     for (int k = 0; k < 2; ++k) c->ovStamp[k] = 0;
 }
 int prepareOverlap(rtb_ctx* c) {
     if (!c->frontStream) {
         RTB_CUDA(c, cudaStreamCreateWithFlags(&c->frontStream, cudaStreamNonBlocking));
+        RTB_CUDA(c, cudaStreamCreateWithFlags(&c->midStream, cudaStreamNonBlocking));
         for (int k = 0; k < 2; ++k) {
+            RTB_CUDA(c, cudaEventCreateWithFlags(&c->evMidDone[k], cudaEventDisableTiming));
             RTB_CUDA(c, cudaEventCreateWithFlags(&c->evFrontDone[k], cudaEventDisableTiming));
             RTB_CUDA(c, cudaEventCreateWithFlags(&c->evBackDone[k], cudaEventDisableTiming));
         }
@@ -673,6 +679,8 @@ int prepareOverlap(rtb_ctx* c) {
         RTB_CUDA(c, c->alt.lane.rays.alloc((size_t)c->fm.localSlots * (c->samples ? c->samples : 1)));
         RTB_CUDA(c, c->alt.lane.hits.alloc(c->fm.localSlots));
         RTB_CUDA(c, c->alt.lane.workCounter.alloc(1));
+        RTB_CUDA(c, c->alt.bits.alloc(c->bits.count));   // (the shadow words of a set: written by its shadow pass, read by its shade pass)
+        RTB_CUDA(c, cudaMemsetAsync(c->alt.bits.p, 0, c->alt.bits.bytes(), c->stream));
         RTB_CUDA(c, cudaMemsetAsync(c->alt.dirT.p, 0, c->alt.dirT.bytes(), c->stream));   // pixels of other ranks stay defined
         RTB_CUDA(c, cudaMemsetAsync(c->alt.uvN.p, 0, c->alt.uvN.bytes(), c->stream));
         RTB_CUDA(c, cudaMemsetAsync(c->alt.lane.workCounter.p, 0, 4, c->stream));
@@ -717,11 +725,18 @@ int overlappedFrame(rtb_ctx* c) {
     }
     RTB_CUDA(c, cudaGraphLaunch(c->ovFront[s], c->frontStream));
     RTB_CUDA(c, cudaEventRecord(c->evFrontDone[s], c->frontStream));
-    // BACK
-    RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evFrontDone[s], 0));
+    // MID: shadow rays + occlusion on a stream of their own (so that they run beside the shade launch of the frame before) unless the
+    // shadow and the shade pass share more than the set's shadow words (the tile light lists of RTB_OPT_LIGHTS); BACK: shade
+    const bool three = c->lightsOpt == 0u;
+    cudaStream_t ms = three ? c->midStream : c->stream;
+    RTB_CUDA(c, cudaStreamWaitEvent(ms, c->evFrontDone[s], 0));
     c->frontDirty = false;
-    if ((rc = waitCopy(c, {RTB_TGT_SHADOW_BITS}))) return rc;
-    RTB_CUDA(c, cudaGraphLaunch(c->ovShadow[s], c->stream));
+    if (c->copyTarget == RTB_TGT_SHADOW_BITS) { RTB_CUDA(c, cudaStreamWaitEvent(ms, c->evCopied, 0)); c->copyTarget = -1; }
+    RTB_CUDA(c, cudaGraphLaunch(c->ovShadow[s], ms));
+    if (three) {
+        RTB_CUDA(c, cudaEventRecord(c->evMidDone[s], ms));
+        RTB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evMidDone[s], 0));   // (and with it everything the front stream held)
+    }
     if ((rc = waitCopy(c, {RTB_TGT_LIGHTING, RTB_TGT_ACCUM, RTB_TGT_RGBA8, RTB_TGT_RGBA8_TILED}))) return rc;
     RTB_CUDA(c, cudaGraphLaunch(c->ovShade[s], c->stream));
     RTB_CUDA(c, cudaEventRecord(c->evBackDone[s], c->stream));
@@ -776,6 +791,7 @@ void rtb_destroy(rtb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->frontStream) cudaStreamSynchronize(c->frontStream);
+    if (c->midStream) cudaStreamSynchronize(c->midStream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
     for (int k = 0; k < 2; ++k) {
@@ -783,12 +799,14 @@ void rtb_destroy(rtb_ctx* c) {
         if (c->ovShadow[k]) cudaGraphExecDestroy(c->ovShadow[k]);
         if (c->ovShade[k]) cudaGraphExecDestroy(c->ovShade[k]);
         if (c->evFrontDone[k]) cudaEventDestroy(c->evFrontDone[k]);
+        if (c->evMidDone[k]) cudaEventDestroy(c->evMidDone[k]);
         if (c->evBackDone[k]) cudaEventDestroy(c->evBackDone[k]);
     }
     if (c->evJoinF) cudaEventDestroy(c->evJoinF);
     if (c->evJoinB) cudaEventDestroy(c->evJoinB);
     if (c->frontStream) cudaStreamDestroy(c->frontStream);
-    c->alt.dirT.release(); c->alt.uvN.release(); c->alt.lane.release(); c->alt.primHitS.release(); c->alt.primHitC.release(); c->seedSnap.release();
+    if (c->midStream) cudaStreamDestroy(c->midStream);
+    c->alt.dirT.release(); c->alt.uvN.release(); c->alt.lane.release(); c->alt.primHitS.release(); c->alt.primHitC.release(); c->alt.bits.release(); c->seedSnap.release();
     if (c->evReady) cudaEventDestroy(c->evReady);
     if (c->evCopied) cudaEventDestroy(c->evCopied);
     c->triangles.release(); c->spheres.release(); c->cubes.release(); c->planes.release(); c->lights.release(); c->materials.release();
@@ -1231,7 +1249,7 @@ int rtb_probe_l2_read_gbs(rtb_ctx* c, size_t bytes, double* outGbs) {
 int rtb_sync(rtb_ctx* c) {
     if (!c) return RTB_ERR_ARG;
     RTB_BIND(c);
-    if (c->frontStream) RTB_CUDA(c, cudaStreamSynchronize(c->frontStream));
+    if (c->frontStream) { RTB_CUDA(c, cudaStreamSynchronize(c->frontStream)); RTB_CUDA(c, cudaStreamSynchronize(c->midStream)); }
     RTB_CUDA(c, cudaStreamSynchronize(c->stream));   // (a frame in lanes has joined the lane stream back into this one)
     if (c->copyStream) RTB_CUDA(c, cudaStreamSynchronize(c->copyStream));
     return RTB_OK;
