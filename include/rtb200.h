@@ -151,7 +151,8 @@ typedef enum rtb_option {
                                       the traversal stack. */
     RTB_OPT_FRAME_OVERLAP = 13,    /* default 1: recorded frames (RTB_OPT_FRAME_GRAPH) of consecutive RTB_PASS_FRAME dispatches overlap — init +
                                       camera rays + nearest hit + G-buffer of frame k+1 run on a second stream while shadow rays, lighting
-                                      and composite of frame k drain, on two sets of the buffers the first half hands to the second (the
+                                      and composite of frame k drain (shadow rays + occlusion on a third stream beside the shade launch before
+                                      them), on two sets of the buffers one stage hands to the next (shadow words and the
                                       Seed as init.comp left it included).  Same launches, same pixels; the tails of the persistent
                                       launches are filled (one rank of eight: 0.65 -> 0.57 ms per 4K soup frame).  Everything else the
                                       API offers is ordered after both streams; pointers from rtb_device_ptr(DIR_T / UV_NORMAL) name the
