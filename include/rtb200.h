@@ -155,8 +155,8 @@ typedef enum rtb_option {
                                       them), on two sets of the buffers one stage hands to the next (shadow words and the
                                       Seed as init.comp left it included).  Same launches, same pixels; the tails of the persistent
                                       launches are filled (one rank of eight: 0.65 -> 0.57 ms per 4K soup frame).  Everything else the
-                                      API offers is ordered after both streams; pointers from rtb_device_ptr(DIR_T / UV_NORMAL) name the
-                                      latest frame's set and are valid until the next RTB_PASS_FRAME.  0: one frame after the other. */
+                                      API offers is ordered after all of them; pointers from rtb_device_ptr(DIR_T / UV_NORMAL / SHADOW_BITS)
+                                      name the latest frame's set and are valid until the next RTB_PASS_FRAME (or rtb_path_frame).  0: one frame after the other. */
     RTB_OPT_LIGHT_CACHE = 14,      /* default 1: the random pair lighting.comp derives per pixel and shadow sample depends on the pixel, the
                                       sample index and the sample count only (its Seed block is unbound: it reads zeros), so it — and for a
                                       directional light 0 the light direction it yields — is computed once per frame size (and light 0) and
