@@ -86,7 +86,8 @@ typedef enum rtb_target {
  * primitive (ref: res/shaders/trace.glsl:25-45,78-94).  BVH is new and returns the same hits. */
 typedef enum rtb_accel_mode {
     RTB_ACCEL_BRUTE = 0,   /* the reference algorithm, verbatim, on the GPU */
-    RTB_ACCEL_BVH = 1,     /* triangles through the 8-wide compressed BVH (128-byte nodes); spheres, cubes, planes stay linear */
+    RTB_ACCEL_BVH = 1,     /* triangles through the 8-wide compressed BVH (128-byte nodes); spheres and cubes through trees of their own from
+                              RTB_OPT_PRIMITIVE_TREES primitives of a type on, in the reference's loops below that; planes stay linear */
     RTB_ACCEL_BVH2 = 2     /* triangles through the binary BVH (64-byte two-box nodes): the first-generation kernel, kept for comparison */
 } rtb_accel_mode;
 
