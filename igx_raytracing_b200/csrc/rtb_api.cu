@@ -934,8 +934,8 @@ int rtb_upload(rtb_ctx* c, rtb_buffer id, size_t off, size_t bytes, const void* 
         }
         case RTB_BUF_SHADOW_PROPS:
             if (off > 4 || bytes > 4 - off) return fail(c, RTB_ERR_CAPACITY, "shadow properties upload past 4 bytes");
+            if (std::memcmp(reinterpret_cast<uint8_t*>(&c->shadowSamplesProp) + off, src, bytes)) ++c->stamp;   // (the facade flushes it every frame)
             std::memcpy(reinterpret_cast<uint8_t*>(&c->shadowSamplesProp) + off, src, bytes);
-            ++c->stamp;
             if (c->width && c->shadowSamplesProp != c->samples) return rtb_resize(c, c->width, c->height, c->shadowSamplesProp);
             return RTB_OK;
         case RTB_BUF_SEED: dst = c->seed.p; cap = sizeof(SeedRec); break;

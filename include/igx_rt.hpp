@@ -220,14 +220,47 @@ private:
 // What the reference calls a CommandList: the ordered list of GPU actions one frame replays
 // (ref: IGNIS/include/graphics/command/command_list.hpp).  Here a command is a call into the C ABI.
 class CommandList {
-    List<std::function<int(rtb_ctx*)>> cmds;
 public:
-    void add(std::function<int(rtb_ctx*)> c) { cmds.push_back(std::move(c)); }
+    // what a recorded command is, as far as replay needs to know: the five dispatches of the reference's frame and the shadow
+    // properties flush are recognised, everything else (uploads, builds, a user's pass) is opaque
+    enum class Kind : u8 { OTHER, INIT, RAYGEN, SHADOW_PROPS, SHADOW, LIGHTING, COMPOSITE };
+private:
+    struct Cmd { std::function<int(rtb_ctx*)> run; Kind kind; };
+    List<Cmd> cmds;
+public:
+    // The reference's frame is INIT, RAYGEN, FlushBuffer(shadow properties), SHADOW, LIGHTING, COMPOSITE, recorded by three tasks
+    // (composite_task.cpp:249-277, raygen_task.cpp:88-94, shadow_task.cpp:189-210).  Replayed as ONE RTB_PASS_FRAME when the six stand
+    // together — same kernels' arithmetic, same targets (tests/test_gpu_parity.py: per-pass dispatches == RTB_PASS_FRAME), but the
+    // library may then fuse lighting + composite, record the frame as CUDA graphs and overlap consecutive frames.  A pass injected
+    // between them (addPrepass / addPostpass record before / after the run, never inside) keeps the per-pass dispatches.
+    bool fuseFrame = true;
+    void add(std::function<int(rtb_ctx*)> c, Kind k = Kind::OTHER) { cmds.push_back(Cmd{std::move(c), k}); }
+    void addDispatch(rtb_pass pass) {
+        static constexpr Kind kinds[5] = {Kind::INIT, Kind::RAYGEN, Kind::SHADOW, Kind::LIGHTING, Kind::COMPOSITE};
+        add([pass](rtb_ctx* c) { return rtb_dispatch(c, pass); }, pass <= RTB_PASS_COMPOSITE ? kinds[pass] : Kind::OTHER);
+    }
     void clear() { cmds.clear(); }
     bool empty() const { return cmds.empty(); }
     usz size() const { return cmds.size(); }
     // Graphics::execute: replay in order; the first failing command stops the list and is returned
-    int execute(rtb_ctx* ctx) const { for (auto& c : cmds) { const int rc = c(ctx); if (rc) return rc; } return 0; }
+    int execute(rtb_ctx* ctx) const {
+        static constexpr Kind frame[6] = {Kind::INIT, Kind::RAYGEN, Kind::SHADOW_PROPS, Kind::SHADOW, Kind::LIGHTING, Kind::COMPOSITE};
+        for (usz i = 0; i < cmds.size();) {
+            bool whole = fuseFrame && i + 6 <= cmds.size();
+            for (usz k = 0; whole && k < 6; ++k) whole = cmds[i + k].kind == frame[k];
+            if (whole) {
+                int rc = cmds[i + 2].run(ctx);                         // the properties flush (a no-op unless the sample count changed) ...
+                if (!rc) rc = rtb_dispatch(ctx, RTB_PASS_FRAME);       // ... then the five dispatches as one
+                if (rc) return rc;
+                i += 6;
+                continue;
+            }
+            const int rc = cmds[i].run(ctx);
+            if (rc) return rc;
+            ++i;
+        }
+        return 0;
+    }
 };
 
 class SceneGraph {
@@ -558,7 +591,7 @@ struct CPUCamera : public Camera {   // include/rt/structs.hpp:16-39, src/rt/str
 class RaygenTask : public RenderTask {
 public:
     explicit RaygenTask(Device& d) : RenderTask(d) {}
-    void prepareCommandList(CommandList* cl) override { cl->add([](rtb_ctx* c) { return rtb_dispatch(c, RTB_PASS_RAYGEN); }); dirty = false; }
+    void prepareCommandList(CommandList* cl) override { cl->addDispatch(RTB_PASS_RAYGEN); dirty = false; }
     void update(f64) override {}
 };
 
@@ -574,9 +607,9 @@ public:
     void prepareCommandList(CommandList* cl) override {
         cachedSamples = properties.Shadow_samples;
         const u32 samples = cachedSamples;
-        cl->add([samples](rtb_ctx* c) { return rtb_upload(c, RTB_BUF_SHADOW_PROPS, 0, 4, &samples); });   // FlushBuffer(shadowProperties)
-        cl->add([](rtb_ctx* c) { return rtb_dispatch(c, RTB_PASS_SHADOW); });
-        cl->add([](rtb_ctx* c) { return rtb_dispatch(c, RTB_PASS_LIGHTING); });
+        cl->add([samples](rtb_ctx* c) { return rtb_upload(c, RTB_BUF_SHADOW_PROPS, 0, 4, &samples); }, CommandList::Kind::SHADOW_PROPS);   // FlushBuffer(shadowProperties)
+        cl->addDispatch(RTB_PASS_SHADOW);
+        cl->addDispatch(RTB_PASS_LIGHTING);
         dirty = false;
     }
     void update(f64) override {}
@@ -618,10 +651,10 @@ public:
     }
     // composite_task.cpp:249-277: FlushBuffer(seed), init, children, composite
     void prepareCommandList(CommandList* cl) override {
-        cl->add([](rtb_ctx* c) { return rtb_dispatch(c, RTB_PASS_INIT); });
+        cl->addDispatch(RTB_PASS_INIT);
         raygen.prepareCommandList(cl);
         shadow.prepareCommandList(cl);
-        cl->add([](rtb_ctx* c) { return rtb_dispatch(c, RTB_PASS_COMPOSITE); });
+        cl->addDispatch(RTB_PASS_COMPOSITE);
         dirty = false;
     }
 };

@@ -956,3 +956,33 @@ def test_light_cache_does_not_change_a_bit(rtb, sky, case):
         for a, b in zip(outs[1][step], outs[0][step]):
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"{case}, step {step}: the cache changed a target"
     assert not np.array_equal(outs[1][0][0].view(np.uint8), outs[1][1][0].view(np.uint8)), "the new first light must change the lighting"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("release", [0, 1])
+def test_per_pass_dispatches_equal_the_frame_pass(rtb, sky, release):
+    """The reference records INIT, RAYGEN, SHADOW, LIGHTING, COMPOSITE as five dispatches; RTB_PASS_FRAME is the same five with
+    lighting + composite fused, recorded and overlapped.  Five accumulating frames either way (the C++ facade replays its command
+    list through RTB_PASS_FRAME when the five stand together): every target identical."""
+    w, h = 300, 170
+    scene = rtb.niels_scene(0.6)
+    outs = []
+    for per_pass in (True, False):
+        ctx = rtb.Context()
+        ctx.set_option(rtb.OPT_SHADER_BUILD, release)
+        ctx.resize(w, h, 2)
+        ctx.upload_scene(scene, sky)
+        ctx.build_accel(rtb.ACCEL_BVH)
+        ctx.upload(rtb.BUF_CAMERA, rtb.pack_camera(w, h, eye=(6, 5, 12), flags=2))
+        ctx.upload(rtb.BUF_SEED, rtb.make_seed((8.0, 3.0)))
+        for _ in range(5):
+            if per_pass:
+                for p in (rtb.PASS_INIT, rtb.PASS_RAYGEN, rtb.PASS_SHADOW, rtb.PASS_LIGHTING, rtb.PASS_COMPOSITE):
+                    ctx.dispatch(p)
+            else:
+                ctx.upload(rtb.BUF_SHADOW_PROPS, np.array([2], np.uint32))   # what the facade flushes before every frame: no re-recording
+                ctx.dispatch(rtb.PASS_FRAME)
+        outs.append([ctx.readback(t).copy() for t in (rtb.TGT_DIR_T, rtb.TGT_UV_NORMAL, rtb.TGT_SHADOW_BITS, rtb.TGT_LIGHTING, rtb.TGT_ACCUM, rtb.TGT_RGBA8, rtb.TGT_SEED)])
+        ctx.close()
+    for i, (a, b) in enumerate(zip(*outs)):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"target {i} differs between five dispatches and RTB_PASS_FRAME"
